@@ -1,0 +1,89 @@
+"""Seeded weights and synthetic image pairs (no network, no checkpoints).
+
+The reference's pretrained checkpoint cannot be downloaded offline
+(pretrained/download.sh), so parity and throughput are measured on seeded
+random weights that carry the reference's ``state_dict`` key names and shapes
+(names probed from networks/patch2pix.py:13-61,
+networks/modules.py:56-99, networks/ncn/conv4d.py:118-120,
+networks/resnet.py:96-123).  BatchNorm running statistics / affines and all
+biases are randomised (a default-initialised BN is the identity and would hide
+folding bugs) and the running variances are calibrated so that activations
+stay O(1) through the regressor, like a trained network's.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+_LAYERS = (('layer1', 3, 64), ('layer2', 4, 128), ('layer3', 6, 256))
+
+
+def _xavier(gen, *shape, fan_in=None, fan_out=None):
+    rf = 1
+    for s in shape[2:]:
+        rf *= s
+    fan_in = fan_in if fan_in is not None else shape[1] * rf
+    fan_out = fan_out if fan_out is not None else shape[0] * rf
+    bound = math.sqrt(6.0 / (fan_in + fan_out))
+    return (torch.rand(*shape, generator=gen) * 2 - 1) * bound
+
+
+def _bn(sd, gen, name, c, var):
+    sd[name + '.weight'] = 0.8 + 0.4 * torch.rand(c, generator=gen)
+    sd[name + '.bias'] = 0.1 * torch.randn(c, generator=gen)
+    sd[name + '.running_mean'] = 0.1 * math.sqrt(var) * torch.randn(c, generator=gen)
+    sd[name + '.running_var'] = var * (0.7 + 0.6 * torch.rand(c, generator=gen))
+
+
+def make_seeded_state_dict(seed=0, backbone=True, regressors=True):
+    """Flat fp32 dict with the reference's state_dict names (layer4 / num_batches_tracked omitted)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    if backbone:
+        sd['extract.conv1.weight'] = _xavier(g, 64, 3, 7, 7)
+        _bn(sd, g, 'extract.bn1', 64, 1.0)
+        cin = 64
+        for lname, nblk, c in _LAYERS:
+            for i in range(nblk):
+                p = f'extract.{lname}.{i}'
+                sd[p + '.conv1.weight'] = _xavier(g, c, cin if i == 0 else c, 3, 3)
+                _bn(sd, g, p + '.bn1', c, 1.0)
+                sd[p + '.conv2.weight'] = _xavier(g, c, c, 3, 3)
+                _bn(sd, g, p + '.bn2', c, 1.0)
+                if i == 0 and cin != c:
+                    sd[p + '.downsample.0.weight'] = _xavier(g, c, cin, 1, 1)
+                    _bn(sd, g, p + '.downsample.1', c, 1.0)
+            cin = c
+    # NCNet: Conv4d weights are stored pre-permuted [k1, Cout, Cin, k2, k3, k4]
+    sd['ncn.conv.0.weight'] = (torch.rand(3, 16, 1, 3, 3, 3, generator=g) * 2 - 1) * 0.1
+    sd['ncn.conv.0.bias'] = 0.01 * torch.randn(16, generator=g)
+    sd['ncn.conv.2.weight'] = (torch.rand(3, 1, 16, 3, 3, 3, generator=g) * 2 - 1) * 0.1
+    sd['ncn.conv.2.bias'] = 0.01 * torch.randn(1, generator=g)
+    if regressors:
+        for r in ('regress_mid', 'regress_fine'):
+            sd[f'{r}.conv.0.weight'] = _xavier(g, 512, 518, 3, 3)
+            _bn(sd, g, f'{r}.conv.1', 512, 0.0039)
+            sd[f'{r}.conv.2.weight'] = _xavier(g, 512, 512, 3, 3)
+            _bn(sd, g, f'{r}.conv.3', 512, 1.0)
+            sd[f'{r}.fc.0.weight'] = _xavier(g, 512, 512)
+            sd[f'{r}.fc.0.bias'] = 0.05 * torch.randn(512, generator=g)
+            _bn(sd, g, f'{r}.fc.1', 512, 4.0)
+            sd[f'{r}.fc.3.weight'] = _xavier(g, 256, 512)
+            sd[f'{r}.fc.3.bias'] = 0.05 * torch.randn(256, generator=g)
+            _bn(sd, g, f'{r}.fc.4', 256, 0.7)
+            sd[f'{r}.fc.6.weight'] = _xavier(g, 5, 256)
+            sd[f'{r}.fc.6.bias'] = 0.05 * torch.randn(5, generator=g)
+    return sd
+
+
+def synthetic_pair(pair_idx, height, width):
+    """Deterministic 'two views of one texture' pair: a low-frequency
+    random texture plus noise, cropped twice with an (8,-8) px shift so that some true
+    mutual matches exist.  Returns im1, im2 as [1,3,H,W] fp32 on CPU."""
+    g = torch.Generator().manual_seed(1000 + int(pair_idx))
+    low = torch.randn(1, 3, height // 8 + 4, width // 8 + 4, generator=g)
+    base = F.interpolate(low, size=(height + 32, width + 32), mode='bicubic', align_corners=False)
+    base = base + 0.3 * torch.randn(1, 3, height + 32, width + 32, generator=g)
+    im1 = base[:, :, 16:16 + height, 16:16 + width].contiguous()
+    im2 = base[:, :, 8:8 + height, 24:24 + width].contiguous()
+    return im1, im2

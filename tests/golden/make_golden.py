@@ -1,0 +1,139 @@
+"""Generate golden vectors by running the LIVE reference (/root/reference) on CPU.
+
+Run in the authoring container only (the reference does not travel to the GPU
+box):   python tests/golden/make_golden.py
+Writes tests/golden/*.npz.  The reference is imported unmodified except for the
+two import-time shims documented in SURVEY.md Appendix B (skip the ResNet
+checkpoint download; do not .cuda() the NC net on a CPU-only host).
+"""
+import os
+import sys
+import warnings
+from argparse import Namespace
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, '/root/reference')
+warnings.filterwarnings('ignore')
+
+import networks.resnet as resnet                                   # noqa: E402
+resnet.ResNet.load_pretrained_ = lambda self, ignore='fc': None     # shim 1
+import networks.ncn.model as ncm                                    # noqa: E402
+_orig_init = ncm.NeighConsensus.__init__
+ncm.NeighConsensus.__init__ = lambda self, use_cuda=True, **kw: _orig_init(self, use_cuda=False, **kw)  # shim 2
+from networks.patch2pix import Patch2Pix                            # noqa: E402
+from networks.modules import maxpool4d, L2Normalize                 # noqa: E402
+from networks.ncn.model import MutualMatching                       # noqa: E402
+from networks.utils import filter_coarse                            # noqa: E402
+
+from patch2pix_b200.synth import make_seeded_state_dict, synthetic_pair  # noqa: E402
+
+
+def build_ref(sd, panc):
+    cfg = Namespace(training=False, device='cpu', regr_batch=1200, backbone='ResNet34',
+                    feat_idx=[0, 1, 2, 3], weights_dict=sd, change_stride=True,
+                    regressor_config=Namespace(conv_dims=[512, 512], conv_kers=[3, 3], conv_strs=[2, 1],
+                                               fc_dims=[512, 256], feat_comb='pre', psize=[16, 16],
+                                               pshift=8, panc=panc, shared=False))
+    return Patch2Pix(cfg).eval()
+
+
+def np_(t):
+    return t.detach().cpu().numpy()
+
+
+def case_stages(net, name, pair_idx, H, W, ksize=2):
+    """predict_fine path with every intermediate of the coarse stage."""
+    im1, im2 = synthetic_pair(pair_idx, H, W)
+    out = {'pair_idx': pair_idx, 'H': H, 'W': W, 'ksize': ksize}
+    with torch.no_grad():
+        f1s, f2s = [], []
+        net.extract.forward_all(im1, f1s, early_feat=True)
+        net.extract.forward_all(im2, f2s, early_feat=True)
+        for lvl in (1, 2, 3, 4):
+            out[f'feat1_l{lvl}_sub'] = np_(f1s[lvl][0, ::7, ::3, ::3])   # sparse probe of the backbone
+        a = L2Normalize(f1s[-1], dim=1)
+        b = L2Normalize(f2s[-1], dim=1)
+        corr = net.combine(a, b)
+        pooled, mi, mj, mk, ml = maxpool4d(corr, k_size=ksize)
+        out['pooled'] = np_(pooled)
+        out['delta'] = np.stack([np_(mi), np_(mj), np_(mk), np_(ml)]).astype(np.int8)
+        m1 = MutualMatching(pooled)
+        out['mutual1'] = np_(m1)
+        nc = net.ncn(m1)
+        out['ncn'] = np_(nc)
+        corr4d, delta4d = net.forward_coarse_match(f1s[-1], f2s[-1], ksize=ksize)
+        out['corr4d'] = np_(corr4d)
+        cm, sc = net.cal_coarse_matches(corr4d, delta4d, ksize=ksize, upsample=net.upsample, center=True)
+        out['cand_matches'] = np_(cm)
+        out['cand_scores'] = np_(sc)
+        fm, fs = filter_coarse(cm, sc, 0.0, True)
+        out['mutual_matches'] = np_(fm[0])
+        out['mutual_scores'] = np_(fs[0])
+        fine, fine_p, mid, mid_p, coarse = net.predict_fine(im1, im2, ksize=ksize, return_all=True)
+        out['fine'] = np_(fine[0]).reshape(-1, 4)
+        out['fine_p'] = np_(fine_p[0]).reshape(-1)
+        out['mid'] = np_(mid[0]).reshape(-1, 4)
+        out['mid_p'] = np_(mid_p[0]).reshape(-1)
+        out['coarse'] = np_(coarse[0])
+        pc_m, pc_s = net.predict_coarse(im1, im2, ksize=ksize, ncn_thres=0.0, mutual=False)
+        out['predict_coarse_nomutual_matches'] = np_(pc_m[0])
+        out['predict_coarse_nomutual_scores'] = np_(pc_s[0])
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+    print(name, 'mutual', out['mutual_matches'].shape, 'fine', out['fine'].shape)
+
+
+def case_train_sequence(net8, name, pair_idx, H, W, ptmax, np_seed):
+    """train_patch2pix.py:97-118 forward sequence under eval()/no_grad (ptmax, panc=8)."""
+    im1, im2 = synthetic_pair(pair_idx, H, W)
+    out = {'pair_idx': pair_idx, 'H': H, 'W': W, 'ptmax': ptmax, 'np_seed': np_seed}
+    with torch.no_grad():
+        corr4d, delta4d, feats1, feats2 = net8.forward(im1, im2, ksize=2, return_feats=True)
+        cm, sc = net8.cal_coarse_matches(corr4d, delta4d, ksize=2, upsample=net8.upsample, center=True)
+        np.random.seed(np_seed)
+        cm, sc = filter_coarse(cm, sc, 0.0, True, ptmax=ptmax)
+        out['sampled'] = np_(cm[0])
+        out['sampled_scores'] = np_(sc[0])
+        cm = net8.shift_to_anchors(cm)
+        out['anchors'] = np_(cm[0])
+        mid, mid_p = net8.forward_fine_match(feats1, feats2, cm, psize=16, ptype='center', regressor=net8.regress_mid)
+        fine, fine_p = net8.forward_fine_match(feats1, feats2, mid, psize=16, ptype='center', regressor=net8.regress_fine)
+        out['mid'] = np_(mid[0])
+        out['mid_p'] = np_(mid_p[0])
+        out['fine'] = np_(fine[0])
+        out['fine_p'] = np_(fine_p[0])
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+    print(name, 'anchors', out['anchors'].shape)
+
+
+def case_refine_only(net, name, pair_idx, H, W, n):
+    """Patch2Pix.refine_matches with float coarse matches incl. border / out-of-range rows."""
+    im1, im2 = synthetic_pair(pair_idx, H, W)
+    g = torch.Generator().manual_seed(77)
+    cm = torch.rand(n, 4, generator=g) * torch.tensor([W, H, W, H]) * 1.1 - 0.05 * torch.tensor([W, H, W, H])
+    cm[0] = torch.tensor([0.0, 0.0, W - 1.0, H - 1.0])
+    cm[1] = torch.tensor([W + 3.0, -2.5, 7.999, 8.0])
+    with torch.no_grad():
+        refined, scores, coarse = net.refine_matches(im1, im2, cm.clone(), io_thres=0.0)
+        refined_t, scores_t, coarse_t = net.refine_matches(im1, im2, cm.clone(), io_thres=0.5)
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), pair_idx=pair_idx, H=H, W=W, coarse_in=np_(cm),
+                        refined=refined, scores=scores, coarse=coarse,
+                        refined_t=refined_t, scores_t=scores_t, coarse_t=coarse_t)
+    print(name, refined.shape, refined_t.shape)
+
+
+if __name__ == '__main__':
+    torch.manual_seed(0)
+    sd = make_seeded_state_dict(0)
+    net1 = build_ref(dict(sd), panc=1)
+    net8 = build_ref(dict(sd), panc=8)
+    missing = [k for k in net1.state_dict() if k not in sd and 'layer4' not in k and 'num_batches' not in k]
+    assert not missing, missing
+    case_stages(net1, 'stages_96x128', 3, 96, 128)
+    case_stages(net1, 'stages_128x96', 5, 128, 96)
+    case_train_sequence(net8, 'trainseq_96x128', 3, 96, 128, ptmax=12, np_seed=123)
+    case_refine_only(net1, 'refine_128x160', 9, 128, 160, 40)
