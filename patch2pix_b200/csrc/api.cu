@@ -1,0 +1,807 @@
+// C ABI of libp2p_b200.so (declared in include/p2p_b200.h): handle, weight packing, stage drivers.
+#include <math.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "../../include/p2p_b200.h"
+#include "kernels.h"
+#include "umma_gemm.h"
+
+namespace p2p {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+long long g_launch_count = 0;
+
+int Arena::reserve(size_t bytes) {
+  off = 0;
+  if (bytes <= cap) return 0;
+  if (base != nullptr) {
+    cudaDeviceSynchronize();
+    cudaFree(base);
+    base = nullptr;
+    cap = 0;
+  }
+  bytes = align_up(bytes + (bytes >> 3), 1 << 20);
+  if (cudaMalloc(&base, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    set_last_error("out of device memory reserving " + std::to_string(bytes >> 20) + " MiB of scratch");
+    return -3;
+  }
+  cap = bytes;
+  return 0;
+}
+void Arena::release() {
+  if (base != nullptr) cudaFree(base);
+  base = nullptr;
+  cap = off = 0;
+}
+
+struct Regressor {
+  bool set = false;
+  __half *w1_hi = nullptr, *w1_lo = nullptr;  // [512][73*64]
+  __half *w2_hi = nullptr, *w2_lo = nullptr;  // [512][72*64]
+  float *scale1 = nullptr, *bias1 = nullptr, *scale2 = nullptr, *bias2 = nullptr;
+  float y_scale = 1.f;
+  FcWeights fc = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  KStep steps1[kConv1Steps];
+  KStep steps2[kConv2Steps];
+  KStep *d_steps1 = nullptr, *d_steps2 = nullptr;
+  char* blob = nullptr;  // one allocation backing all of the above
+};
+
+}  // namespace p2p
+
+using namespace p2p;
+
+struct p2p_handle_s {
+  int device = 0;
+  int num_sms = 148;
+  int opt_mid_passes = 3, opt_fine_passes = 1, opt_corr_passes = 0, opt_seg_len = 3, opt_gemm_impl = 0, opt_num_sms = 0;
+  bool nc_set = false;
+  float *nc_w1p = nullptr, *nc_b1p = nullptr, *nc_w2p = nullptr;
+  float nc_b2 = 0.f;
+  Regressor reg[2];
+  Arena coarse, refine, feat, misc;
+  PairFeatures pf[2];
+  bool prepared = false;
+  // optional per-kernel CUDA-event profile (p2p_set_option("profile", 1))
+  int opt_profile = 0;
+  struct ProfEntry { cudaEvent_t a, b; int kind; };
+  std::vector<ProfEntry> prof;
+  std::vector<cudaEvent_t> event_pool;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) ok = false;
+    if (ok && prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+#define P2P_ENTER(h)                                                  \
+  P2P_REQUIRE((h) != nullptr, "null handle");                         \
+  DeviceGuard _guard((h)->device);                                    \
+  if (!_guard.ok) {                                                   \
+    set_last_error("cannot select CUDA device of the handle");        \
+    return -2;                                                        \
+  }
+
+float pow2_floor_scale(float maxabs, float target_hi) {
+  // power of two s such that maxabs * s lies in [target_hi/2, target_hi)
+  if (!(maxabs > 0.f) || !isfinite(maxabs)) return 1.f;
+  int e;
+  frexpf(maxabs, &e);  // maxabs = m * 2^e, m in [0.5,1)
+  int et;
+  frexpf(target_hi, &et);
+  return ldexpf(1.f, et - 1 - e);
+}
+
+void split_half(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+
+template <typename T>
+T* carve(char*& p, size_t count) {
+  T* r = reinterpret_cast<T*>(p);
+  p += align_up(count * sizeof(T), 256);
+  return r;
+}
+
+void fold_bn(const p2p_bn_t& bn, int n, float eps, std::vector<float>& g, std::vector<float>& b) {
+  g.resize(n);
+  b.resize(n);
+  for (int i = 0; i < n; ++i) {
+    g[i] = bn.weight[i] / sqrtf(bn.running_var[i] + eps);
+    b[i] = bn.bias[i] - bn.running_mean[i] * g[i];
+  }
+}
+
+int tap_plane(int t, int& start) {  // conv1 tap -> (parity plane bit, box start)
+  if (t == 0) { start = -1; return 0; }
+  if (t == 1) { start = 0; return 1; }
+  start = 0;
+  return 0;
+}
+
+int pack_regressor(p2p_handle_s* h, Regressor& R, const p2p_regressor_weights_t& w) {
+  const int K1 = kConv1Steps * 64, K2 = kConv2Steps * 64;
+  std::vector<float> g1, b1, g2, b2, gf1, bf1, gf2, bf2;
+  fold_bn(w.conv1_bn, 512, w.bn_eps, g1, b1);
+  fold_bn(w.conv3_bn, 512, w.bn_eps, g2, b2);
+  fold_bn(w.fc1_bn, 512, w.bn_eps, gf1, bf1);
+  fold_bn(w.fc4_bn, 256, w.bn_eps, gf2, bf2);
+
+  std::vector<__half> w1h((size_t)512 * K1), w1l((size_t)512 * K1), w2h((size_t)512 * K2), w2l((size_t)512 * K2);
+  std::vector<float> sc1(512), sc2(512), bi1(b1), bi2(b2);
+  float max_bound = 0.f;
+  std::vector<float> sw1(512), sw2(512);
+  for (int o = 0; o < 512; ++o) {
+    const float* wo = w.conv0_weight + (size_t)o * 518 * 9;
+    float m = 0.f;
+    double tapn[9] = {0};
+    for (int c = 0; c < 518; ++c)
+      for (int t = 0; t < 9; ++t) {
+        const float v = wo[c * 9 + t] * g1[o];
+        m = fmaxf(m, fabsf(v));
+        tapn[t] += (double)v * v;
+      }
+    float bound = fabsf(b1[o]);
+    for (int t = 0; t < 9; ++t) bound += 1.41421357f * (float)sqrt(tapn[t]);
+    max_bound = fmaxf(max_bound, bound);
+    sw1[o] = pow2_floor_scale(m, 1024.f);
+    sc1[o] = 1.f / (kActScale * sw1[o]);
+    __half* dh = w1h.data() + (size_t)o * K1;
+    __half* dl = w1l.data() + (size_t)o * K1;
+    for (int s = 0; s < 72; ++s) {
+      const int tap = s / 8, chunk = s % 8;
+      for (int kk = 0; kk < 64; ++kk) {
+        const int c512 = chunk * 64 + kk;
+        const int orig = (c512 / 256) * 259 + 3 + (c512 % 256);
+        split_half(wo[orig * 9 + tap] * g1[o] * sw1[o], dh[s * 64 + kk], dl[s * 64 + kk]);
+      }
+    }
+    for (int kk = 0; kk < 64; ++kk) {
+      float v = 0.f;
+      if (kk < 54) {
+        const int tap = kk / 6, r = kk % 6;
+        const int orig = (r / 3) * 259 + (r % 3);
+        v = wo[orig * 9 + tap] * g1[o] * sw1[o];
+      }
+      split_half(v, dh[72 * 64 + kk], dl[72 * 64 + kk]);
+    }
+  }
+  R.y_scale = pow2_floor_scale(max_bound, 32768.f);
+  for (int o = 0; o < 512; ++o) {
+    const float* wo = w.conv2_weight + (size_t)o * 512 * 9;
+    float m = 0.f;
+    for (int i = 0; i < 512 * 9; ++i) m = fmaxf(m, fabsf(wo[i] * g2[o]));
+    sw2[o] = pow2_floor_scale(m, 1024.f);
+    sc2[o] = 1.f / (R.y_scale * sw2[o]);
+    __half* dh = w2h.data() + (size_t)o * K2;
+    __half* dl = w2l.data() + (size_t)o * K2;
+    for (int s = 0; s < 72; ++s) {
+      const int tap = s / 8, chunk = s % 8;
+      for (int kk = 0; kk < 64; ++kk)
+        split_half(wo[(chunk * 64 + kk) * 9 + tap] * g2[o] * sw2[o], dh[s * 64 + kk], dl[s * 64 + kk]);
+    }
+  }
+  // k-step plans
+  for (int s = 0; s < 72; ++s) {
+    const int tap = s / 8, chunk = s % 8, ty = tap / 3, tx = tap % 3;
+    int sx, sy;
+    const int px = tap_plane(tx, sx), py = tap_plane(ty, sy);
+    R.steps1[s] = KStep{(short)(chunk * 64), (signed char)sx, (signed char)sy, (signed char)(py * 2 + px), 0, 0, s * 64};
+    R.steps2[s] = KStep{(short)(chunk * 64), (signed char)(tx - 1), (signed char)(ty - 1), 0, 0, 0, s * 64};
+  }
+  R.steps1[72] = KStep{0, 0, 0, 0, 1, 0, 72 * 64};
+  // FC (BN folded, transposed)
+  std::vector<float> f1t((size_t)512 * 512), f1b(512), f2t((size_t)512 * 256), f2b(256), f3t(256 * 5), f3b(5);
+  for (int o = 0; o < 512; ++o) {
+    for (int k = 0; k < 512; ++k) f1t[(size_t)k * 512 + o] = w.fc0_weight[(size_t)o * 512 + k] * gf1[o];
+    f1b[o] = w.fc0_bias[o] * gf1[o] + bf1[o];
+  }
+  for (int o = 0; o < 256; ++o) {
+    for (int k = 0; k < 512; ++k) f2t[(size_t)k * 256 + o] = w.fc3_weight[(size_t)o * 512 + k] * gf2[o];
+    f2b[o] = w.fc3_bias[o] * gf2[o] + bf2[o];
+  }
+  for (int o = 0; o < 5; ++o) {
+    for (int k = 0; k < 256; ++k) f3t[k * 5 + o] = w.fc6_weight[o * 256 + k];
+    f3b[o] = w.fc6_bias[o];
+  }
+  // device blob
+  const size_t total = 4 * align_up((size_t)512 * K1 * 2, 256) + 8 * 4096 + align_up(f1t.size() * 4, 256) +
+                       align_up(f2t.size() * 4, 256) + 8 * 8192 + 65536;
+  if (R.blob == nullptr) {
+    if (cudaMalloc(&R.blob, total) != cudaSuccess) {
+      cudaGetLastError();
+      set_last_error("out of device memory packing regressor weights");
+      return -3;
+    }
+  }
+  char* p = R.blob;
+  R.w1_hi = carve<__half>(p, (size_t)512 * K1);
+  R.w1_lo = carve<__half>(p, (size_t)512 * K1);
+  R.w2_hi = carve<__half>(p, (size_t)512 * K2);
+  R.w2_lo = carve<__half>(p, (size_t)512 * K2);
+  R.scale1 = carve<float>(p, 512);
+  R.bias1 = carve<float>(p, 512);
+  R.scale2 = carve<float>(p, 512);
+  R.bias2 = carve<float>(p, 512);
+  R.fc.w1t = carve<float>(p, f1t.size());
+  R.fc.b1 = carve<float>(p, 512);
+  R.fc.w2t = carve<float>(p, f2t.size());
+  R.fc.b2 = carve<float>(p, 256);
+  R.fc.w3t = carve<float>(p, f3t.size());
+  R.fc.b3 = carve<float>(p, 5);
+  R.d_steps1 = carve<KStep>(p, kConv1Steps);
+  R.d_steps2 = carve<KStep>(p, kConv2Steps);
+#define UP(dst, src, bytes) P2P_CUDA_OK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice))
+  UP(R.w1_hi, w1h.data(), w1h.size() * 2);
+  UP(R.w1_lo, w1l.data(), w1l.size() * 2);
+  UP(R.w2_hi, w2h.data(), w2h.size() * 2);
+  UP(R.w2_lo, w2l.data(), w2l.size() * 2);
+  UP(R.scale1, sc1.data(), 2048);
+  UP(R.bias1, bi1.data(), 2048);
+  UP(R.scale2, sc2.data(), 2048);
+  UP(R.bias2, bi2.data(), 2048);
+  UP(R.fc.w1t, f1t.data(), f1t.size() * 4);
+  UP(R.fc.b1, f1b.data(), 2048);
+  UP(R.fc.w2t, f2t.data(), f2t.size() * 4);
+  UP(R.fc.b2, f2b.data(), 1024);
+  UP(R.fc.w3t, f3t.data(), f3t.size() * 4);
+  UP(R.fc.b3, f3b.data(), 20);
+  UP(R.d_steps1, R.steps1, sizeof(R.steps1));
+  UP(R.d_steps2, R.steps2, sizeof(R.steps2));
+#undef UP
+  R.set = true;
+  (void)h;
+  return 0;
+}
+
+int sms(const p2p_handle_s* h) { return h->opt_num_sms > 0 ? h->opt_num_sms : h->num_sms; }
+
+// Brackets a group of launches with CUDA events on the launching stream when profiling is on.
+struct ProfScope {
+  p2p_handle_s* h;
+  cudaStream_t st;
+  cudaEvent_t a = nullptr, b = nullptr;
+  int kind;
+  static cudaEvent_t get(p2p_handle_s* h) {
+    if (!h->event_pool.empty()) {
+      cudaEvent_t e = h->event_pool.back();
+      h->event_pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+  ProfScope(p2p_handle_s* h_, int kind_, cudaStream_t st_) : h(h_), st(st_), kind(kind_) {
+    if (h->opt_profile) {
+      a = get(h);
+      b = get(h);
+      cudaEventRecord(a, st);
+    }
+  }
+  ~ProfScope() {
+    if (a != nullptr) {
+      cudaEventRecord(b, st);
+      h->prof.push_back({a, b, kind});
+    }
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* p2p_last_error(void) { return g_last_error.c_str(); }
+int p2p_version(void) { return 100; }
+
+int p2p_create(int device, p2p_handle_t* out) {
+  P2P_REQUIRE(out != nullptr, "out is null");
+  int ndev = 0;
+  P2P_CUDA_OK(cudaGetDeviceCount(&ndev));
+  P2P_REQUIRE(device >= 0 && device < ndev, "device index out of range");
+  cudaDeviceProp prop;
+  P2P_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_last_error(std::string("libp2p_b200 targets sm_100a (B200) only; device is sm_") + std::to_string(prop.major) +
+                   std::to_string(prop.minor));
+    return -2;
+  }
+  p2p_handle_s* h = new p2p_handle_s();
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  *out = h;
+  return 0;
+}
+
+int p2p_destroy(p2p_handle_t h) {
+  if (h == nullptr) return 0;
+  DeviceGuard g(h->device);
+  cudaDeviceSynchronize();
+  h->coarse.release();
+  h->refine.release();
+  h->feat.release();
+  h->misc.release();
+  for (auto& e : h->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  for (auto e : h->event_pool) cudaEventDestroy(e);
+  if (h->nc_w1p) cudaFree(h->nc_w1p);
+  for (int i = 0; i < 2; ++i)
+    if (h->reg[i].blob) cudaFree(h->reg[i].blob);
+  delete h;
+  return 0;
+}
+
+int p2p_set_ncn_weights(p2p_handle_t h, const float* w1, const float* b1, const float* w2, const float* b2) {
+  P2P_ENTER(h);
+  P2P_REQUIRE(w1 && b1 && w2 && b2, "null weight pointer");
+  // reference layout [k1][Cout][Cin][k2][k3][k4]; logical W[o][c][a][b][d][e] = weight[a][o][c][b][d][e]
+  std::vector<float> w1p(81 * 32), b1p(32), w2p(81 * 32);
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b)
+      for (int d = 0; d < 3; ++d)
+        for (int e = 0; e < 3; ++e) {
+          const int tap = ((a * 3 + b) * 3 + d) * 3 + e;
+          for (int c = 0; c < 16; ++c) {
+            // net 0: plain weights; net 1: (a,b) <-> (d,e) swapped (the "transposed" pass)
+            w1p[tap * 32 + c] = w1[((a * 16 + c) * 1 + 0) * 27 + (b * 3 + d) * 3 + e];
+            w1p[tap * 32 + 16 + c] = w1[((d * 16 + c) * 1 + 0) * 27 + (e * 3 + a) * 3 + b];
+            w2p[tap * 32 + c] = w2[((a * 1 + 0) * 16 + c) * 27 + (b * 3 + d) * 3 + e];
+            w2p[tap * 32 + 16 + c] = w2[((d * 1 + 0) * 16 + c) * 27 + (e * 3 + a) * 3 + b];
+          }
+        }
+  for (int c = 0; c < 16; ++c) b1p[c] = b1p[16 + c] = b1[c];
+  if (h->nc_w1p == nullptr) P2P_CUDA_OK(cudaMalloc(&h->nc_w1p, sizeof(float) * (81 * 32 * 2 + 32)));
+  h->nc_w2p = h->nc_w1p + 81 * 32;
+  h->nc_b1p = h->nc_w2p + 81 * 32;
+  P2P_CUDA_OK(cudaMemcpy(h->nc_w1p, w1p.data(), sizeof(float) * 81 * 32, cudaMemcpyHostToDevice));
+  P2P_CUDA_OK(cudaMemcpy(h->nc_w2p, w2p.data(), sizeof(float) * 81 * 32, cudaMemcpyHostToDevice));
+  P2P_CUDA_OK(cudaMemcpy(h->nc_b1p, b1p.data(), sizeof(float) * 32, cudaMemcpyHostToDevice));
+  h->nc_b2 = b2[0];
+  h->nc_set = true;
+  return 0;
+}
+
+int p2p_set_regressor_weights(p2p_handle_t h, int which, const p2p_regressor_weights_t* w) {
+  P2P_ENTER(h);
+  P2P_REQUIRE(which == 0 || which == 1, "which must be 0 (mid) or 1 (fine)");
+  P2P_REQUIRE(w != nullptr && w->conv0_weight && w->conv2_weight && w->fc0_weight && w->fc3_weight && w->fc6_weight,
+              "null weight pointer");
+  return pack_regressor(h, h->reg[which], *w);
+}
+
+static int* option_slot(p2p_handle_t h, const char* key) {
+  if (!strcmp(key, "mid_passes")) return &h->opt_mid_passes;
+  if (!strcmp(key, "fine_passes")) return &h->opt_fine_passes;
+  if (!strcmp(key, "corr_passes")) return &h->opt_corr_passes;
+  if (!strcmp(key, "seg_len")) return &h->opt_seg_len;
+  if (!strcmp(key, "gemm_impl")) return &h->opt_gemm_impl;
+  if (!strcmp(key, "num_sms")) return &h->opt_num_sms;
+  if (!strcmp(key, "profile")) return &h->opt_profile;
+  return nullptr;
+}
+
+int p2p_set_option(p2p_handle_t h, const char* key, int value) {
+  P2P_REQUIRE(h != nullptr && key != nullptr, "null argument");
+  int* s = option_slot(h, key);
+  P2P_REQUIRE(s != nullptr, std::string("unknown option ") + key);
+  if (s == &h->opt_mid_passes || s == &h->opt_fine_passes) P2P_REQUIRE(value == 1 || value == 3, "passes must be 1 or 3");
+  if (s == &h->opt_corr_passes) P2P_REQUIRE(value == 0 || value == 1 || value == 3, "corr_passes must be 0, 1 or 3");
+  P2P_REQUIRE(value >= 0, "option values are non-negative");
+  *s = value;
+  return 0;
+}
+
+int p2p_get_option(p2p_handle_t h, const char* key, int* value) {
+  P2P_REQUIRE(h != nullptr && key != nullptr && value != nullptr, "null argument");
+  int* s = option_slot(h, key);
+  P2P_REQUIRE(s != nullptr, std::string("unknown option ") + key);
+  *value = *s;
+  return 0;
+}
+
+int p2p_launch_count(p2p_handle_t h, long long* count) {
+  P2P_REQUIRE(h != nullptr && count != nullptr, "null argument");
+  *count = g_launch_count;
+  return 0;
+}
+
+int p2p_profile_read(p2p_handle_t h, float* ms_by_kind, int* count_by_kind, int nkinds) {
+  P2P_ENTER(h);
+  P2P_REQUIRE(ms_by_kind && count_by_kind && nkinds >= P2P_PROF_KINDS, "need room for P2P_PROF_KINDS entries");
+  for (int i = 0; i < nkinds; ++i) {
+    ms_by_kind[i] = 0.f;
+    count_by_kind[i] = 0;
+  }
+  for (auto& e : h->prof) {
+    P2P_CUDA_OK(cudaEventSynchronize(e.b));
+    float ms = 0.f;
+    P2P_CUDA_OK(cudaEventElapsedTime(&ms, e.a, e.b));
+    ms_by_kind[e.kind] += ms;
+    count_by_kind[e.kind] += 1;
+    h->event_pool.push_back(e.a);
+    h->event_pool.push_back(e.b);
+  }
+  h->prof.clear();
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// coarse
+// -------------------------------------------------------------------------------------------------
+static int corr_umma(p2p_handle_s* h, const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo,
+                     int C, int n1, int n2, int n1pad, int n2pad, int ksize, float* out, uint8_t* code,
+                     cudaStream_t st) {
+  UmmaGemmParams p;
+  memset(&p, 0, sizeof(p));
+  const uint64_t ad[5] = {(uint64_t)C, 1, 1, 1, (uint64_t)n1pad};
+  const uint64_t as[4] = {(uint64_t)C * 2, (uint64_t)C * 2, (uint64_t)C * 2, (uint64_t)C * 2};
+  const uint32_t ab[5] = {64, 1, 1, 1, 128};
+  const uint64_t bd[2] = {(uint64_t)C, (uint64_t)n2pad};
+  const uint64_t bs[1] = {(uint64_t)C * 2};
+  const uint32_t bb[2] = {64, 256};
+  int rc;
+  if ((rc = make_tmap_fp16(&p.a_main_hi, a_hi, 5, ad, as, ab))) return rc;
+  if ((rc = make_tmap_fp16(&p.b_hi, b_hi, 2, bd, bs, bb))) return rc;
+  if (h->opt_corr_passes == 3) {
+    if ((rc = make_tmap_fp16(&p.a_main_lo, a_lo, 5, ad, as, ab))) return rc;
+    if ((rc = make_tmap_fp16(&p.b_lo, b_lo, 2, bd, bs, bb))) return rc;
+  }
+  p.a_rgb_hi = p.a_main_hi;
+  p.a_rgb_lo = p.a_main_hi;
+  p.nsteps = C / 64;
+  for (int s = 0; s < p.nsteps; ++s) p.steps[s] = KStep{(short)(s * 64), 0, 0, 0, 0, 0, s * 64};
+  p.m_tiles = n1pad / 128;
+  p.n_tiles = n2pad / 256;
+  p.a_units_per_tile = 128;
+  p.seg_len = h->opt_seg_len > 0 ? 1 : 0;
+  p.epi.c = out;
+  p.epi.alpha = 1.f / (kActScale * kActScale);
+  if (ksize == 2) {
+    p.epi.code = code;
+    p.epi.np1 = n1 / 4;
+    p.epi.np2 = n2 / 4;
+    return launch_umma_gemm(p, EPI_CORR, h->opt_corr_passes, sms(h), st);
+  }
+  p.epi.ldc = n2;
+  p.epi.m_rows = n1;
+  p.epi.n_cols = n2;
+  return launch_umma_gemm(p, EPI_PLAIN, h->opt_corr_passes, sms(h), st);
+}
+
+int p2p_coarse(p2p_handle_t h, const float* feat1, const float* feat2, int c, int h1, int w1, int h2, int w2,
+               int ksize, float* corr4d_out, uint8_t* delta_code_out, float* pooled_out, float* ncn_out,
+               void* stream) {
+  P2P_ENTER(h);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  P2P_REQUIRE(h->nc_set, "p2p_set_ncn_weights has not been called");
+  P2P_REQUIRE(feat1 && feat2 && corr4d_out, "null tensor pointer");
+  P2P_REQUIRE(ksize == 1 || ksize == 2, "ksize must be 1 or 2");
+  P2P_REQUIRE(c > 0 && h1 > 0 && w1 > 0 && h2 > 0 && w2 > 0, "empty feature map");
+  if (ksize == 2) {
+    P2P_REQUIRE(h1 % 2 == 0 && w1 % 2 == 0 && h2 % 2 == 0 && w2 % 2 == 0, "ksize 2 needs even feature sizes");
+    P2P_REQUIRE(delta_code_out != nullptr, "delta_code_out is required for ksize 2");
+  }
+  const int n1 = h1 * w1, n2 = h2 * w2;
+  const int hA = h1 / ksize, wA = w1 / ksize, hB = h2 / ksize, wB = w2 / ksize;
+  const int nA = hA * wA, nB = hB * wB;
+  const size_t V = (size_t)nA * nB;
+  const bool tc = h->opt_corr_passes > 0;
+  if (tc) P2P_REQUIRE(c % 64 == 0 && c / 64 <= kMaxKSteps, "tensor-core correlation needs C % 64 == 0");
+  const int n1pad = (int)align_up(n1, 128), n2pad = (int)align_up(n2, 256);
+  size_t need = 4 * V * 4 + (size_t)nA * 32 * nB * 4 + (size_t)(nA + nB) * 8 + (1 << 16);
+  need += tc ? (size_t)(n1pad + n2pad) * c * 4 : (size_t)(n1 + n2) * c * 4;
+  int rc = h->coarse.reserve(need);
+  if (rc) return rc;
+  Arena& A = h->coarse;
+  float* pooled = pooled_out ? pooled_out : (float*)A.take(V * 4);
+  float* m1 = (float*)A.take(V * 4);
+  float* nc = ncn_out ? ncn_out : (float*)A.take(V * 4);
+  float* hidden = (float*)A.take((size_t)nA * 32 * nB * 4);
+  float* rowmax = (float*)A.take((size_t)nA * 4);
+  unsigned int* colmax = (unsigned int*)A.take((size_t)nB * 4);
+  if (tc) {
+    __half* a_hi = (__half*)A.take((size_t)n1pad * c * 2);
+    __half* a_lo = (__half*)A.take((size_t)n1pad * c * 2);
+    __half* b_hi = (__half*)A.take((size_t)n2pad * c * 2);
+    __half* b_lo = (__half*)A.take((size_t)n2pad * c * 2);
+    P2P_REQUIRE(a_hi && a_lo && b_hi && b_lo && hidden && colmax, "scratch carve failed");
+    const bool lo = h->opt_corr_passes == 3;
+    {
+      ProfScope ps(h, P2P_PROF_L2NORM, st);
+      if ((rc = launch_l2norm_perm_kmajor(feat1, a_hi, lo ? a_lo : nullptr, c, h1, w1, ksize, st))) return rc;
+      if ((rc = launch_l2norm_perm_kmajor(feat2, b_hi, lo ? b_lo : nullptr, c, h2, w2, ksize, st))) return rc;
+    }
+    ProfScope ps(h, P2P_PROF_CORR, st);
+    if ((rc = corr_umma(h, a_hi, a_lo, b_hi, b_lo, c, n1, n2, n1pad, n2pad, ksize, pooled, delta_code_out, st)))
+      return rc;
+  } else {
+    float* fa = (float*)A.take((size_t)n1 * c * 4);
+    float* fb = (float*)A.take((size_t)n2 * c * 4);
+    P2P_REQUIRE(fa && fb && hidden && colmax, "scratch carve failed");
+    {
+      ProfScope ps(h, P2P_PROF_L2NORM, st);
+      if ((rc = launch_l2norm_perm(feat1, fa, c, h1, w1, ksize, st))) return rc;
+      if ((rc = launch_l2norm_perm(feat2, fb, c, h2, w2, ksize, st))) return rc;
+    }
+    ProfScope ps(h, P2P_PROF_CORR, st);
+    if ((rc = launch_corr_pool_simt(fa, fb, c, n1, n2, ksize, pooled, delta_code_out, st))) return rc;
+  }
+  {
+    ProfScope ps(h, P2P_PROF_MUTUAL, st);
+    if ((rc = launch_mutual_matching(pooled, nA, nB, rowmax, colmax, m1, st))) return rc;
+  }
+  {
+    ProfScope ps(h, P2P_PROF_NC, st);
+    if ((rc = launch_neigh_consensus(m1, hA, wA, hB, wB, h->nc_w1p, h->nc_b1p, h->nc_w2p, h->nc_b2, hidden, nc, st)))
+      return rc;
+  }
+  ProfScope ps(h, P2P_PROF_MUTUAL, st);
+  if ((rc = launch_mutual_matching(nc, nA, nB, rowmax, colmax, corr4d_out, st))) return rc;
+  return 0;
+}
+
+int p2p_delta_unpack(p2p_handle_t h, const uint8_t* code, long long n, int ksize, int64_t* di, int64_t* dj,
+                     int64_t* dk, int64_t* dl, void* stream) {
+  P2P_ENTER(h);
+  P2P_REQUIRE(code && di && dj && dk && dl && n >= 0 && ksize >= 1 && ksize <= 3, "bad argument");
+  if (n == 0) return 0;
+  return launch_delta_unpack(code, (size_t)n, ksize, (long long*)di, (long long*)dj, (long long*)dk, (long long*)dl,
+                             reinterpret_cast<cudaStream_t>(stream));
+}
+
+int p2p_delta_pack(p2p_handle_t h, const int64_t* di, const int64_t* dj, const int64_t* dk, const int64_t* dl,
+                   long long n, int ksize, uint8_t* code, void* stream) {
+  P2P_ENTER(h);
+  P2P_REQUIRE(code && di && dj && dk && dl && n >= 0 && ksize >= 1 && ksize <= 3, "bad argument");
+  if (n == 0) return 0;
+  return launch_delta_pack((const long long*)di, (const long long*)dj, (const long long*)dk, (const long long*)dl,
+                           (size_t)n, ksize, code, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int p2p_mutual_matching(p2p_handle_t h, const float* in, int nA, int nB, float* out, void* stream) {
+  P2P_ENTER(h);
+  P2P_REQUIRE(in && out && nA > 0 && nB > 0, "bad argument");
+  int rc = h->misc.reserve((size_t)(nA + nB) * 4 + 4096);
+  if (rc) return rc;
+  float* rowmax = (float*)h->misc.take((size_t)nA * 4);
+  unsigned int* colmax = (unsigned int*)h->misc.take((size_t)nB * 4);
+  return launch_mutual_matching(in, nA, nB, rowmax, colmax, out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int p2p_neigh_consensus(p2p_handle_t h, const float* in, int hA, int wA, int hB, int wB, float* out, void* stream) {
+  P2P_ENTER(h);
+  P2P_REQUIRE(h->nc_set, "p2p_set_ncn_weights has not been called");
+  P2P_REQUIRE(in && out && hA > 0 && wA > 0 && hB > 0 && wB > 0, "bad argument");
+  const size_t hid = (size_t)hA * wA * 32 * hB * wB * 4;
+  int rc = h->misc.reserve(hid + 4096);
+  if (rc) return rc;
+  float* hidden = (float*)h->misc.take(hid);
+  return launch_neigh_consensus(in, hA, wA, hB, wB, h->nc_w1p, h->nc_b1p, h->nc_w2p, h->nc_b2, hidden, out,
+                                reinterpret_cast<cudaStream_t>(stream));
+}
+
+int p2p_proposals(p2p_handle_t h, const float* corr4d, const uint8_t* delta_code, int hA, int wA, int hB, int wB,
+                  int ksize, int upsample, int center, int do_softmax, int64_t* matches_out, float* scores_out,
+                  void* stream) {
+  P2P_ENTER(h);
+  P2P_REQUIRE(corr4d && matches_out && scores_out, "null tensor pointer");
+  P2P_REQUIRE(hA > 0 && wA > 0 && hB > 0 && wB > 0 && ksize >= 1 && ksize <= 3 && upsample > 0, "bad dims");
+  P2P_REQUIRE(ksize == 1 || delta_code != nullptr, "delta_code is required for ksize > 1");
+  ProfScope ps(h, P2P_PROF_PROPOSALS, reinterpret_cast<cudaStream_t>(stream));
+  return launch_proposals(corr4d, ksize > 1 ? delta_code : nullptr, hA, wA, hB, wB, ksize, upsample, center,
+                          do_softmax, (long long*)matches_out, scores_out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int p2p_unique_rows(p2p_handle_t h, const int64_t* rows, int n, int mutual, int32_t* ids_out, int32_t* count_out,
+                    void* stream) {
+  P2P_ENTER(h);
+  P2P_REQUIRE(rows && ids_out && count_out, "null tensor pointer");
+  ProfScope ps(h, P2P_PROF_PROPOSALS, reinterpret_cast<cudaStream_t>(stream));
+  return launch_unique_rows((const long long*)rows, n, mutual, ids_out, count_out,
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+
+// -------------------------------------------------------------------------------------------------
+// refine
+// -------------------------------------------------------------------------------------------------
+int p2p_refine_prepare(p2p_handle_t h, const float* const* feats1, const float* const* feats2, int H1, int W1,
+                       int H2, int W2, void* stream) {
+  P2P_ENTER(h);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  P2P_REQUIRE(feats1 && feats2, "null feature list");
+  for (int l = 0; l < 4; ++l) P2P_REQUIRE(feats1[l] && feats2[l], "null feature level");
+  P2P_REQUIRE(H1 >= 8 && W1 >= 8 && H2 >= 8 && W2 >= 8 && H1 % 8 == 0 && W1 % 8 == 0 && H2 % 8 == 0 && W2 % 8 == 0,
+              "image sizes must be positive multiples of 8");
+  const int Hs[2] = {H1, H2}, Ws[2] = {W1, W2};
+  size_t need = 1 << 16;
+  for (int s = 0; s < 2; ++s) {
+    const size_t px = (size_t)Hs[s] * Ws[s];
+    need += (px / 4 * 64 + px / 16 * 64 + px / 64 * 128) * 4 + (px + px / 4 + px / 16 + px / 64) * 4 + 16384;
+  }
+  int rc = h->feat.reserve(need);
+  if (rc) return rc;
+  const int chans[3] = {64, 64, 128};
+  for (int s = 0; s < 2; ++s) {
+    PairFeatures& pf = h->pf[s];
+    for (int l = 0; l < 4; ++l) {
+      const int ds = 1 << l;
+      pf.nsq[l] = (float*)h->feat.take((size_t)(Hs[s] / ds) * (Ws[s] / ds) * 4);
+      P2P_REQUIRE(pf.nsq[l] != nullptr, "scratch carve failed");
+    }
+    for (int l = 0; l < 3; ++l) {
+      const int ds = 2 << l;
+      pf.nhwc[l] = (float*)h->feat.take((size_t)(Hs[s] / ds) * (Ws[s] / ds) * chans[l] * 4);
+      P2P_REQUIRE(pf.nhwc[l] != nullptr, "scratch carve failed");
+    }
+    ProfScope ps(h, P2P_PROF_PREP, st);
+    if ((rc = launch_feature_prep(s == 0 ? feats1 : feats2, Hs[s], Ws[s], pf, st))) return rc;
+  }
+  h->prepared = true;
+  return 0;
+}
+
+int p2p_refine(p2p_handle_t h, int which, const void* matches_in, int is_float, int n, float* matches_out,
+               float* probs_out, void* stream) {
+  P2P_ENTER(h);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  P2P_REQUIRE(which == 0 || which == 1, "which must be 0 (mid) or 1 (fine)");
+  P2P_REQUIRE(h->reg[which].set, "p2p_set_regressor_weights has not been called for this regressor");
+  P2P_REQUIRE(h->prepared, "p2p_refine_prepare has not been called");
+  P2P_REQUIRE(n >= 0, "negative match count");
+  if (n == 0) return 0;
+  P2P_REQUIRE(matches_in && matches_out && probs_out, "null tensor pointer");
+  Regressor& R = h->reg[which];
+  const int passes = which == 0 ? h->opt_mid_passes : h->opt_fine_passes;
+  const bool lo = passes == 3;
+  const int npad = (int)align_up(n, 2);
+  const size_t pbytes = (size_t)npad * kPatchPos * kMainCh * 2, rbytes = (size_t)npad * 4096 * 2,
+               ybytes = (size_t)npad * 64 * 512 * 2, qbytes = (size_t)npad * 512 * 4;
+  int rc = h->refine.reserve(2 * (pbytes + rbytes + ybytes) + qbytes + (1 << 16));
+  if (rc) return rc;
+  Arena& A = h->refine;
+  __half* p_hi = (__half*)A.take(pbytes);
+  __half* p_lo = (__half*)A.take(pbytes);
+  __half* r_hi = (__half*)A.take(rbytes);
+  __half* r_lo = (__half*)A.take(rbytes);
+  __half* y_hi = (__half*)A.take(ybytes);
+  __half* y_lo = (__half*)A.take(ybytes);
+  float* pooled = (float*)A.take(qbytes);
+  P2P_REQUIRE(p_hi && p_lo && r_hi && r_lo && y_hi && y_lo && pooled, "scratch carve failed");
+  const int kb = which == 0 ? P2P_PROF_GATHER_MID : P2P_PROF_GATHER_FINE;  // gather, conv1, conv2, fc
+  {
+    ProfScope ps(h, kb, st);
+    if ((rc = launch_patch_gather(h->pf[0], h->pf[1], matches_in, is_float, n, p_hi, lo ? p_lo : nullptr, r_hi,
+                                  lo ? r_lo : nullptr, st)))
+      return rc;
+  }
+  if (h->opt_gemm_impl == 1) {
+    GemmOperands g1 = {p_hi, p_lo, r_hi, r_lo, R.w1_hi, R.w1_lo, 4, kConv1Steps * 64, n, passes, R.d_steps1, kConv1Steps};
+    ConvEpilogue e1 = {R.scale1, R.bias1, 0, R.y_scale, y_hi, lo ? y_lo : nullptr, nullptr};
+    {
+      ProfScope ps(h, kb + 1, st);
+      if ((rc = launch_conv_gemm_simt(g1, e1, st))) return rc;
+    }
+    ProfScope ps(h, kb + 2, st);
+    GemmOperands g2 = {y_hi, y_lo, nullptr, nullptr, R.w2_hi, R.w2_lo, 1, kConv2Steps * 64, n, passes, R.d_steps2, kConv2Steps};
+    ConvEpilogue e2 = {R.scale2, R.bias2, 1, 1.f, nullptr, nullptr, pooled};
+    if ((rc = launch_conv_gemm_simt(g2, e2, st))) return rc;
+  } else {
+    UmmaGemmParams p;
+    memset(&p, 0, sizeof(p));
+    const uint32_t abox[5] = {64, 8, 8, 1, 2};
+    const uint32_t bbox[2] = {64, 256};
+    {  // conv1
+      const uint64_t ad[5] = {512, 8, 8, 4, (uint64_t)npad};
+      const uint64_t as[4] = {1024, 8192, 65536, 262144};
+      const uint64_t rd[5] = {64, 8, 8, 1, (uint64_t)npad};
+      const uint64_t rs[4] = {128, 1024, 8192, 8192};
+      const uint64_t bd[2] = {(uint64_t)kConv1Steps * 64, 512};
+      const uint64_t bs[1] = {(uint64_t)kConv1Steps * 64 * 2};
+      if ((rc = make_tmap_fp16(&p.a_main_hi, p_hi, 5, ad, as, abox))) return rc;
+      if ((rc = make_tmap_fp16(&p.a_rgb_hi, r_hi, 5, rd, rs, abox))) return rc;
+      if ((rc = make_tmap_fp16(&p.b_hi, R.w1_hi, 2, bd, bs, bbox))) return rc;
+      if ((rc = make_tmap_fp16(&p.a_main_lo, lo ? p_lo : p_hi, 5, ad, as, abox))) return rc;
+      if ((rc = make_tmap_fp16(&p.a_rgb_lo, lo ? r_lo : r_hi, 5, rd, rs, abox))) return rc;
+      if ((rc = make_tmap_fp16(&p.b_lo, R.w1_lo, 2, bd, bs, bbox))) return rc;
+      p.nsteps = kConv1Steps;
+      memcpy(p.steps, R.steps1, sizeof(R.steps1));
+      p.m_tiles = npad / 2;
+      p.n_tiles = 2;
+      p.a_units_per_tile = 2;
+      p.seg_len = lo ? h->opt_seg_len : 0;
+      p.epi.scale = R.scale1;
+      p.epi.bias = R.bias1;
+      p.epi.y_scale = R.y_scale;
+      p.epi.y_hi = y_hi;
+      p.epi.y_lo = lo ? y_lo : nullptr;
+      p.epi.n_patches = n;
+      ProfScope ps(h, kb + 1, st);
+      if ((rc = launch_umma_gemm(p, EPI_CONV1, passes, sms(h), st))) return rc;
+    }
+    {  // conv2
+      const uint64_t ad[5] = {512, 8, 8, 1, (uint64_t)npad};
+      const uint64_t as[4] = {1024, 8192, 65536, 65536};
+      const uint64_t bd[2] = {(uint64_t)kConv2Steps * 64, 512};
+      const uint64_t bs[1] = {(uint64_t)kConv2Steps * 64 * 2};
+      if ((rc = make_tmap_fp16(&p.a_main_hi, y_hi, 5, ad, as, abox))) return rc;
+      if ((rc = make_tmap_fp16(&p.a_main_lo, lo ? y_lo : y_hi, 5, ad, as, abox))) return rc;
+      if ((rc = make_tmap_fp16(&p.b_hi, R.w2_hi, 2, bd, bs, bbox))) return rc;
+      if ((rc = make_tmap_fp16(&p.b_lo, R.w2_lo, 2, bd, bs, bbox))) return rc;
+      p.a_rgb_hi = p.a_main_hi;
+      p.a_rgb_lo = p.a_main_lo;
+      p.nsteps = kConv2Steps;
+      memcpy(p.steps, R.steps2, sizeof(R.steps2));
+      p.epi.scale = R.scale2;
+      p.epi.bias = R.bias2;
+      p.epi.pooled = pooled;
+      P2P_CUDA_OK(cudaMemsetAsync(pooled, 0, qbytes, st));
+      ProfScope ps(h, kb + 2, st);
+      if ((rc = launch_umma_gemm(p, EPI_CONV2, passes, sms(h), st))) return rc;
+    }
+  }
+  ProfScope ps(h, kb + 3, st);
+  return launch_fc_parse(pooled, R.fc, matches_in, is_float, n, h->pf[0].W, h->pf[0].H, h->pf[1].W, h->pf[1].H,
+                         matches_out, probs_out, st);
+}
+
+int p2p_test_gemm(p2p_handle_t h, const float* a, const float* b, float* c, int M, int N, int K, int passes,
+                  int seg_len, float in_scale, void* stream) {
+  P2P_ENTER(h);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  P2P_REQUIRE(a && b && c && M > 0 && N > 0 && K > 0, "bad argument");
+  P2P_REQUIRE(K % 64 == 0 && K / 64 <= kMaxKSteps, "K must be a multiple of 64 and at most 6144");
+  P2P_REQUIRE(passes == 1 || passes == 3, "passes must be 1 or 3");
+  const int mpad = (int)align_up(M, 128), npad = (int)align_up(N, 256);
+  const size_t ab = (size_t)mpad * K * 2, bb = (size_t)npad * K * 2;
+  int rc = h->misc.reserve(2 * (ab + bb) + (1 << 16));
+  if (rc) return rc;
+  __half* a_hi = (__half*)h->misc.take(ab);
+  __half* a_lo = (__half*)h->misc.take(ab);
+  __half* b_hi = (__half*)h->misc.take(bb);
+  __half* b_lo = (__half*)h->misc.take(bb);
+  P2P_CUDA_OK(cudaMemsetAsync(a_hi, 0, 2 * ab, st));
+  P2P_CUDA_OK(cudaMemsetAsync(b_hi, 0, 2 * bb, st));
+  if ((rc = launch_split_rows(a, a_hi, a_lo, (size_t)M * K, in_scale, st))) return rc;
+  if ((rc = launch_split_rows(b, b_hi, b_lo, (size_t)N * K, in_scale, st))) return rc;
+  UmmaGemmParams p;
+  memset(&p, 0, sizeof(p));
+  const uint64_t ad[5] = {(uint64_t)K, 1, 1, 1, (uint64_t)mpad};
+  const uint64_t as[4] = {(uint64_t)K * 2, (uint64_t)K * 2, (uint64_t)K * 2, (uint64_t)K * 2};
+  const uint32_t abx[5] = {64, 1, 1, 1, 128};
+  const uint64_t bd[2] = {(uint64_t)K, (uint64_t)npad};
+  const uint64_t bs[1] = {(uint64_t)K * 2};
+  const uint32_t bbx[2] = {64, 256};
+  if ((rc = make_tmap_fp16(&p.a_main_hi, a_hi, 5, ad, as, abx))) return rc;
+  if ((rc = make_tmap_fp16(&p.a_main_lo, a_lo, 5, ad, as, abx))) return rc;
+  if ((rc = make_tmap_fp16(&p.b_hi, b_hi, 2, bd, bs, bbx))) return rc;
+  if ((rc = make_tmap_fp16(&p.b_lo, b_lo, 2, bd, bs, bbx))) return rc;
+  p.a_rgb_hi = p.a_main_hi;
+  p.a_rgb_lo = p.a_main_lo;
+  p.nsteps = K / 64;
+  for (int s = 0; s < p.nsteps; ++s) p.steps[s] = KStep{(short)(s * 64), 0, 0, 0, 0, 0, s * 64};
+  p.m_tiles = mpad / 128;
+  p.n_tiles = npad / 256;
+  p.a_units_per_tile = 128;
+  p.seg_len = seg_len;
+  p.epi.c = c;
+  p.epi.ldc = N;
+  p.epi.m_rows = M;
+  p.epi.n_cols = N;
+  p.epi.alpha = 1.f / (in_scale * in_scale);
+  return launch_umma_gemm(p, EPI_PLAIN, passes, sms(h), st);
+}
+
+}  // extern "C"

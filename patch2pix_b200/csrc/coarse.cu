@@ -1,0 +1,682 @@
+// Coarse stage: L2-normalise -> 4D correlation (+4D max-pool) -> MutualMatching -> symmetric
+// 4D neighbourhood-consensus conv -> MutualMatching -> softmax/argmax proposals -> unique/mutual.
+//
+// Reference semantics (file:line relative to the reference repo):
+//   L2Normalize            networks/modules.py:6
+//   FeatCorrelation        networks/modules.py:36-53
+//   maxpool4d              networks/modules.py:11-34
+//   MutualMatching         networks/ncn/model.py:157-176
+//   NeighConsensus/Conv4d  networks/ncn/model.py:124-155, networks/ncn/conv4d.py:12-74
+//   corr_to_matches        networks/ncn/extract_ncmatches.py:6-94
+//   cal_coarse_matches     networks/patch2pix.py:340-375
+//   filter_coarse (unique) networks/utils.py:38-50
+//
+// All arithmetic here is fp32 FMA on the CUDA cores: "proposal indices bit-exact" needs
+// fp32-grade correlation / NC scores.  The tensor-core correlation lives in
+// umma_gemm.cuh; this file keeps the HBM-bound scans and the fp32 NC convolution.
+#include "kernels.h"
+
+namespace p2p {
+
+// ------------------------------------------------------------------------------------------------
+// K1: L2 normalise over channels and (for ksize 2) permute positions into pooling-window order:
+// out[c][cell*4 + m], m = di*2+dj, so that the 4 members of a 2x2 window are adjacent.
+// ------------------------------------------------------------------------------------------------
+template <int KS>
+__global__ void __launch_bounds__(256) l2norm_perm_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                         int C, int h, int w) {
+  const int n = h * w;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;  // output index
+  if (q >= n) return;
+  int pos;
+  if (KS == 2) {
+    const int wp = w >> 1;
+    const int cell = q >> 2, m = q & 3;
+    const int pi = cell / wp, pj = cell - pi * wp;
+    pos = (2 * pi + (m >> 1)) * w + 2 * pj + (m & 1);
+  } else {
+    pos = q;
+  }
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) {
+    const float v = __ldg(in + (size_t)c * n + pos);
+    s = fmaf(v, v, s);
+  }
+  const float d = sqrtf(s + 1e-6f);
+  for (int c = 0; c < C; ++c) out[(size_t)c * n + q] = __ldg(in + (size_t)c * n + pos) / d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2+K3 (CUDA-core variant): corr[m][n] = sum_c A[c][m] B[c][n] with the 2^4 max-pool and the
+// argmax code fused into the epilogue.  Each thread owns a 4x4 micro-tile which, thanks to the
+// window-order permutation above, is exactly one 4D pooling window.
+// code = ((di*2+dj)*2+dk)*2+dl with ties resolved to the lowest code (torch.max semantics).
+// ------------------------------------------------------------------------------------------------
+template <int KS>
+__global__ void __launch_bounds__(256) corr_pool_kernel(const float* __restrict__ fa, const float* __restrict__ fb,
+                                                       int C, int n1, int n2, float* __restrict__ out,
+                                                       uint8_t* __restrict__ code) {
+  constexpr int KC = 16;
+  __shared__ __align__(16) float As[KC][64];
+  __shared__ __align__(16) float Bs[KC][64];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int a0 = blockIdx.y * 64, b0 = blockIdx.x * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < C; k0 += KC) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int idx = tid + r * 256;
+      const int kk = idx >> 6, q = idx & 63;
+      const bool kin = (k0 + kk) < C;
+      As[kk][q] = (kin && a0 + q < n1) ? __ldg(fa + (size_t)(k0 + kk) * n1 + a0 + q) : 0.f;
+      Bs[kk][q] = (kin && b0 + q < n2) ? __ldg(fb + (size_t)(k0 + kk) * n2 + b0 + q) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < KC; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  if (KS == 2) {
+    const int np1 = n1 >> 2, np2 = n2 >> 2;
+    const int ca = (a0 >> 2) + ty, cb = (b0 >> 2) + tx;
+    if (ca < np1 && cb < np2) {
+      float best = acc[0][0];
+      int bi = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (acc[i][j] > best) {
+            best = acc[i][j];
+            bi = i * 4 + j;
+          }
+      out[(size_t)ca * np2 + cb] = best;
+      code[(size_t)ca * np2 + cb] = (uint8_t)bi;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = a0 + ty * 4 + i;
+      if (row >= n1) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = b0 + tx * 4 + j;
+        if (col < n2) out[(size_t)row * n2 + col] = acc[i][j];
+      }
+    }
+  }
+}
+
+// K-major fp16 hi/lo output for the tcgen05 correlation: one warp per output position.
+template <int KS>
+__global__ void __launch_bounds__(256) l2norm_perm_kmajor_kernel(const float* __restrict__ in, __half* __restrict__ hi,
+                                                                __half* __restrict__ lo, int C, int h, int w) {
+  const int n = h * w;
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (q >= n) return;
+  int pos;
+  if (KS == 2) {
+    const int wp = w >> 1;
+    const int cell = q >> 2, m = q & 3;
+    const int pi = cell / wp, pj = cell - pi * wp;
+    pos = (2 * pi + (m >> 1)) * w + 2 * pj + (m & 1);
+  } else {
+    pos = q;
+  }
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float v = __ldg(in + (size_t)c * n + pos);
+    s = fmaf(v, v, s);
+  }
+  s = warp_sum(s);
+  const float d = sqrtf(s + 1e-6f);
+  for (int c = lane; c < C; c += 32) {
+    const float v = __fdiv_rn(__ldg(in + (size_t)c * n + pos), d) * kActScale;
+    const __half hh = __float2half_rn(v);
+    hi[(size_t)q * C + c] = hh;
+    if (lo != nullptr) lo[(size_t)q * C + c] = __float2half_rn(v - __half2float(hh));
+  }
+}
+
+int launch_l2norm_perm_kmajor(const float* in, __half* hi, __half* lo, int C, int h, int w, int ksize,
+                              cudaStream_t st) {
+  const int n = h * w;
+  if (ksize == 2)
+    l2norm_perm_kmajor_kernel<2><<<cdiv(n, 8), 256, 0, st>>>(in, hi, lo, C, h, w);
+  else
+    l2norm_perm_kmajor_kernel<1><<<cdiv(n, 8), 256, 0, st>>>(in, hi, lo, C, h, w);
+  P2P_LAUNCH_OK();
+  return 0;
+}
+
+__global__ void split_rows_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo,
+                                  size_t n, float scale) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = in[i] * scale;
+  const __half hh = __float2half_rn(v);
+  hi[i] = hh;
+  if (lo != nullptr) lo[i] = __float2half_rn(v - __half2float(hh));
+}
+
+int launch_split_rows(const float* in, __half* hi, __half* lo, size_t n, float scale, cudaStream_t st) {
+  split_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, hi, lo, n, scale);
+  P2P_LAUNCH_OK();
+  return 0;
+}
+
+__global__ void delta_pack_kernel(const long long* di, const long long* dj, const long long* dk, const long long* dl,
+                                  size_t n, int ks, uint8_t* code) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  code[i] = (uint8_t)(((di[i] * ks + dj[i]) * ks + dk[i]) * ks + dl[i]);
+}
+
+int launch_delta_pack(const long long* di, const long long* dj, const long long* dk, const long long* dl, size_t n,
+                      int ks, uint8_t* code, cudaStream_t st) {
+  delta_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(di, dj, dk, dl, n, ks, code);
+  P2P_LAUNCH_OK();
+  return 0;
+}
+
+int launch_l2norm_perm(const float* in, float* out, int C, int h, int w, int ksize, cudaStream_t st) {
+  const int n = h * w;
+  if (ksize == 2)
+    l2norm_perm_kernel<2><<<cdiv(n, 256), 256, 0, st>>>(in, out, C, h, w);
+  else
+    l2norm_perm_kernel<1><<<cdiv(n, 256), 256, 0, st>>>(in, out, C, h, w);
+  P2P_LAUNCH_OK();
+  return 0;
+}
+
+int launch_corr_pool_simt(const float* fa, const float* fb, int C, int n1, int n2, int ksize, float* out,
+                          uint8_t* code, cudaStream_t st) {
+  dim3 grid(cdiv(n2, 64), cdiv(n1, 64));
+  if (ksize == 2)
+    corr_pool_kernel<2><<<grid, 256, 0, st>>>(fa, fb, C, n1, n2, out, code);
+  else
+    corr_pool_kernel<1><<<grid, 256, 0, st>>>(fa, fb, C, n1, n2, out, code);
+  P2P_LAUNCH_OK();
+  return 0;
+}
+
+// Expand the packed argmax code into the reference's four int64 delta tensors.
+__global__ void delta_unpack_kernel(const uint8_t* __restrict__ code, size_t n, int ks, long long* di, long long* dj,
+                                    long long* dk, long long* dl) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = code[i];
+  const int l = c % ks;
+  c /= ks;
+  const int k = c % ks;
+  c /= ks;
+  const int j = c % ks;
+  c /= ks;
+  di[i] = c;
+  dj[i] = j;
+  dk[i] = k;
+  dl[i] = l;
+}
+
+int launch_delta_unpack(const uint8_t* code, size_t n, int ks, long long* di, long long* dj, long long* dk,
+                        long long* dl, cudaStream_t st) {
+  delta_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(code, n, ks, di, dj, dk, dl);
+  P2P_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: MutualMatching.  rowmax[a] = max_b x[a][b] (max over B for a fixed A cell),
+// colmax[b] = max_a x[a][b]; out = x * ((x/(rowmax+eps)) * (x/(colmax+eps))).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rowcolmax_kernel(const float* __restrict__ x, int nA, int nB,
+                                                       float* __restrict__ rowmax, unsigned int* __restrict__ colmax) {
+  constexpr int R = 8;
+  __shared__ float red[8][R];
+  const int r0 = blockIdx.x * R;
+  float rm[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) rm[r] = -INFINITY;
+  for (int col = threadIdx.x; col < nB; col += 256) {
+    float cm = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (r0 + r < nA) {
+        const float v = x[(size_t)(r0 + r) * nB + col];
+        rm[r] = fmaxf(rm[r], v);
+        cm = fmaxf(cm, v);
+      }
+    }
+    atomicMax(colmax + col, f2ord(cm));
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const float v = warp_max(rm[r]);
+    if (lane == 0) red[wid][r] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < R && r0 + threadIdx.x < nA) {
+    float v = red[0][threadIdx.x];
+#pragma unroll
+    for (int wv = 1; wv < 8; ++wv) v = fmaxf(v, red[wv][threadIdx.x]);
+    rowmax[r0 + threadIdx.x] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) mutual_apply_kernel(const float* __restrict__ x, int nA, int nB,
+                                                          const float* __restrict__ rowmax,
+                                                          const unsigned int* __restrict__ colmax,
+                                                          float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)nA * nB) return;
+  const int a = (int)(i / nB), b = (int)(i - (size_t)a * nB);
+  const float v = x[i];
+  const float ra = __fdiv_rn(v, rowmax[a] + 1e-5f);
+  const float rb = __fdiv_rn(v, ord2f(colmax[b]) + 1e-5f);
+  out[i] = __fmul_rn(v, __fmul_rn(ra, rb));
+}
+
+int launch_mutual_matching(const float* x, int nA, int nB, float* rowmax, unsigned int* colmax, float* out,
+                           cudaStream_t st) {
+  P2P_CUDA_OK(cudaMemsetAsync(colmax, 0, sizeof(unsigned int) * nB, st));
+  rowcolmax_kernel<<<cdiv(nA, 8), 256, 0, st>>>(x, nA, nB, rowmax, colmax);
+  P2P_LAUNCH_OK();
+  const size_t n = (size_t)nA * nB;
+  mutual_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, nA, nB, rowmax, colmax, out);
+  P2P_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: symmetric NC conv.  conv(x) + conv(x^T)^T with shared weights equals two independent
+// two-layer nets on the SAME input, the second with tap axes (a,b)<->(d,e) swapped, so layer 1
+// produces 32 channels (16 per net) and layer 2 reduces each group of 16 to one map.
+// hidden layout: [A cell][32][hB][wB] fp32 (HBM round trip: 2*32*V*4 B, << the FMA time).
+// ------------------------------------------------------------------------------------------------
+// layer 1: grid (ceil(hB/8), nA), block (ceil(wB/2), 8); thread = 2 adjacent B cells x 32 channels.
+__global__ void __launch_bounds__(512) nc_layer1_kernel(const float* __restrict__ x, int hA, int wA, int hB, int wB,
+                                                       const float* __restrict__ w1p, const float* __restrict__ b1p,
+                                                       float* __restrict__ hidden) {
+  extern __shared__ __align__(16) float smem[];
+  const int PW = wB + 4;                 // halo row pitch (>= wB+2, covers the 2-wide thread tile)
+  float* w1s = smem;                     // [81][32]
+  float* xs = smem + 81 * 32;            // [9][10][PW]
+  const int nthreads = blockDim.x * blockDim.y;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int a = blockIdx.y, ia = a / wA, ja = a - ia * wA;
+  const int k0 = blockIdx.x * 8;
+  const int nB = hB * wB;
+  for (int i = tid; i < 81 * 32; i += nthreads) w1s[i] = w1p[i];
+  for (int i = tid; i < 9 * 10 * PW; i += nthreads) {
+    const int ab = i / (10 * PW);
+    const int rem = i - ab * 10 * PW;
+    const int kk = rem / PW, ll = rem - kk * PW;
+    const int si = ia + ab / 3 - 1, sj = ja + ab % 3 - 1;
+    const int sk = k0 + kk - 1, sl = ll - 1;
+    float v = 0.f;
+    if (si >= 0 && si < hA && sj >= 0 && sj < wA && sk >= 0 && sk < hB && sl >= 0 && sl < wB)
+      v = __ldg(x + (size_t)(si * wA + sj) * nB + sk * wB + sl);
+    xs[i] = v;
+  }
+  __syncthreads();
+  const int tl = threadIdx.x, tk = threadIdx.y;
+  const int l0 = 2 * tl, k = k0 + tk;
+  float acc0[32], acc1[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) acc0[c] = acc1[c] = b1p[c];
+  for (int ab = 0; ab < 9; ++ab) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float* row = xs + (ab * 10 + tk + d) * PW + l0;
+      const float v0 = row[0], v1 = row[1], v2 = row[2], v3 = row[3];
+#pragma unroll
+      for (int e = 0; e < 3; ++e) {
+        const float u0 = e == 0 ? v0 : (e == 1 ? v1 : v2);
+        const float u1 = e == 0 ? v1 : (e == 1 ? v2 : v3);
+        const float4* wv = reinterpret_cast<const float4*>(w1s + (ab * 9 + d * 3 + e) * 32);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 wq = wv[c4];
+          acc0[c4 * 4 + 0] = fmaf(u0, wq.x, acc0[c4 * 4 + 0]);
+          acc0[c4 * 4 + 1] = fmaf(u0, wq.y, acc0[c4 * 4 + 1]);
+          acc0[c4 * 4 + 2] = fmaf(u0, wq.z, acc0[c4 * 4 + 2]);
+          acc0[c4 * 4 + 3] = fmaf(u0, wq.w, acc0[c4 * 4 + 3]);
+          acc1[c4 * 4 + 0] = fmaf(u1, wq.x, acc1[c4 * 4 + 0]);
+          acc1[c4 * 4 + 1] = fmaf(u1, wq.y, acc1[c4 * 4 + 1]);
+          acc1[c4 * 4 + 2] = fmaf(u1, wq.z, acc1[c4 * 4 + 2]);
+          acc1[c4 * 4 + 3] = fmaf(u1, wq.w, acc1[c4 * 4 + 3]);
+        }
+      }
+    }
+  }
+  if (k < hB) {
+    float* hp = hidden + (size_t)a * 32 * nB + k * wB;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      if (l0 < wB) hp[(size_t)c * nB + l0] = fmaxf(acc0[c], 0.f);
+      if (l0 + 1 < wB) hp[(size_t)c * nB + l0 + 1] = fmaxf(acc1[c], 0.f);
+    }
+  }
+}
+
+// layer 2: grid (nA), block (ceil(wB/4), ceil(hB/2)); thread = 2x4 B cells; loops 9 A-neighbours x
+// 4-channel groups, staging hidden planes (with halo) through shared memory.
+__global__ void __launch_bounds__(512) nc_layer2_kernel(const float* __restrict__ hidden, int hA, int wA, int hB,
+                                                        int wB, const float* __restrict__ w2p, float b2,
+                                                        float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  const int PW = ((wB + 2 + 3) / 4) * 4 + 4;  // pitch: multiple of 4 floats, covers 4*tl+5
+  const int PH = hB + 2 + 1;                  // covers 2*tk+3
+  float* w2s = smem;                          // [81][32]
+  float* tile = smem + 81 * 32;               // [4][PH][PW]
+  const int nthreads = blockDim.x * blockDim.y;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int a = blockIdx.x, ia = a / wA, ja = a - ia * wA;
+  const int nB = hB * wB;
+  for (int i = tid; i < 81 * 32; i += nthreads) w2s[i] = w2p[i];
+  const int tl = threadIdx.x, tk = threadIdx.y;
+  float total[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) total[i] = 0.f;
+  const int plane = PH * PW;
+  for (int net = 0; net < 2; ++net) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = b2;
+    for (int ab = 0; ab < 9; ++ab) {
+      const int si = ia + ab / 3 - 1, sj = ja + ab % 3 - 1;
+      if (si < 0 || si >= hA || sj < 0 || sj >= wA) continue;  // uniform across the block
+      const float* src = hidden + (size_t)(si * wA + sj) * 32 * nB;
+      for (int cg = 0; cg < 4; ++cg) {
+        const int c0 = net * 16 + cg * 4;
+        __syncthreads();
+        for (int i = tid; i < 4 * plane; i += nthreads) {
+          const int cc = i / plane;
+          const int rem = i - cc * plane;
+          const int kk = rem / PW, ll = rem - kk * PW;
+          const int sk = kk - 1, sl = ll - 1;
+          float v = 0.f;
+          if (sk >= 0 && sk < hB && sl >= 0 && sl < wB) v = __ldg(src + (size_t)(c0 + cc) * nB + sk * wB + sl);
+          tile[i] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          float r[4][6];
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) {
+            const float* p = tile + cc * plane + (2 * tk + rr) * PW + 4 * tl;
+            const float4 q = *reinterpret_cast<const float4*>(p);
+            const float2 q2 = *reinterpret_cast<const float2*>(p + 4);
+            r[rr][0] = q.x; r[rr][1] = q.y; r[rr][2] = q.z; r[rr][3] = q.w; r[rr][4] = q2.x; r[rr][5] = q2.y;
+          }
+#pragma unroll
+          for (int d = 0; d < 3; ++d)
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+              const float wv = w2s[(ab * 9 + d * 3 + e) * 32 + c0 + cc];
+#pragma unroll
+              for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+                for (int ll = 0; ll < 4; ++ll) acc[kk * 4 + ll] = fmaf(r[kk + d][ll + e], wv, acc[kk * 4 + ll]);
+            }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) total[i] += fmaxf(acc[i], 0.f);
+  }
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+    for (int ll = 0; ll < 4; ++ll) {
+      const int k = 2 * tk + kk, l = 4 * tl + ll;
+      if (k < hB && l < wB) out[(size_t)a * nB + k * wB + l] = total[kk * 4 + ll];
+    }
+}
+
+int launch_neigh_consensus(const float* x, int hA, int wA, int hB, int wB, const float* w1p, const float* b1p,
+                           const float* w2p, float b2, float* hidden, float* out, cudaStream_t st) {
+  const int nA = hA * wA;
+  {
+    dim3 block(cdiv(wB, 2), 8);
+    P2P_REQUIRE(block.x * block.y <= 512, "NC layer 1: pooled width too large (wB <= 128)");
+    dim3 grid(cdiv(hB, 8), nA);
+    const size_t smem = sizeof(float) * (81 * 32 + 9 * 10 * (wB + 4));
+    P2P_CUDA_OK(cudaFuncSetAttribute(nc_layer1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nc_layer1_kernel<<<grid, block, smem, st>>>(x, hA, wA, hB, wB, w1p, b1p, hidden);
+    P2P_LAUNCH_OK();
+  }
+  {
+    dim3 block(cdiv(wB, 4), cdiv(hB, 2));
+    P2P_REQUIRE(block.x * block.y <= 512, "NC layer 2: pooled B grid too large (hB*wB <= 4096)");
+    const int PW = ((wB + 2 + 3) / 4) * 4 + 4, PH = hB + 3;
+    const size_t smem = sizeof(float) * (81 * 32 + 4 * PH * PW);
+    P2P_REQUIRE(smem <= 200 * 1024, "NC layer 2: pooled B grid does not fit shared memory");
+    P2P_CUDA_OK(cudaFuncSetAttribute(nc_layer2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nc_layer2_kernel<<<nA, block, smem, st>>>(hidden, hA, wA, hB, wB, w2p, b2, out);
+    P2P_LAUNCH_OK();
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6+K7: proposals.  score = max softmax prob = 1 / sum exp(x - max); argmax with lowest-index
+// ties; relocalise with the pooling code; scale to pixels.  Rows [0,nB): best A for every B cell
+// (softmax over A); rows [nB, nB+nA): best B for every A cell.  Row = (x1,y1,x2,y2) int64.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void better(float& v, int& i, float v2, int i2) {
+  if (v2 > v || (v2 == v && i2 < i)) {
+    v = v2;
+    i = i2;
+  }
+}
+
+__device__ __forceinline__ void emit_match(long long* m, float* sc, int row, int a, int b, float score, int wA, int wB,
+                                           int nB, const uint8_t* code, int ks, int upsample, int shift) {
+  int iA = a / wA, jA = a - iA * wA, iB = b / wB, jB = b - iB * wB;
+  if (code != nullptr) {
+    int c = code[(size_t)a * nB + b];
+    const int dl = c % ks; c /= ks;
+    const int dk = c % ks; c /= ks;
+    const int dj = c % ks; c /= ks;
+    iA = iA * ks + c; jA = jA * ks + dj; iB = iB * ks + dk; jB = jB * ks + dl;
+  }
+  m[(size_t)row * 4 + 0] = (long long)jA * upsample + shift;
+  m[(size_t)row * 4 + 1] = (long long)iA * upsample + shift;
+  m[(size_t)row * 4 + 2] = (long long)jB * upsample + shift;
+  m[(size_t)row * 4 + 3] = (long long)iB * upsample + shift;
+  sc[row] = score;
+}
+
+// best A for every B cell: block (32 columns) x (8 row phases)
+__global__ void __launch_bounds__(256) proposals_dir1_kernel(const float* __restrict__ x, int nA, int nB, int wA, int wB,
+                                                            const uint8_t* __restrict__ code, int ks, int upsample,
+                                                            int shift, int do_softmax, long long* __restrict__ m,
+                                                            float* __restrict__ sc) {
+  __shared__ float sv[8][33];
+  __shared__ int si[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int b = blockIdx.x * 32 + tx;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  if (b < nB)
+    for (int a = ty; a < nA; a += 8) better(best, bi, x[(size_t)a * nB + b], a);
+  sv[ty][tx] = best;
+  si[ty][tx] = bi;
+  __syncthreads();
+  best = sv[0][tx];
+  bi = si[0][tx];
+#pragma unroll
+  for (int r = 1; r < 8; ++r) better(best, bi, sv[r][tx], si[r][tx]);
+  __syncthreads();
+  float s = 0.f;
+  if (b < nB && do_softmax)
+    for (int a = ty; a < nA; a += 8) s += expf(x[(size_t)a * nB + b] - best);
+  sv[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && b < nB) {
+    float tot = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) tot += sv[r][tx];
+    const float score = do_softmax ? __fdiv_rn(1.f, tot) : best;
+    emit_match(m, sc, b, bi, b, score, wA, wB, nB, code, ks, upsample, shift);
+  }
+}
+
+// best B for every A cell: one warp per row
+__global__ void __launch_bounds__(256) proposals_dir2_kernel(const float* __restrict__ x, int nA, int nB, int wA, int wB,
+                                                            const uint8_t* __restrict__ code, int ks, int upsample,
+                                                            int shift, int do_softmax, long long* __restrict__ m,
+                                                            float* __restrict__ sc) {
+  const int lane = threadIdx.x & 31;
+  const int a = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (a >= nA) return;
+  const float* row = x + (size_t)a * nB;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int b = lane; b < nB; b += 32) better(best, bi, row[b], b);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float v2 = __shfl_xor_sync(0xffffffffu, best, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+    better(best, bi, v2, i2);
+  }
+  float s = 0.f;
+  if (do_softmax)
+    for (int b = lane; b < nB; b += 32) s += expf(row[b] - best);
+  s = warp_sum(s);
+  if (lane == 0) {
+    const float score = do_softmax ? __fdiv_rn(1.f, s) : best;
+    emit_match(m, sc, nB + a, a, bi, score, wA, wB, nB, code, ks, upsample, shift);
+  }
+}
+
+int launch_proposals(const float* corr, const uint8_t* code, int hA, int wA, int hB, int wB, int ksize, int upsample,
+                     int center, int do_softmax, long long* matches, float* scores, cudaStream_t st) {
+  const int nA = hA * wA, nB = hB * wB;
+  const int shift = center ? upsample / 2 : 0;
+  proposals_dir1_kernel<<<cdiv(nB, 32), 256, 0, st>>>(corr, nA, nB, wA, wB, code, ksize, upsample, shift, do_softmax,
+                                                      matches, scores);
+  P2P_LAUNCH_OK();
+  proposals_dir2_kernel<<<cdiv(nA, 8), 256, 0, st>>>(corr, nA, nB, wA, wB, code, ksize, upsample, shift, do_softmax,
+                                                     matches, scores);
+  P2P_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8: the np.unique(axis=0, return_index, return_counts) part of filter_coarse, on the device.
+// Rows are packed to 64-bit keys (4 x 16-bit coords), (key, first index) pairs are sorted by a
+// single-block bitonic network, runs are detected and (for mutual) only runs of length > 1 keep
+// their first-occurrence index.  Output order is lexicographic, like np.unique.
+// count_out[0] = number of ids written, count_out[1] = 1 if a coordinate was out of [0,65535].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) unique_rows_kernel(const long long* __restrict__ rows, int n, int P, int mutual,
+                                                          int* __restrict__ ids_out, int* __restrict__ count_out) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smraw);
+  int* idx = reinterpret_cast<int*>(smraw + (size_t)P * 8);
+  __shared__ int s_bad;
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, T = blockDim.x;
+  if (tid == 0) { s_bad = 0; s_base = 0; }
+  __syncthreads();
+  for (int i = tid; i < P; i += T) {
+    unsigned long long k = ~0ull;
+    if (i < n) {
+      k = 0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const long long v = rows[(size_t)i * 4 + c];
+        if (v < 0 || v > 65535) s_bad = 1;
+        k = (k << 16) | (unsigned long long)(v & 0xffff);
+      }
+    }
+    keys[i] = k;
+    idx[i] = i;
+  }
+  __syncthreads();
+  for (int size = 2; size <= P; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < (P >> 1); t += T) {
+        const int lo = (t / stride) * (stride << 1) + (t % stride);
+        const int hi = lo + stride;
+        const bool asc = ((lo & size) == 0);
+        const unsigned long long k0 = keys[lo], k1 = keys[hi];
+        const int i0 = idx[lo], i1 = idx[hi];
+        const bool gt = (k0 > k1) || (k0 == k1 && i0 > i1);
+        if (gt == asc) {
+          keys[lo] = k1; keys[hi] = k0;
+          idx[lo] = i1; idx[hi] = i0;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // compaction in sorted order: chunks of T elements, block-wide exclusive scan per chunk
+  for (int c0 = 0; c0 < P; c0 += T) {
+    const int p = c0 + tid;
+    int sel = 0;
+    if (p < n) {
+      const bool first = (p == 0) || (keys[p] != keys[p - 1]);
+      const bool dup = (p + 1 < n) && (keys[p + 1] == keys[p]);
+      sel = first && (mutual ? dup : true);
+    }
+    const unsigned int ball = __ballot_sync(0xffffffffu, sel);
+    const int lane = tid & 31, wid = tid >> 5;
+    const int wpre = __popc(ball & ((1u << lane) - 1u));
+    if (lane == 0) s_warp[wid] = __popc(ball);
+    __syncthreads();
+    int woff = 0, tot = 0;
+    for (int wv = 0; wv < (T >> 5); ++wv) {
+      const int cnt = s_warp[wv];
+      if (wv < wid) woff += cnt;
+      tot += cnt;
+    }
+    const int base = s_base;
+    if (sel) ids_out[base + woff + wpre] = idx[p];
+    __syncthreads();
+    if (tid == 0) s_base = base + tot;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    count_out[0] = s_base;
+    count_out[1] = s_bad;
+  }
+}
+
+int launch_unique_rows(const long long* rows, int n, int mutual, int* ids_out, int* count_out, cudaStream_t st) {
+  P2P_REQUIRE(n >= 0 && n <= 16384, "unique_rows: at most 16384 candidate rows");
+  if (n == 0) {
+    P2P_CUDA_OK(cudaMemsetAsync(count_out, 0, 2 * sizeof(int), st));
+    return 0;
+  }
+  int P = 2;
+  while (P < n) P <<= 1;
+  const size_t smem = (size_t)P * 12;
+  P2P_CUDA_OK(cudaFuncSetAttribute(unique_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  unique_rows_kernel<<<1, 1024, smem, st>>>(rows, n, P, mutual, ids_out, count_out);
+  P2P_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace p2p

@@ -1,0 +1,86 @@
+// Internal launcher declarations shared by the translation units of libp2p_b200.so.
+#pragma once
+#include "common.cuh"
+
+namespace p2p {
+
+// ---- coarse.cu ---------------------------------------------------------------------------------
+int launch_l2norm_perm(const float* in, float* out, int C, int h, int w, int ksize, cudaStream_t st);
+// K-major fp16 hi/lo variant for the tensor-core correlation: out[q][c] = split(kActScale * f/|f|)
+int launch_l2norm_perm_kmajor(const float* in, __half* hi, __half* lo, int C, int h, int w, int ksize, cudaStream_t st);
+int launch_split_rows(const float* in, __half* hi, __half* lo, size_t n, float scale, cudaStream_t st);
+int launch_delta_pack(const long long* di, const long long* dj, const long long* dk, const long long* dl, size_t n,
+                      int ks, uint8_t* code, cudaStream_t st);
+int launch_corr_pool_simt(const float* fa, const float* fb, int C, int n1, int n2, int ksize, float* out,
+                          uint8_t* code, cudaStream_t st);
+int launch_delta_unpack(const uint8_t* code, size_t n, int ks, long long* di, long long* dj, long long* dk,
+                        long long* dl, cudaStream_t st);
+int launch_mutual_matching(const float* x, int nA, int nB, float* rowmax, unsigned int* colmax, float* out,
+                           cudaStream_t st);
+int launch_neigh_consensus(const float* x, int hA, int wA, int hB, int wB, const float* w1p, const float* b1p,
+                           const float* w2p, float b2, float* hidden, float* out, cudaStream_t st);
+int launch_proposals(const float* corr, const uint8_t* code, int hA, int wA, int hB, int wB, int ksize, int upsample,
+                     int center, int do_softmax, long long* matches, float* scores, cudaStream_t st);
+int launch_unique_rows(const long long* rows, int n, int mutual, int* ids_out, int* count_out, cudaStream_t st);
+
+// ---- refine.cu ---------------------------------------------------------------------------------
+// Activation scale applied before the fp16 hi/lo split of the L2-normalised patch features.
+constexpr float kActScale = 4096.f;
+constexpr int kPatchPos = 256;    // 4 parity planes x 8 x 8 window positions
+constexpr int kMainCh = 512;      // (64 + 64 + 128) x 2 images
+constexpr int kRgbK = 64;         // 9 taps x 2 images x 3 channels = 54, padded to 64
+constexpr int kConv1Steps = 73;   // 9 taps x 8 chunks + 1 rgb chunk (K = 73*64 = 4672)
+constexpr int kConv2Steps = 72;   // 9 taps x 8 chunks          (K = 4608)
+
+struct PairFeatures {             // per image: channels-last copies + squared-norm maps
+  const float* img;               // [3][H][W]   (level 0 stays NCHW)
+  float* nhwc[3];                 // levels 1..3: [h][w][C], C = 64, 64, 128
+  float* nsq[4];                  // levels 0..3: [h][w]
+  int H, W;
+};
+
+int launch_feature_prep(const float* const feats[4], int H, int W, PairFeatures& out, cudaStream_t st);
+int launch_patch_gather(const PairFeatures& f1, const PairFeatures& f2, const void* matches, int is_float, int N,
+                        __half* p_hi, __half* p_lo, __half* rgb_hi, __half* rgb_lo, cudaStream_t st);
+
+struct FcWeights {                // BN folded, transposed to [in][out] for coalesced reads
+  float *w1t, *b1, *w2t, *b2, *w3t, *b3;
+};
+int launch_fc_parse(const float* pooled, const FcWeights& fc, const void* matches_in, int is_float, int N, int W1,
+                    int H1, int W2, int H2, float* matches_out, float* probs_out, cudaStream_t st);
+
+// One k-step of an implicit GEMM: where the [128 rows x 64 ch] A box starts and which K offset of
+// the K-major weight matrix it multiplies.
+struct KStep {
+  short c0;                       // channel coordinate of the A box
+  signed char x, y;               // spatial start (may be -1: TMA zero-fills out-of-bounds)
+  signed char plane;              // parity plane (conv1) or 0
+  signed char kind;               // 0 = main activation tensor, 1 = rgb im2col tensor
+  short pad;
+  int bk;                         // K coordinate in the weight matrix
+};
+
+// CUDA-core debug GEMM over exactly the tensors the tcgen05 kernel consumes (bring-up checker;
+// not a product path: selected only by p2p_set_option("gemm_impl", 1)).
+struct GemmOperands {
+  const __half *a_hi, *a_lo;      // main A tensor [N][planes][8][8][512]
+  const __half *r_hi, *r_lo;      // rgb A tensor  [N][64][64]  (nullptr for conv2)
+  const __half *b_hi, *b_lo;      // weights [512][Ktot], K-major
+  int planes;                     // 4 (conv1) or 1 (conv2)
+  int ktot;                       // K extent of B
+  int n_patches;
+  int passes;                     // 1: hi*hi ; 3: hi*hi + lo*hi + hi*lo
+  const KStep* steps;             // device array
+  int nsteps;
+};
+struct ConvEpilogue {
+  const float* scale;             // [512] = 1 / (act_scale * w_scale[o])
+  const float* bias;              // [512]
+  int mode;                       // 0: write y1 hi/lo (scaled by y_scale); 1: relu + 8x8 max -> pooled
+  float y_scale;
+  __half *y_hi, *y_lo;            // [N][8][8][512]
+  float* pooled;                  // [N][512]
+};
+int launch_conv_gemm_simt(const GemmOperands& g, const ConvEpilogue& e, cudaStream_t st);
+
+}  // namespace p2p

@@ -1,0 +1,397 @@
+// Refine stage, everything except the tensor-core implicit GEMMs (umma_gemm.cu):
+//   feature_prep   per pair: channels-last copies of the 3 feature levels + squared-norm maps
+//   patch_gather   select_local_patch_feats + patch L2 normalise + fp16 hi/lo split, written in
+//                  the parity-plane layout the conv1 implicit GEMM consumes through TMA
+//   fc_parse       FeatRegressNet.fc (BN folded) + parse_regressor_out
+//   conv_gemm_simt CUDA-core checker for the implicit GEMMs (bring-up only)
+//
+// Reference semantics:
+//   select_local_patch_feats        networks/utils.py:4-36
+//   patch normalise / reshape       networks/patch2pix.py:173-178
+//   FeatRegressNet                  networks/modules.py:56-112
+//   parse_regressor_out             networks/patch2pix.py:138-155
+#include "kernels.h"
+
+namespace p2p {
+
+// ------------------------------------------------------------------------------------------------
+// feature prep
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nchw_to_nhwc_nsq_kernel(const float* __restrict__ in, int C, int npx,
+                                                              float* __restrict__ out, float* __restrict__ nsq) {
+  extern __shared__ float tile[];  // [C][33]
+  __shared__ float part[8][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int px0 = blockIdx.x * 32;
+  const int px = px0 + lane;
+  float s = 0.f;
+  for (int c = wid; c < C; c += 8) {
+    const float v = px < npx ? __ldg(in + (size_t)c * npx + px) : 0.f;
+    tile[c * 33 + lane] = v;
+    s = fmaf(v, v, s);
+  }
+  part[wid][lane] = s;
+  __syncthreads();
+  if (wid == 0 && px < npx) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += part[w][lane];
+    nsq[px] = t;
+  }
+  for (int i = threadIdx.x; i < 32 * C; i += 256) {
+    const int p = i / C, c = i - p * C;
+    if (px0 + p < npx) out[(size_t)(px0 + p) * C + c] = tile[c * 33 + p];
+  }
+}
+
+__global__ void nsq_rgb_kernel(const float* __restrict__ img, int npx, float* __restrict__ nsq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npx) return;
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = __ldg(img + (size_t)c * npx + i);
+    s = fmaf(v, v, s);
+  }
+  nsq[i] = s;
+}
+
+int launch_feature_prep(const float* const feats[4], int H, int W, PairFeatures& out, cudaStream_t st) {
+  out.img = feats[0];
+  out.H = H;
+  out.W = W;
+  nsq_rgb_kernel<<<cdiv(H * W, 256), 256, 0, st>>>(feats[0], H * W, out.nsq[0]);
+  P2P_LAUNCH_OK();
+  const int chans[3] = {64, 64, 128};
+  for (int l = 0; l < 3; ++l) {
+    const int ds = 2 << l;
+    const int npx = (H / ds) * (W / ds);
+    const int C = chans[l];
+    nchw_to_nhwc_nsq_kernel<<<cdiv(npx, 32), 256, sizeof(float) * C * 33, st>>>(feats[l + 1], C, npx, out.nhwc[l],
+                                                                               out.nsq[l + 1]);
+    P2P_LAUNCH_OK();
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// patch gather.  One block per patch.
+// conv1 (k3, s2, p1) reads window pixel wx = 2*ox - 1 + tx.  Window pixels are stored in four
+// parity planes so that every tap is a dense 8x8 box:  plane = py*2+px, px = 0 holds odd wx
+// (entry ix <-> wx = 2*ix+1), px = 1 holds even wx (ix <-> wx = 2*ix).  Tap tx=0 -> (px 0, start -1,
+// the -1 column is TMA zero fill = conv padding), tx=1 -> (px 1, start 0), tx=2 -> (px 0, start 0).
+// Main tensor [N][4][8][8][512] fp16 (hi and lo), channel order
+//   [img1: conv1 64 | layer1 64 | layer2 128 | img2: same];
+// rgb tensor [N][64 out pixels][64] fp16 is a plain im2col of the 2x3 image channels
+// (k = tap*6 + img*3 + ch; k >= 54 zero).
+// ------------------------------------------------------------------------------------------------
+struct GatherArgs {
+  const float* img[2];
+  const float* nhwc[2][3];
+  const float* nsq[2][4];
+  int H[2], W[2];
+};
+
+__device__ __forceinline__ int clamp_idx(int v, int ds, int full) {
+  // ((x + dx) // ds).clamp(0, full // ds - 1) with Python floor division
+  if (v < 0) return 0;
+  const int q = v / ds, m = full / ds - 1;
+  return q < m ? q : m;
+}
+
+__device__ __forceinline__ void split_store8(const float* v, __half* hi, __half* lo) {
+  __align__(16) __half h[8];
+  __align__(16) __half l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    h[i] = __float2half_rn(v[i]);
+    l[i] = __float2half_rn(v[i] - __half2float(h[i]));
+  }
+  *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<const uint4*>(h);
+  if (lo != nullptr) *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<const uint4*>(l);
+}
+
+template <bool IS_FLOAT>
+__global__ void __launch_bounds__(256) patch_gather_kernel(GatherArgs g, const void* __restrict__ matches, int N,
+                                                          __half* __restrict__ p_hi, __half* __restrict__ p_lo,
+                                                          __half* __restrict__ rgb_hi, __half* __restrict__ rgb_lo) {
+  __shared__ float dinv[2][16][16];  // act_scale / sqrt(sum_c f^2 + 1e-6) per window pixel
+  __shared__ int org[4];
+  const int n = blockIdx.x;
+  const int tid = threadIdx.x;
+  if (tid < 4) {
+    int v;
+    if (IS_FLOAT)
+      v = (int)reinterpret_cast<const float*>(matches)[(size_t)n * 4 + tid];  // .long(): truncation
+    else
+      v = (int)reinterpret_cast<const long long*>(matches)[(size_t)n * 4 + tid];
+    org[tid] = v - 8;
+  }
+  __syncthreads();
+  for (int i = tid; i < 512; i += 256) {
+    const int s = i >> 8, wy = (i >> 4) & 15, wx = i & 15;
+    const int X = org[2 * s] + wx, Y = org[2 * s + 1] + wy;
+    float t = 0.f;
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const int ds = 1 << l;
+      const int xi = clamp_idx(X, ds, g.W[s]), yi = clamp_idx(Y, ds, g.H[s]);
+      t += __ldg(g.nsq[s][l] + (size_t)yi * (g.W[s] / ds) + xi);
+    }
+    dinv[s][wy][wx] = __fdiv_rn(kActScale, sqrtf(t + 1e-6f));
+  }
+  __syncthreads();
+  // main channels: one warp per window position, lane = 16 consecutive channels of the 512
+  const int lane = tid & 31, wid = tid >> 5;
+  const int j = lane >> 2, sub = lane & 3;     // 64-channel chunk, 16-channel quarter
+  const int s = j >> 2, jj = j & 3;
+  const int lvl = jj == 0 ? 0 : (jj == 1 ? 1 : 2);  // index into nhwc[] (feature levels 1..3)
+  const int ds = 2 << lvl;
+  const int C = lvl == 2 ? 128 : 64;
+  const int coff = (jj == 3 ? 64 : 0) + sub * 16;
+  const float* fmap = g.nhwc[s][lvl];
+  const int wl = g.W[s] / ds;
+  for (int pos = wid; pos < kPatchPos; pos += 8) {
+    const int plane = pos >> 6, iy = (pos >> 3) & 7, ix = pos & 7;
+    const int wx = (plane & 1) ? 2 * ix : 2 * ix + 1;
+    const int wy = (plane & 2) ? 2 * iy : 2 * iy + 1;
+    const int xi = clamp_idx(org[2 * s] + wx, ds, g.W[s]), yi = clamp_idx(org[2 * s + 1] + wy, ds, g.H[s]);
+    const float sc = dinv[s][wy][wx];
+    const float4* src = reinterpret_cast<const float4*>(fmap + ((size_t)yi * wl + xi) * C + coff);
+    float v[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 t = __ldg(src + q);
+      v[q * 4 + 0] = t.x * sc; v[q * 4 + 1] = t.y * sc; v[q * 4 + 2] = t.z * sc; v[q * 4 + 3] = t.w * sc;
+    }
+    const size_t o = ((size_t)n * kPatchPos + pos) * kMainCh + j * 64 + sub * 16;
+    split_store8(v, p_hi + o, p_lo ? p_lo + o : nullptr);
+    split_store8(v + 8, p_hi + o + 8, p_lo ? p_lo + o + 8 : nullptr);
+  }
+  // rgb im2col: 64 output pixels x 64 k
+  for (int e = tid; e < 64 * 64; e += 256) {
+    const int o = e >> 6, k = e & 63;
+    float v = 0.f;
+    if (k < 54) {
+      const int tap = k / 6, r = k - tap * 6;
+      const int si = r / 3, ch = r - si * 3;
+      const int wx = 2 * (o & 7) - 1 + tap % 3, wy = 2 * (o >> 3) - 1 + tap / 3;
+      if (wx >= 0 && wy >= 0) {
+        const int xi = clamp_idx(org[2 * si] + wx, 1, g.W[si]), yi = clamp_idx(org[2 * si + 1] + wy, 1, g.H[si]);
+        v = __ldg(g.img[si] + ((size_t)ch * g.H[si] + yi) * g.W[si] + xi) * dinv[si][wy][wx];
+      }
+    }
+    const __half h = __float2half_rn(v);
+    const size_t oi = (size_t)n * 4096 + e;
+    rgb_hi[oi] = h;
+    if (rgb_lo) rgb_lo[oi] = __float2half_rn(v - __half2float(h));
+  }
+}
+
+int launch_patch_gather(const PairFeatures& f1, const PairFeatures& f2, const void* matches, int is_float, int N,
+                        __half* p_hi, __half* p_lo, __half* rgb_hi, __half* rgb_lo, cudaStream_t st) {
+  if (N == 0) return 0;
+  GatherArgs g;
+  const PairFeatures* f[2] = {&f1, &f2};
+  for (int s = 0; s < 2; ++s) {
+    g.img[s] = f[s]->img;
+    for (int l = 0; l < 3; ++l) g.nhwc[s][l] = f[s]->nhwc[l];
+    for (int l = 0; l < 4; ++l) g.nsq[s][l] = f[s]->nsq[l];
+    g.H[s] = f[s]->H;
+    g.W[s] = f[s]->W;
+  }
+  if (is_float)
+    patch_gather_kernel<true><<<N, 256, 0, st>>>(g, matches, N, p_hi, p_lo, rgb_hi, rgb_lo);
+  else
+    patch_gather_kernel<false><<<N, 256, 0, st>>>(g, matches, N, p_hi, p_lo, rgb_hi, rgb_lo);
+  P2P_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FC stack + parse_regressor_out.  8 patches per block; weights transposed [in][out].
+// ------------------------------------------------------------------------------------------------
+template <bool IS_FLOAT>
+__global__ void __launch_bounds__(256) fc_parse_kernel(const float* __restrict__ pooled, FcWeights fc,
+                                                      const void* __restrict__ matches_in, int N, float W1, float H1,
+                                                      float W2, float H2, float* __restrict__ matches_out,
+                                                      float* __restrict__ probs_out) {
+  constexpr int PB = 8;
+  __shared__ __align__(16) float xs[512][PB];
+  __shared__ __align__(16) float h1[512][PB];
+  __shared__ __align__(16) float h2[256][PB];
+  __shared__ float o5[5][PB];
+  const int t = threadIdx.x;
+  const int n0 = blockIdx.x * PB;
+  for (int i = t; i < 512 * PB; i += 256) {
+    const int p = i / 512, k = i - p * 512;
+    xs[k][p] = (n0 + p < N) ? pooled[(size_t)(n0 + p) * 512 + k] : 0.f;
+  }
+  __syncthreads();
+  {
+    float a0[PB], a1[PB];
+#pragma unroll
+    for (int p = 0; p < PB; ++p) { a0[p] = 0.f; a1[p] = 0.f; }
+    for (int k = 0; k < 512; ++k) {
+      const float w0 = __ldg(fc.w1t + (size_t)k * 512 + t), w1 = __ldg(fc.w1t + (size_t)k * 512 + t + 256);
+      const float4 xa = *reinterpret_cast<const float4*>(&xs[k][0]);
+      const float4 xb = *reinterpret_cast<const float4*>(&xs[k][4]);
+      const float xv[PB] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+      for (int p = 0; p < PB; ++p) { a0[p] = fmaf(xv[p], w0, a0[p]); a1[p] = fmaf(xv[p], w1, a1[p]); }
+    }
+    const float b0 = fc.b1[t], b1 = fc.b1[t + 256];
+#pragma unroll
+    for (int p = 0; p < PB; ++p) { h1[t][p] = fmaxf(a0[p] + b0, 0.f); h1[t + 256][p] = fmaxf(a1[p] + b1, 0.f); }
+  }
+  __syncthreads();
+  {
+    float a[PB];
+#pragma unroll
+    for (int p = 0; p < PB; ++p) a[p] = 0.f;
+    for (int k = 0; k < 512; ++k) {
+      const float w = __ldg(fc.w2t + (size_t)k * 256 + t);
+      const float4 xa = *reinterpret_cast<const float4*>(&h1[k][0]);
+      const float4 xb = *reinterpret_cast<const float4*>(&h1[k][4]);
+      const float xv[PB] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+      for (int p = 0; p < PB; ++p) a[p] = fmaf(xv[p], w, a[p]);
+    }
+    const float b = fc.b2[t];
+#pragma unroll
+    for (int p = 0; p < PB; ++p) h2[t][p] = fmaxf(a[p] + b, 0.f);
+  }
+  __syncthreads();
+  if (t < 5 * PB) {
+    const int o = t / PB, p = t - o * PB;
+    float a = 0.f;
+    for (int k = 0; k < 256; ++k) a = fmaf(h2[k][p], __ldg(fc.w3t + k * 5 + o), a);
+    o5[o][p] = a + fc.b3[o];
+  }
+  __syncthreads();
+  if (t < 5 * PB) {
+    const int j = t / PB, p = t - j * PB;
+    const int n = n0 + p;
+    if (n < N) {
+      const float o = o5[j][p];
+      if (j < 4) {
+        float m;
+        if (IS_FLOAT)
+          m = reinterpret_cast<const float*>(matches_in)[(size_t)n * 4 + j];
+        else
+          m = (float)reinterpret_cast<const long long*>(matches_in)[(size_t)n * 4 + j];
+        const float off = 16.f * tanhf(fmaxf(o, 0.f)) - 8.f;
+        const float hi = (j == 0) ? W1 : (j == 1) ? H1 : (j == 2) ? W2 : H2;
+        matches_out[(size_t)n * 4 + j] = fminf(fmaxf(m + off, 0.f), hi);
+      } else {
+        probs_out[n] = __fdiv_rn(1.f, 1.f + expf(-o));
+      }
+    }
+  }
+}
+
+int launch_fc_parse(const float* pooled, const FcWeights& fc, const void* matches_in, int is_float, int N, int W1,
+                    int H1, int W2, int H2, float* matches_out, float* probs_out, cudaStream_t st) {
+  if (N == 0) return 0;
+  if (is_float)
+    fc_parse_kernel<true><<<cdiv(N, 8), 256, 0, st>>>(pooled, fc, matches_in, N, (float)W1, (float)H1, (float)W2,
+                                                     (float)H2, matches_out, probs_out);
+  else
+    fc_parse_kernel<false><<<cdiv(N, 8), 256, 0, st>>>(pooled, fc, matches_in, N, (float)W1, (float)H1, (float)W2,
+                                                      (float)H2, matches_out, probs_out);
+  P2P_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-core checker GEMM (bring-up only).  Tile 128 rows (2 patches) x 64 output channels.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) conv_gemm_simt_kernel(GemmOperands g, ConvEpilogue e) {
+  __shared__ float As[32][129];
+  __shared__ float Bs[32][65];
+  const int tid = threadIdx.x;
+  const int n0 = blockIdx.x * 2, o0 = blockIdx.y * 64;
+  const int tx = tid & 15, ty = tid >> 4;  // cols tx*4.., rows ty*8..
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int si = 0; si < g.nsteps; ++si) {
+    const KStep ks = g.steps[si];
+    for (int half = 0; half < 2; ++half) {
+      __syncthreads();
+      for (int i = tid; i < 128 * 32; i += 256) {
+        const int row = i >> 5, kk = (i & 31) + half * 32;
+        const int n = n0 + (row >> 6), py = (row >> 3) & 7, px = row & 7;
+        float v = 0.f;
+        if (n < g.n_patches) {
+          if (ks.kind == 1) {
+            const size_t a = ((size_t)n * 64 + (row & 63)) * 64 + kk;
+            v = __half2float(g.r_hi[a]);
+            if (g.passes == 3) v += __half2float(g.r_lo[a]);
+          } else {
+            const int x = px + ks.x, y = py + ks.y;
+            if (x >= 0 && x < 8 && y >= 0 && y < 8) {
+              const size_t a = ((((size_t)n * g.planes + ks.plane) * 8 + y) * 8 + x) * 512 + ks.c0 + kk;
+              v = __half2float(g.a_hi[a]);
+              if (g.passes == 3) v += __half2float(g.a_lo[a]);
+            }
+          }
+        }
+        As[i & 31][row] = v;
+      }
+      for (int i = tid; i < 64 * 32; i += 256) {
+        const int col = i >> 5, kk = (i & 31) + half * 32;
+        const size_t b = (size_t)(o0 + col) * g.ktot + ks.bk + kk;
+        float v = __half2float(g.b_hi[b]);
+        if (g.passes == 3) v += __half2float(g.b_lo[b]);
+        Bs[i & 31][col] = v;
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int kk = 0; kk < 32; ++kk) {
+        float a[8], b[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = As[kk][ty * 8 + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = ty * 8 + i;
+    const int n = n0 + (row >> 6);
+    if (n >= g.n_patches) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int o = o0 + tx * 4 + j;
+      const float y = fmaf(acc[i][j], e.scale[o], e.bias[o]);
+      if (e.mode == 0) {
+        const float v = y * e.y_scale;
+        const __half h = __float2half_rn(v);
+        const size_t a = ((size_t)n * 64 + (row & 63)) * 512 + o;
+        e.y_hi[a] = h;
+        if (e.y_lo) e.y_lo[a] = __float2half_rn(v - __half2float(h));
+      } else {
+        atomicMax(reinterpret_cast<unsigned int*>(e.pooled) + (size_t)n * 512 + o, __float_as_uint(fmaxf(y, 0.f)));
+      }
+    }
+  }
+}
+
+int launch_conv_gemm_simt(const GemmOperands& g, const ConvEpilogue& e, cudaStream_t st) {
+  if (g.n_patches == 0) return 0;
+  if (e.mode == 1) P2P_CUDA_OK(cudaMemsetAsync(e.pooled, 0, sizeof(float) * 512 * (size_t)g.n_patches, st));
+  dim3 grid(cdiv(g.n_patches, 2), 8);
+  conv_gemm_simt_kernel<<<grid, 256, 0, st>>>(g, e);
+  P2P_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace p2p

@@ -1,0 +1,489 @@
+// tcgen05 implicit-GEMM kernel for sm_100a: TMA-staged fp16 operand tiles in shared memory
+// (128B swizzle, K-major), tcgen05.mma (kind::f16, fp32 accumulate) into TMEM, tcgen05.ld epilogue.
+//
+// One kernel serves three contractions of the Patch2Pix hot path (reference file:line):
+//   conv1 of FeatRegressNet  (Conv2d 518->512 k3 s2 p1 + BN)       networks/modules.py:76-87,103-105
+//   conv2 of FeatRegressNet  (Conv2d 512->512 k3 s1 p1 + BN, ReLU, MaxPool 8)   same
+//   FeatCorrelation + maxpool4d (C x n1 x n2 contraction + 2^4 max)  networks/modules.py:11-53
+//
+// Precision: operands are fp16 "hi" (+ optional fp16 "lo" residual) pairs of scaled fp32 values.
+//   PASSES = 1:  hi*hi                      (fp16-grade inputs, fp32 accumulate)
+//   PASSES = 3:  lo*hi + hi*lo + hi*hi      (~2^-22 relative products, i.e. fp32-grade)
+// SEGMENTED accumulation: the tensor core accumulates only `seg_len` k-steps at a time in TMEM;
+// the epilogue warps drain each partial sum and add it to fp32 register totals with
+// round-to-nearest, which bounds the accumulator-rounding drift of long K chains.
+//
+// CTA = 384 threads: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warp 3 idle,
+// warps 4..11 epilogue (TMEM lane quadrant = warp % 4, column half = (warp-4)/4).
+// Tile = 128 rows x 256 columns, K chunk 64 (one 128-byte swizzle row); two TMEM accumulator
+// slots (2 x 256 columns) so the drain of one segment/tile overlaps the MMAs of the next.
+#include <cuda.h>
+
+#include "kernels.h"
+#include "umma_gemm.h"
+
+namespace p2p {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded spin: a protocol bug traps (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0 && clock64() - t0 > 6000000000ll) __trap();   // ~3-4 s
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
+      "%7}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T ; single-thread issue
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread t <-> TMEM lane base+t)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte-swizzled smem matrix descriptor (8-row groups 1024 B apart).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);   // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                     // leading byte offset (ignored for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;           // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                     // descriptor version 1 (sm_100)
+  d |= (uint64_t)2 << 61;                     // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: A=B=fp16, D=fp32, both K-major, M=128, N=256.
+__device__ __forceinline__ constexpr uint32_t make_idesc_f16(int m, int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// epilogues: consume one piece of 32 accumulator columns of one row
+// ------------------------------------------------------------------------------------------------
+template <int EPI>
+__device__ __forceinline__ void epilogue_piece(const UmmaEpilogue& e, int m_tile, int row, int col0, const float* v) {
+  if (EPI == EPI_PLAIN) {
+    const int r = m_tile * 128 + row;
+    if (r < e.m_rows) {
+      float* dst = e.c + (size_t)r * e.ldc + col0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < e.n_cols) dst[i] = v[i] * e.alpha;
+    }
+  } else if (EPI == EPI_CONV1) {
+    const int n = m_tile * 2 + (row >> 6);
+    if (n < e.n_patches) {
+      __align__(16) __half h[32];
+      __align__(16) __half l[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float y = fmaf(v[i], __ldg(e.scale + col0 + i), __ldg(e.bias + col0 + i)) * e.y_scale;
+        h[i] = __float2half_rn(y);
+        l[i] = __float2half_rn(y - __half2float(h[i]));
+      }
+      const size_t o = ((size_t)n * 64 + (row & 63)) * 512 + col0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(e.y_hi + o)[q] = reinterpret_cast<const uint4*>(h)[q];
+      if (e.y_lo != nullptr) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(e.y_lo + o)[q] = reinterpret_cast<const uint4*>(l)[q];
+      }
+    }
+  } else if (EPI == EPI_CONV2) {
+    // relu + max over the 32 rows held by this warp (half a patch); atomically merged in HBM
+    const int n = m_tile * 2 + (row >> 6);
+    const int lane = threadIdx.x & 31;
+    unsigned int mine = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float y = fmaxf(fmaf(v[i], __ldg(e.scale + col0 + i), __ldg(e.bias + col0 + i)), 0.f);
+      const unsigned int m = __reduce_max_sync(0xffffffffu, __float_as_uint(y));
+      if (lane == i) mine = m;
+    }
+    if (n < e.n_patches) atomicMax(reinterpret_cast<unsigned int*>(e.pooled) + (size_t)n * 512 + col0 + lane, mine);
+  } else if (EPI == EPI_CORR) {
+    // rows/cols are in pooling-window order: 4 rows x 4 cols = one 4D window
+    const int lane = threadIdx.x & 31;
+    const int pa = m_tile * 128 + row;
+    const int ca = pa >> 2, mi = pa & 3;
+#pragma unroll
+    for (int cell = 0; cell < 8; ++cell) {
+      float best = v[cell * 4];
+      int code = mi * 4;
+#pragma unroll
+      for (int j = 1; j < 4; ++j)
+        if (v[cell * 4 + j] > best) {
+          best = v[cell * 4 + j];
+          code = mi * 4 + j;
+        }
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {
+        const float b2 = __shfl_xor_sync(0xffffffffu, best, o);
+        const int c2 = __shfl_xor_sync(0xffffffffu, code, o);
+        if (b2 > best || (b2 == best && c2 < code)) {
+          best = b2;
+          code = c2;
+        }
+      }
+      const int cb = (col0 >> 2) + cell;
+      if ((lane & 3) == 0 && ca < e.np1 && cb < e.np2) {
+        e.c[(size_t)ca * e.np2 + cb] = best * e.alpha;
+        e.code[(size_t)ca * e.np2 + cb] = (uint8_t)code;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int kATile = 128 * 128;   // 128 rows x 64 fp16
+constexpr int kBTile = 256 * 128;   // 256 rows x 64 fp16
+
+template <int PASSES, bool SEGMENTED, int EPI>
+__global__ void __launch_bounds__(384, 1) umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p) {
+  constexpr int STAGES = (PASSES == 3) ? 2 : 4;
+  constexpr int NOP = (PASSES == 3) ? 2 : 1;
+  constexpr int STAGE_BYTES = NOP * (kATile + kBTile);
+  constexpr uint32_t IDESC = make_idesc_f16(128, 256);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int nsteps = p.nsteps;
+  const int seg_len = SEGMENTED ? p.seg_len : nsteps;
+  const int nseg = (nsteps + seg_len - 1) / seg_len;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a_main_hi);
+    tma_prefetch_desc(&p.b_hi);
+    if (PASSES == 3) {
+      tma_prefetch_desc(&p.a_main_lo);
+      tma_prefetch_desc(&p.b_lo);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp < 4) {
+    if (SEGMENTED) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+        for (int ks = 0; ks < nsteps; ++ks, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          const KStep k = p.steps[ks];  // param space (constant bank)
+          uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          const int a4 = m_tile * p.a_units_per_tile;
+          if (k.kind == 0) {
+            tma_load_5d(&p.a_main_hi, &full_bar[s], st, k.c0, k.x, k.y, k.plane, a4);
+            if (PASSES == 3) tma_load_5d(&p.a_main_lo, &full_bar[s], st + kATile, k.c0, k.x, k.y, k.plane, a4);
+          } else {
+            tma_load_5d(&p.a_rgb_hi, &full_bar[s], st, 0, 0, 0, 0, a4);
+            if (PASSES == 3) tma_load_5d(&p.a_rgb_lo, &full_bar[s], st + kATile, 0, 0, 0, 0, a4);
+          }
+          tma_load_2d(&p.b_hi, &full_bar[s], st + NOP * kATile, k.bk, n_tile * 256);
+          if (PASSES == 3) tma_load_2d(&p.b_lo, &full_bar[s], st + NOP * kATile + kBTile, k.bk, n_tile * 256);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int it = 0, seg = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        uint32_t d_tmem = 0;
+        for (int ks = 0; ks < nsteps; ++ks, ++it) {
+          const bool seg_start = (ks % seg_len) == 0;
+          if (seg_start) {
+            const int slot = seg & 1;
+            const uint32_t sph = (uint32_t)(seg >> 1) & 1u;
+            mbar_wait(&tempty_bar[slot], sph ^ 1u);
+            tc_fence_after();
+            d_tmem = tmem_base + (uint32_t)slot * 256u;
+          }
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+          const uint64_t a_hi = make_sw128_desc(sa);
+          const uint64_t b_hi = make_sw128_desc(sa + NOP * kATile);
+          uint32_t acc = seg_start ? 0u : 1u;
+          if (PASSES == 3) {
+            const uint64_t a_lo = make_sw128_desc(sa + kATile);
+            const uint64_t b_lo = make_sw128_desc(sa + NOP * kATile + kBTile);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              umma_f16(d_tmem, a_lo + 2 * kk, b_hi + 2 * kk, IDESC, acc);
+              acc = 1u;
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) umma_f16(d_tmem, a_hi + 2 * kk, b_lo + 2 * kk, IDESC, 1u);
+          }
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            umma_f16(d_tmem, a_hi + 2 * kk, b_hi + 2 * kk, IDESC, acc);
+            acc = 1u;
+          }
+          umma_commit(&empty_bar[s]);
+          const bool seg_end = ((ks + 1) % seg_len) == 0 || (ks + 1) == nsteps;
+          if (seg_end) {
+            umma_commit(&tfull_bar[seg & 1]);
+            ++seg;
+          }
+        }
+      }
+    }
+  }
+  } else {
+    // ===================== epilogue =====================
+    if (SEGMENTED) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    const int q = warp & 3, hf = (warp - 4) >> 2;
+    const int row = q * 32 + lane;
+    int seg = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      const int colbase = n_tile * 256 + hf * 128;
+      if (SEGMENTED) {
+        float tot[128];
+#pragma unroll
+        for (int i = 0; i < 128; ++i) tot[i] = 0.f;
+        for (int sg = 0; sg < nseg; ++sg, ++seg) {
+          const int slot = seg & 1;
+          const uint32_t sph = (uint32_t)(seg >> 1) & 1u;
+          mbar_wait(&tfull_bar[slot], sph);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 256 + hf * 128);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float v[32];
+            tmem_ld32(taddr + c * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) tot[c * 32 + i] += v[i];
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[slot]);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) epilogue_piece<EPI>(p.epi, m_tile, row, colbase + c * 32, tot + c * 32);
+      } else {
+        const int slot = seg & 1;
+        const uint32_t sph = (uint32_t)(seg >> 1) & 1u;
+        mbar_wait(&tfull_bar[slot], sph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 256 + hf * 128);
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float v[32];
+          tmem_ld32(taddr + c * 32, v);
+          epilogue_piece<EPI>(p.epi, m_tile, row, colbase + c * 32, v);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[slot]);
+        ++seg;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode_fn() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  }
+  return fn;
+}
+
+int make_tmap_fp16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  PFN_tmapEncodeTiled fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_last_error("cuTensorMapEncodeTiled is not available from the driver");
+    return -2;
+  }
+  cuuint64_t gd[5];
+  cuuint64_t gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return -2;
+  }
+  return 0;
+}
+
+template <int PASSES, bool SEGMENTED, int EPI>
+static int launch_one(const UmmaGemmParams& p, int grid, cudaStream_t st) {
+  constexpr int STAGES = (PASSES == 3) ? 2 : 4;
+  constexpr int NOP = (PASSES == 3) ? 2 : 1;
+  const int smem = STAGES * NOP * (kATile + kBTile) + 1024;
+  auto kern = umma_gemm_kernel<PASSES, SEGMENTED, EPI>;
+  P2P_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<grid, 384, smem, st>>>(p);
+  P2P_LAUNCH_OK();
+  return 0;
+}
+
+template <int EPI>
+static int launch_epi(const UmmaGemmParams& p, int passes, bool seg, int grid, cudaStream_t st) {
+  if (passes == 3) return seg ? launch_one<3, true, EPI>(p, grid, st) : launch_one<3, false, EPI>(p, grid, st);
+  return seg ? launch_one<1, true, EPI>(p, grid, st) : launch_one<1, false, EPI>(p, grid, st);
+}
+
+int launch_umma_gemm(const UmmaGemmParams& p, int epi, int passes, int num_sms, cudaStream_t st) {
+  P2P_REQUIRE(passes == 1 || passes == 3, "umma gemm: passes must be 1 or 3");
+  P2P_REQUIRE(p.nsteps > 0 && p.m_tiles > 0 && p.n_tiles > 0, "umma gemm: empty problem");
+  const bool seg = p.seg_len > 0 && p.seg_len < p.nsteps;
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < num_sms ? total : num_sms;
+  switch (epi) {
+    case EPI_PLAIN: return launch_epi<EPI_PLAIN>(p, passes, seg, grid, st);
+    case EPI_CONV1: return launch_epi<EPI_CONV1>(p, passes, seg, grid, st);
+    case EPI_CONV2: return launch_epi<EPI_CONV2>(p, passes, seg, grid, st);
+    case EPI_CORR: return launch_epi<EPI_CORR>(p, passes, seg, grid, st);
+  }
+  set_last_error("umma gemm: unknown epilogue");
+  return -1;
+}
+
+}  // namespace p2p

@@ -1,0 +1,45 @@
+// Parameters of the tcgen05 implicit-GEMM kernel (umma_gemm.cu).
+#pragma once
+#include <cuda.h>
+
+#include "kernels.h"
+
+namespace p2p {
+
+enum { EPI_PLAIN = 0, EPI_CONV1 = 1, EPI_CONV2 = 2, EPI_CORR = 3 };
+constexpr int kMaxKSteps = 96;
+
+struct UmmaEpilogue {
+  // EPI_PLAIN / EPI_CORR output
+  float* c;
+  int ldc, m_rows, n_cols;
+  float alpha;
+  // EPI_CORR: pooled grid sizes and the argmax code
+  uint8_t* code;
+  int np1, np2;
+  // EPI_CONV1 / EPI_CONV2
+  const float* scale;   // [512]
+  const float* bias;    // [512]
+  float y_scale;
+  __half* y_hi;
+  __half* y_lo;
+  float* pooled;
+  int n_patches;
+};
+
+struct UmmaGemmParams {
+  CUtensorMap a_main_hi, a_main_lo, a_rgb_hi, a_rgb_lo, b_hi, b_lo;
+  KStep steps[kMaxKSteps];
+  int nsteps;
+  int m_tiles;           // 128-row tiles
+  int n_tiles;           // 256-column tiles
+  int a_units_per_tile;  // step of the outermost A coordinate per m-tile (2 patches, or 128 rows)
+  int seg_len;           // k-steps accumulated in TMEM before a drain (0 / >= nsteps: whole K)
+  UmmaEpilogue epi;
+};
+
+int make_tmap_fp16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box);
+int launch_umma_gemm(const UmmaGemmParams& p, int epi, int passes, int num_sms, cudaStream_t st);
+
+}  // namespace p2p

@@ -1,0 +1,129 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every declared symbol, the host
+mirror refuses to run without CUDA, the pair sharder works over gloo with world_size 2, and the
+bench reference arm prints a well-formed line."""
+import json
+import os
+import re
+import subprocess
+import sys
+from argparse import Namespace
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    from patch2pix_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'p2p_b200.h')).read()
+    declared = re.findall(r'P2P_API\s+[\w\s\*]+?\b(p2p_\w+)\s*\(', hdr)
+    assert len(declared) >= 18
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in include/p2p_b200.h but not exported'
+        assert name in _lib.EXPORTED_SYMBOLS, f'{name} has no ctypes signature'
+    assert lib.p2p_version() == 100
+    assert lib.p2p_last_error() is not None
+
+
+def test_c_abi_rejects_bad_arguments_without_a_gpu():
+    from patch2pix_b200 import _lib
+    lib = _lib.load()
+    assert lib.p2p_destroy(None) == 0
+    assert lib.p2p_set_option(None, b'mid_passes', 3) == -1
+    assert b'null' in lib.p2p_last_error()
+    import ctypes as C
+    h = C.c_void_p()
+    rc = lib.p2p_create(0, C.byref(h))
+    if not torch.cuda.is_available():
+        assert rc != 0 and lib.p2p_last_error()
+
+
+def test_host_mirror_has_no_cpu_fallback():
+    from patch2pix_b200.model import Patch2PixB200, filter_coarse
+    cfg = Namespace(training=False, device='cpu', regr_batch=1200, backbone='ResNet34', feat_idx=[0, 1, 2, 3],
+                    weights_dict=None, change_stride=True, regressor_config=None)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        Patch2PixB200(cfg)
+    with pytest.raises(RuntimeError):
+        filter_coarse([torch.zeros(4, 4, dtype=torch.int64)], [torch.zeros(4)])
+    cfg.training = True
+    with pytest.raises(RuntimeError, match='inference'):
+        Patch2PixB200(cfg)
+
+
+def test_seeded_state_dict_matches_reference_names(seeded_sd):
+    sd = seeded_sd
+    assert tuple(sd['ncn.conv.0.weight'].shape) == (3, 16, 1, 3, 3, 3)
+    assert tuple(sd['ncn.conv.2.weight'].shape) == (3, 1, 16, 3, 3, 3)
+    assert tuple(sd['regress_mid.conv.0.weight'].shape) == (512, 518, 3, 3)
+    assert tuple(sd['regress_fine.fc.6.weight'].shape) == (5, 256)
+    assert 'extract.layer3.0.downsample.1.running_var' in sd
+    from patch2pix_b200.synth import make_seeded_state_dict, synthetic_pair
+    sd2 = make_seeded_state_dict(0)
+    assert all(torch.equal(sd[k], sd2[k]) for k in sd)
+    a, b = synthetic_pair(3, 96, 128)
+    a2, _ = synthetic_pair(3, 96, 128)
+    assert a.shape == (1, 3, 96, 128) and torch.equal(a, a2) and not torch.equal(a, b)
+
+
+def test_backbone_matches_oracle_on_cpu(seeded_sd):
+    from oracle import p2p_oracle as O
+    from patch2pix_b200.backbone import ResNet34Features
+    from patch2pix_b200.synth import synthetic_pair
+    net = ResNet34Features(True).eval()
+    sd = {k[len('extract.'):]: v for k, v in seeded_sd.items() if k.startswith('extract.')}
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not unexpected and all('num_batches_tracked' in m for m in missing)
+    im, _ = synthetic_pair(1, 64, 96)
+    with torch.no_grad():
+        got = net.forward_all(im, [], True)
+        ref = O.backbone_forward_all(im, seeded_sd)
+    assert [tuple(t.shape) for t in got] == [(1, 3, 64, 96), (1, 64, 32, 48), (1, 64, 16, 24), (1, 128, 8, 12), (1, 256, 8, 12)]
+    for g, r in zip(got, ref):
+        torch.testing.assert_close(g, r, rtol=1e-4, atol=1e-5)
+
+
+def _shard_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from patch2pix_b200.sharding import PairSharder
+    sh = PairSharder(rank, world, 'cpu')
+    src = torch.arange(100, 112) if rank == 0 else torch.zeros(3, dtype=torch.int64)   # only rank 0's list counts
+    mine = sh.scatter_pair_indices(src)
+    local = torch.stack([torch.full((4, 5), float(p)) for p in mine.tolist()])          # [steps, patches, 5]
+    stacked = sh.gather_results(local)
+    flat = PairSharder.interleave(stacked)
+    q.put((rank, mine.tolist(), flat[:, 0, 0].tolist()))
+    dist.destroy_process_group()
+
+
+def test_pair_sharding_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert outs[0][1] == list(range(100, 112, 2)) and outs[1][1] == list(range(101, 112, 2))
+    assert outs[0][2] == [float(v) for v in range(100, 112)] == outs[1][2]
+
+
+def test_bench_reference_arm_line():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0',
+                        '--height', '96', '--width', '128', '--ptmax', '6', '--cpu-sample-patches', '8'],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['value'] > 0 and line['cpu_baseline']['kind'] == 'port'
+    assert line['e2e']['h2d_bytes_per_step'] == 0 and line['unit'] == 'pairs/s'

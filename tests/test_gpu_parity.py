@@ -1,0 +1,374 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via patch2pix_b200.model) against the CPU
+oracle on identical seeded inputs, against the committed golden vectors of the live reference,
+and -- at the benchmark size -- through size-independent properties.
+
+Tolerances (BASELINE.json north_star): proposal rows bit-exact (int64, incl. order), refined
+coordinates within 0.5 px, confidences within 1e-3.  The per-stage checks below are much tighter
+than that wherever the arithmetic is fp32-grade.
+"""
+import json
+import os
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+OUT = os.path.join(os.path.dirname(os.path.dirname(__file__)), 'gpurun_out')
+
+
+def _cfg(panc=1, regress=True):
+    rc = Namespace(conv_dims=[512, 512], conv_kers=[3, 3], conv_strs=[2, 1], fc_dims=[512, 256], feat_comb='pre',
+                   psize=[16, 16], pshift=8, panc=panc, shared=False) if regress else None
+    return Namespace(training=False, device='cuda:0', regr_batch=1200, backbone='ResNet34', feat_idx=[0, 1, 2, 3],
+                     weights_dict=None, change_stride=True, regressor_config=rc)
+
+
+@pytest.fixture(scope='module')
+def nets(seeded_sd):
+    from patch2pix_b200.model import Patch2PixB200
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    out = {}
+    for panc in (1, 8):
+        cfg = _cfg(panc)
+        cfg.weights_dict = seeded_sd
+        out[panc] = Patch2PixB200(cfg)
+    return out
+
+
+def _feats(net, pair_idx, H, W):
+    from patch2pix_b200.synth import synthetic_pair
+    im1, im2 = synthetic_pair(pair_idx, H, W)
+    with torch.no_grad():
+        f1 = net.extract.forward_all(im1.cuda(), [], early_feat=True)
+        f2 = net.extract.forward_all(im2.cuda(), [], early_feat=True)
+    return f1, f2, [t.cpu() for t in f1], [t.cpu() for t in f2]
+
+
+def _report(name, payload):
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, f'parity_{name}.json'), 'w') as f:
+        json.dump(payload, f, indent=1)
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 GEMM unit test + accumulation-accuracy probe
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('M,N,K', [(128, 256, 64), (200, 300, 256), (256, 512, 4672), (1000, 512, 1024)])
+def test_umma_gemm_matches_fp64(M, N, K):
+    from patch2pix_b200 import _lib
+    h = _lib.default_handle('cuda:0')
+    g = torch.Generator().manual_seed(M * 7 + K)
+    a = torch.randn(M, K, generator=g)
+    b = torch.randn(N, K, generator=g)
+    ref = (a.double() @ b.double().t())
+    scale = ref.abs().mean().item()
+    ad, bd = a.cuda(), b.cuda()
+    res = {}
+    for passes, seg, tol in ((1, 0, 3e-3), (3, 0, 2e-5), (3, 1, 3e-6), (3, 4, 3e-6), (1, 2, 3e-3)):
+        c = torch.full((M, N), float('nan'), device='cuda')
+        _lib.check(h.lib.p2p_test_gemm(h.h, _lib.ptr(ad), _lib.ptr(bd), _lib.ptr(c), M, N, K, passes, seg, 64.0,
+                                       h.stream()))
+        torch.cuda.synchronize()
+        err = (c.cpu().double() - ref).abs()
+        res[f'p{passes}_s{seg}'] = {'max': err.max().item() / scale, 'mean': err.mean().item() / scale,
+                                    'bias': ((c.cpu().double() - ref) * ref.sign()).mean().item() / scale}
+        assert torch.isfinite(c).all()
+        assert err.max().item() / scale < tol * max(1.0, (K / 256) ** 0.5), (passes, seg, res)
+    _report(f'gemm_{M}x{N}x{K}', res)
+
+
+def test_umma_gemm_positive_accumulation_drift():
+    """All-positive operands expose accumulator rounding (RZ vs RN) as a systematic bias."""
+    from patch2pix_b200 import _lib
+    h = _lib.default_handle('cuda:0')
+    M, N, K = 256, 256, 4608
+    g = torch.Generator().manual_seed(5)
+    a = torch.rand(M, K, generator=g) + 0.5
+    b = torch.rand(N, K, generator=g) + 0.5
+    ref = a.double() @ b.double().t()
+    ref32 = (a.cuda() @ b.cuda().t()).cpu().double()
+    ad, bd = a.cuda(), b.cuda()
+    res = {'fp32_cublas_rel_bias': ((ref32 - ref) / ref).mean().item()}
+    for passes, seg in ((3, 0), (3, 1), (3, 3), (3, 9)):
+        c = torch.empty(M, N, device='cuda')
+        _lib.check(h.lib.p2p_test_gemm(h.h, _lib.ptr(ad), _lib.ptr(bd), _lib.ptr(c), M, N, K, passes, seg, 64.0,
+                                       h.stream()))
+        rel = (c.cpu().double() - ref) / ref
+        res[f'p{passes}_s{seg}'] = {'rel_bias': rel.mean().item(), 'rel_absmax': rel.abs().max().item()}
+    _report('gemm_drift', res)
+    assert abs(res['p3_s1']['rel_bias']) < 2e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# coarse stage
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('pair_idx,H,W', [(3, 96, 128), (5, 128, 96), (11, 160, 240)])
+@pytest.mark.parametrize('corr_passes', [0, 3])
+def test_coarse_stages_vs_oracle(nets, seeded_sd, pair_idx, H, W, corr_passes):
+    from oracle import p2p_oracle as O
+    from patch2pix_b200.model import filter_coarse
+    net = nets[1]
+    net.set_option('corr_passes', corr_passes)
+    try:
+        f1, f2, c1, c2 = _feats(net, pair_idx, H, W)
+        with torch.no_grad():
+            st = {}
+            o_corr, o_delta = O.forward_coarse_match(c1[-1], c2[-1], seeded_sd, ksize=2, stages=st)
+            corr4d, delta4d, stages = net.forward_coarse_match(f1[-1], f2[-1], ksize=2, return_stages=True)
+            torch.cuda.synchronize()
+            assert corr4d.shape == o_corr.shape and len(delta4d) == 4 and delta4d[0].dtype == torch.int64
+            np.testing.assert_allclose(stages['pooled'].cpu().numpy(), st['pooled'].numpy(), rtol=2e-5, atol=2e-6)
+            for d, od in zip(delta4d, o_delta):
+                assert torch.equal(d.cpu(), od)
+            np.testing.assert_allclose(stages['ncn'].cpu().numpy(), st['ncn'].numpy(), rtol=2e-4, atol=2e-6)
+            np.testing.assert_allclose(corr4d.cpu().numpy(), o_corr.numpy(), rtol=5e-4, atol=1e-7)
+            o_m, o_s = O.cal_coarse_matches(o_corr, o_delta, ksize=2, upsample=8, center=True)
+            m, s = net.cal_coarse_matches(corr4d, delta4d, ksize=2, upsample=net.upsample, center=True)
+            assert m.dtype == torch.int64 and torch.equal(m.cpu(), o_m)
+            np.testing.assert_allclose(s.cpu().numpy(), o_s.numpy(), rtol=1e-4)
+            fm, fs = filter_coarse(m, s, 0.0, True)
+            ofm, ofs = O.filter_coarse(o_m, o_s, 0.0, True)
+            assert torch.equal(fm[0].cpu(), ofm[0])
+            np.testing.assert_allclose(fs[0].cpu().numpy(), ofs[0].numpy(), rtol=1e-4)
+            # same kernels fed with the ORACLE's corr4d/delta (reference-shaped inputs from outside)
+            m2, s2 = net.cal_coarse_matches(o_corr.cuda(), tuple(d.cuda() for d in o_delta), ksize=2, upsample=8)
+            assert torch.equal(m2.cpu(), o_m)
+    finally:
+        net.set_option('corr_passes', 0)
+
+
+def test_coarse_ksize1_vs_oracle(nets, seeded_sd):
+    from oracle import p2p_oracle as O
+    net = nets[1]
+    f1, f2, c1, c2 = _feats(net, 2, 64, 96)
+    with torch.no_grad():
+        o_corr, o_delta = O.forward_coarse_match(c1[-1], c2[-1], seeded_sd, ksize=1)
+        corr4d, delta4d = net.forward_coarse_match(f1[-1], f2[-1], ksize=1)
+        assert delta4d is None and o_delta is None
+        np.testing.assert_allclose(corr4d.cpu().numpy(), o_corr.numpy(), rtol=5e-4, atol=1e-7)
+        o_m, o_s = O.cal_coarse_matches(o_corr, None, ksize=1, upsample=8, center=True)
+        m, s = net.cal_coarse_matches(corr4d, None, ksize=1, upsample=8, center=True)
+        assert torch.equal(m.cpu(), o_m)
+
+
+def test_mutual_matching_and_unique_rows_ops():
+    from oracle import p2p_oracle as O
+    from patch2pix_b200.model import mutual_matching, unique_rows
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(1, 1, 5, 7, 6, 4, generator=g) - 0.2
+    got = mutual_matching(x.cuda()).cpu()
+    np.testing.assert_allclose(got.numpy(), O.mutual_matching(x).numpy(), rtol=1e-6, atol=1e-8)
+    rows = torch.randint(0, 6, (5000, 4), generator=g) * 8 + 4
+    for mutual in (True, False):
+        ids = unique_rows(rows.cuda(), mutual).cpu().numpy()
+        _, ref_ids, counts = np.unique(rows.numpy(), axis=0, return_index=True, return_counts=True)
+        if mutual:
+            ref_ids = ref_ids[counts > 1]
+        assert np.array_equal(ids, ref_ids)
+    assert len(unique_rows(torch.tensor([[1, 2, 3, 4], [4, 3, 2, 1]]).cuda(), True)) == 0
+    with pytest.raises(RuntimeError):
+        unique_rows(torch.tensor([[-1, 2, 3, 4]]).cuda(), True)
+
+
+# ------------------------------------------------------------------------------------------------
+# refine stage
+# ------------------------------------------------------------------------------------------------
+def _refine_case(net, sd, pair_idx, H, W, matches, impl, mid_passes, fine_passes):
+    from oracle import p2p_oracle as O
+    f1, f2, c1, c2 = _feats(net, pair_idx, H, W)
+    net.set_option('gemm_impl', impl)
+    net.set_option('mid_passes', mid_passes)
+    net.set_option('fine_passes', fine_passes)
+    try:
+        with torch.no_grad():
+            o_mid, o_midp = O.forward_fine_match(c1, c2, [matches], sd, 'regress_mid.')
+            o_fine, o_finep = O.forward_fine_match(c1, c2, o_mid, sd, 'regress_fine.')
+            mid, midp = net.forward_fine_match(f1, f2, [matches.cuda()], 16, 'center', net.regress_mid)
+            fine_same, finep_same = net.forward_fine_match(f1, f2, [o_mid[0].cuda()], 16, 'center', net.regress_fine)
+            fine_e2e, finep_e2e = net.forward_fine_match(f1, f2, mid, 16, 'center', net.regress_fine)
+            torch.cuda.synchronize()
+    finally:
+        net.set_option('gemm_impl', 0)
+        net.set_option('mid_passes', 3)
+        net.set_option('fine_passes', 1)
+    r = {
+        'mid_err': (mid[0].cpu() - o_mid[0]).abs().max().item(),
+        'mid_p_err': (midp[0].cpu() - o_midp[0]).abs().max().item(),
+        'fine_same_err': (fine_same[0].cpu() - o_fine[0]).abs().max().item(),
+        'fine_same_p_err': (finep_same[0].cpu() - o_finep[0]).abs().max().item(),
+        'straddle_rows': int((mid[0].cpu().long() != o_mid[0].long()).any(1).sum()),
+        'n': int(matches.shape[0]),
+    }
+    e2e = (fine_e2e[0].cpu() - o_fine[0]).abs().max(1)[0]
+    strad = (mid[0].cpu().long() != o_mid[0].long()).any(1)
+    r['fine_e2e_err_nonstraddle'] = e2e[~strad].max().item() if (~strad).any() else 0.0
+    r['fine_e2e_p_err_nonstraddle'] = (finep_e2e[0].cpu() - o_finep[0]).abs()[~strad].max().item() if (~strad).any() else 0.0
+    return r
+
+
+def _random_matches(n, H, W, seed, integer):
+    g = torch.Generator().manual_seed(seed)
+    m = torch.rand(n, 4, generator=g) * torch.tensor([W, H, W, H]) * 1.1 - 0.05 * torch.tensor([W, H, W, H])
+    m[0] = torch.tensor([0.0, 0.0, W - 1.0, H - 1.0])
+    if n > 1:
+        m[1] = torch.tensor([W + 3.0, -2.5, 7.999, 8.0])
+    return m.long() if integer else m
+
+
+@pytest.mark.parametrize('impl,mid_passes,fine_passes', [(1, 3, 3), (0, 3, 3), (0, 3, 1), (0, 1, 1)])
+@pytest.mark.parametrize('integer', [True, False])
+def test_refine_vs_oracle(nets, seeded_sd, impl, mid_passes, fine_passes, integer):
+    net = nets[1]
+    H, W = 128, 160
+    r = _refine_case(net, seeded_sd, 9, H, W, _random_matches(77, H, W, 3, integer), impl, mid_passes, fine_passes)
+    _report(f'refine_impl{impl}_m{mid_passes}_f{fine_passes}_{"i" if integer else "f"}', r)
+    mid_tol = 2e-4 if mid_passes == 3 else 0.05
+    fine_tol = 2e-4 if fine_passes == 3 else 0.05
+    assert r['mid_err'] < mid_tol, r
+    assert r['fine_same_err'] < fine_tol, r
+    assert r['mid_p_err'] < 1e-3 and r['fine_same_p_err'] < 1e-3, r
+    assert r['fine_e2e_err_nonstraddle'] < 0.5 and r['fine_e2e_p_err_nonstraddle'] < 1e-3, r
+    if mid_passes == 3:
+        assert r['straddle_rows'] == 0, r
+
+
+@pytest.mark.parametrize('n', [1, 2, 3, 129, 1201])
+def test_refine_ragged_sizes(nets, seeded_sd, n):
+    net = nets[1]
+    H, W = 96, 128
+    r = _refine_case(net, seeded_sd, 4, H, W, _random_matches(n, H, W, n, True), 0, 3, 1)
+    assert r['mid_err'] < 2e-4 and r['fine_same_err'] < 0.05 and r['fine_same_p_err'] < 1e-3, r
+
+
+def test_refine_empty_and_errors(nets):
+    net = nets[1]
+    f1, f2, _, _ = _feats(net, 4, 96, 128)
+    out, pr = net.forward_fine_match(f1, f2, [torch.zeros(0, 4, dtype=torch.int64, device='cuda')], 16, 'center',
+                                     net.regress_mid)
+    assert out[0].shape == (0, 4) and pr[0].shape == (0,)
+    with pytest.raises(RuntimeError):
+        net.forward_fine_match(f1, f2, [torch.zeros(3, 4)], 16, 'center', net.regress_mid)      # CPU tensor
+    with pytest.raises(RuntimeError):
+        net.forward_fine_match(f1, f2, [torch.zeros(3, 4, device='cuda')], 8, 'center', net.regress_mid)  # psize
+    with pytest.raises(RuntimeError):
+        net.forward_coarse_match(f1[-1].cpu(), f2[-1].cpu(), ksize=2)
+
+
+# ------------------------------------------------------------------------------------------------
+# end to end sequences
+# ------------------------------------------------------------------------------------------------
+def _e2e(net, sd, pair_idx, H, W, ptmax, panc, np_seed=7):
+    from oracle import p2p_oracle as O
+    f1, f2, c1, c2 = _feats(net, pair_idx, H, W)
+    with torch.no_grad():
+        np.random.seed(np_seed)
+        o = O.hot_path_from_feats(c1, c2, sd, 2, 0.0, True, ptmax, panc, return_all=True)
+        np.random.seed(np_seed)
+        g = net.match_from_feats(f1, f2, 2, 0.0, True, ptmax, return_all=True)
+        torch.cuda.synchronize()
+    return o, g
+
+
+@pytest.mark.parametrize('pair_idx,H,W,ptmax,panc', [(3, 96, 128, None, 1), (6, 240, 320, None, 1), (3, 96, 128, 12, 8),
+                                                    (8, 240, 320, 50, 8)])
+def test_end_to_end_vs_oracle(nets, seeded_sd, pair_idx, H, W, ptmax, panc):
+    o, g = _e2e(nets[panc], seeded_sd, pair_idx, H, W, ptmax, panc)
+    o_fine, o_finep, o_mid, o_midp, o_cm = o
+    fine, finep, mid, midp, cm = g
+    assert cm[0].dtype == torch.int64 and torch.equal(cm[0].cpu(), o_cm[0]), 'proposals must be bit-exact'
+    strad = (mid[0].cpu().reshape(-1, 4).long() != o_mid[0].reshape(-1, 4).long()).any(1)
+    err = (fine[0].cpu().reshape(-1, 4) - o_fine[0].reshape(-1, 4)).abs().max(1)[0]
+    perr = (finep[0].cpu().reshape(-1) - o_finep[0].reshape(-1)).abs()
+    rep = {'n': int(err.numel()), 'straddle_rows': int(strad.sum()), 'max_err_px': err.max().item(),
+           'max_err_px_nonstraddle': err[~strad].max().item(), 'max_conf_err': perr[~strad].max().item(),
+           'mid_err': (mid[0].cpu().reshape(-1, 4) - o_mid[0].reshape(-1, 4)).abs().max().item()}
+    _report(f'e2e_{H}x{W}_pt{ptmax}_pa{panc}', rep)
+    assert rep['max_err_px_nonstraddle'] < 0.5 and rep['max_conf_err'] < 1e-3, rep
+    assert rep['straddle_rows'] <= max(1, rep['n'] // 500), rep
+
+
+@pytest.mark.parametrize('name', ['stages_96x128', 'stages_128x96'])
+def test_golden_reference_vectors(nets, name):
+    """CUDA path (incl. our cuDNN fp32 backbone) against outputs of the LIVE reference."""
+    from patch2pix_b200.synth import synthetic_pair
+    g = np.load(os.path.join(GOLD, name + '.npz'))
+    net = nets[1]
+    im1, im2 = synthetic_pair(int(g['pair_idx']), int(g['H']), int(g['W']))
+    with torch.no_grad():
+        fine, finep, mid, midp, coarse = net.predict_fine(im1.cuda(), im2.cuda(), ksize=2, return_all=True)
+        corr4d, delta4d = net.forward(im1.cuda(), im2.cuda(), ksize=2)
+    np.testing.assert_allclose(corr4d.cpu().numpy(), g['corr4d'], rtol=2e-3, atol=1e-6)
+    assert np.array_equal(torch.stack([d.cpu() for d in delta4d]).numpy().astype(np.int8), g['delta'])
+    assert np.array_equal(coarse[0].cpu().numpy(), g['coarse'])
+    assert np.abs(fine[0].cpu().numpy().reshape(-1, 4) - g['fine']).max() < 0.5
+    assert np.abs(finep[0].cpu().numpy().reshape(-1) - g['fine_p']).max() < 1e-3
+
+
+def test_golden_train_sequence_and_refine_only(nets):
+    from patch2pix_b200.synth import synthetic_pair
+    g = np.load(os.path.join(GOLD, 'trainseq_96x128.npz'))
+    net = nets[8]
+    im1, im2 = synthetic_pair(int(g['pair_idx']), int(g['H']), int(g['W']))
+    with torch.no_grad():
+        f1 = net.extract.forward_all(im1.cuda(), [], True)
+        f2 = net.extract.forward_all(im2.cuda(), [], True)
+        np.random.seed(int(g['np_seed']))
+        fine, finep, mid, midp, anchors = net.match_from_feats(f1, f2, 2, ptmax=int(g['ptmax']), return_all=True)
+    assert np.array_equal(anchors[0].cpu().numpy(), g['anchors'])
+    assert np.abs(mid[0].cpu().numpy() - g['mid']).max() < 1e-2
+    assert np.abs(fine[0].cpu().numpy() - g['fine']).max() < 0.5
+    assert np.abs(finep[0].cpu().numpy() - g['fine_p']).max() < 1e-3
+    g = np.load(os.path.join(GOLD, 'refine_128x160.npz'))
+    net = nets[1]
+    im1, im2 = synthetic_pair(int(g['pair_idx']), int(g['H']), int(g['W']))
+    with torch.no_grad():
+        r, s, c = net.refine_matches(im1.cuda(), im2.cuda(), torch.from_numpy(g['coarse_in']).cuda(), io_thres=0.0)
+        rt, st, ct = net.refine_matches(im1.cuda(), im2.cuda(), g['coarse_in'], io_thres=0.5)
+    assert np.abs(r - g['refined']).max() < 0.5 and np.abs(s - g['scores']).max() < 1e-3
+    assert rt.shape == g['refined_t'].shape and np.abs(ct - g['coarse_t']).max() == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# benchmark size (640x480, ptmax 400, panc 8): oracle for the coarse stage, properties for the rest
+# ------------------------------------------------------------------------------------------------
+def test_full_size_640x480(nets, seeded_sd):
+    from oracle import p2p_oracle as O
+    net = nets[8]
+    H, W = 480, 640
+    f1, f2, c1, c2 = _feats(net, 0, H, W)
+    with torch.no_grad():
+        o_corr, o_delta = O.forward_coarse_match(c1[-1], c2[-1], seeded_sd, ksize=2)
+        o_m, o_s = O.cal_coarse_matches(o_corr, o_delta, ksize=2, upsample=8, center=True)
+        np.random.seed(11)
+        o_cm, _ = O.filter_coarse(o_m, o_s, 0.0, True, ptmax=400)
+        o_anch = O.shift_to_anchors(o_cm, 8)
+        np.random.seed(11)
+        fine, finep, mid, midp, anch = net.match_from_feats(f1, f2, 2, ptmax=400, return_all=True)
+        torch.cuda.synchronize()
+        assert anch[0].shape == (3200, 4) and torch.equal(anch[0].cpu(), o_anch[0]), 'proposals must be bit-exact'
+        # properties of the refine outputs
+        fm, pm = fine[0].cpu(), finep[0].cpu()
+        assert fm.shape == (3200, 4) and pm.shape == (3200,)
+        assert (fm[:, 0::2] >= 0).all() and (fm[:, 0::2] <= W).all() and (fm[:, 1::2] >= 0).all() and (fm[:, 1::2] <= H).all()
+        assert (pm > 0).all() and (pm < 1).all()
+        assert ((mid[0].cpu() - anch[0].cpu().float()).abs() <= 8.0 + 1e-4).all()   # offsets live in [-8, 8)
+        # run-to-run determinism
+        np.random.seed(11)
+        fine2, finep2, _, _, _ = net.match_from_feats(f1, f2, 2, ptmax=400, return_all=True)
+        assert torch.equal(fine2[0], fine[0]) and torch.equal(finep2[0], finep[0])
+        # oracle on a subsample of the patches
+        idx = torch.arange(0, 3200, 25)
+        o_mid, _ = O.forward_fine_match(c1, c2, [o_anch[0][idx]], seeded_sd, 'regress_mid.')
+        o_fine, o_fp = O.forward_fine_match(c1, c2, o_mid, seeded_sd, 'regress_fine.')
+        strad = (mid[0].cpu()[idx].long() != o_mid[0].long()).any(1)
+        err = (fm[idx] - o_fine[0]).abs().max(1)[0]
+        rep = {'n_sub': int(idx.numel()), 'straddle_rows': int(strad.sum()), 'max_err_px_nonstraddle': err[~strad].max().item(),
+               'max_conf_err': (pm[idx] - o_fp[0]).abs()[~strad].max().item(),
+               'mid_err': (mid[0].cpu()[idx] - o_mid[0]).abs().max().item()}
+        _report('full_640x480', rep)
+        assert rep['max_err_px_nonstraddle'] < 0.5 and rep['max_conf_err'] < 1e-3 and rep['straddle_rows'] <= 1, rep
