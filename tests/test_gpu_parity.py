@@ -108,7 +108,7 @@ def test_umma_gemm_positive_accumulation_drift():
 # coarse stage
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize('pair_idx,H,W', [(3, 96, 128), (5, 128, 96), (11, 160, 240)])
-@pytest.mark.parametrize('corr_passes', [0, 3])
+@pytest.mark.parametrize('corr_passes', [0, 3], ids=['simtcorr', 'tccorr'])
 def test_coarse_stages_vs_oracle(nets, seeded_sd, pair_idx, H, W, corr_passes):
     from oracle import p2p_oracle as O
     from patch2pix_b200.model import filter_coarse
@@ -220,7 +220,8 @@ def _random_matches(n, H, W, seed, integer):
     return m.long() if integer else m
 
 
-@pytest.mark.parametrize('impl,mid_passes,fine_passes', [(1, 3, 3), (0, 3, 3), (0, 3, 1), (0, 1, 1)])
+@pytest.mark.parametrize('impl,mid_passes,fine_passes', [(1, 3, 3), (0, 3, 3), (0, 3, 1), (0, 1, 1)],
+                         ids=['simt33', 'tc33', 'tc31', 'tc11'])
 @pytest.mark.parametrize('integer', [True, False])
 def test_refine_vs_oracle(nets, seeded_sd, impl, mid_passes, fine_passes, integer):
     net = nets[1]
