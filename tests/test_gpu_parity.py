@@ -60,6 +60,10 @@ def _report(name, payload):
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize('M,N,K', [(128, 256, 64), (200, 300, 256), (256, 512, 4672), (1000, 512, 1024)])
 def test_umma_gemm_matches_fp64(M, N, K):
+    """tcgen05 GEMM vs fp64.  Errors are normalised by mean |C|.  Expected levels (measured, see
+    profiles/): 1-pass ~3e-4 mean (fp16 operand rounding); 3-pass with whole-K TMEM accumulation drifts
+    with K because the tensor core truncates (RZ) on every accumulate; 3-pass with short RN-accumulated
+    segments is fp32-grade."""
     from patch2pix_b200 import _lib
     h = _lib.default_handle('cuda:0')
     g = torch.Generator().manual_seed(M * 7 + K)
@@ -68,8 +72,11 @@ def test_umma_gemm_matches_fp64(M, N, K):
     ref = (a.double() @ b.double().t())
     scale = ref.abs().mean().item()
     ad, bd = a.cuda(), b.cuda()
-    res = {}
-    for passes, seg, tol in ((1, 0, 3e-3), (3, 0, 2e-5), (3, 1, 3e-6), (3, 4, 3e-6), (1, 2, 3e-3)):
+    ref32 = (ad @ bd.t()).cpu().double()
+    res = {'cublas_fp32': {'max': (ref32 - ref).abs().max().item() / scale, 'mean': (ref32 - ref).abs().mean().item() / scale}}
+    limits = {(1, 0): (1e-3, 6e-3), (1, 2): (1e-3, 6e-3), (3, 0): (3e-7 + 4e-9 * K, 2e-5 + 3e-8 * K),
+              (3, 1): (4e-7, 2e-5), (3, 4): (1.5e-6, 3e-5)}
+    for (passes, seg), (mean_tol, max_tol) in limits.items():
         c = torch.full((M, N), float('nan'), device='cuda')
         _lib.check(h.lib.p2p_test_gemm(h.h, _lib.ptr(ad), _lib.ptr(bd), _lib.ptr(c), M, N, K, passes, seg, 64.0,
                                        h.stream()))
@@ -78,7 +85,7 @@ def test_umma_gemm_matches_fp64(M, N, K):
         res[f'p{passes}_s{seg}'] = {'max': err.max().item() / scale, 'mean': err.mean().item() / scale,
                                     'bias': ((c.cpu().double() - ref) * ref.sign()).mean().item() / scale}
         assert torch.isfinite(c).all()
-        assert err.max().item() / scale < tol * max(1.0, (K / 256) ** 0.5), (passes, seg, res)
+        assert err.mean().item() / scale < mean_tol and err.max().item() / scale < max_tol, (passes, seg, res)
     _report(f'gemm_{M}x{N}x{K}', res)
 
 
@@ -107,6 +114,23 @@ def test_umma_gemm_positive_accumulation_drift():
 # ------------------------------------------------------------------------------------------------
 # coarse stage
 # ------------------------------------------------------------------------------------------------
+def _delta_mismatch_report(delta4d, o_delta, c1, c2, tie_eps=1e-6):
+    """Cells where our pooling argmax differs from the oracle's are legitimate only where the
+    oracle's own top-2 gap inside the 2^4 window is within fp32 rounding noise of a tie."""
+    from oracle import p2p_oracle as O
+    ours = torch.stack([d.cpu() for d in delta4d])
+    ref = torch.stack(list(o_delta))
+    bad = (ours != ref).any(0)
+    if not bad.any():
+        return 0, 0
+    corr = O.feat_correlation_4d(O.l2_normalize(c1, 1), O.l2_normalize(c2, 1))
+    sl = torch.cat([corr[:, :, i::2, j::2, k::2, l::2] for i in range(2) for j in range(2) for k in range(2) for l in range(2)], 1)
+    top2 = sl.topk(2, dim=1)[0]
+    gap = (top2[:, 0] - top2[:, 1]).unsqueeze(1)
+    unexplained = bad & (gap > tie_eps)
+    return int(bad.sum()), int(unexplained.sum())
+
+
 @pytest.mark.parametrize('pair_idx,H,W', [(3, 96, 128), (5, 128, 96), (11, 160, 240)])
 @pytest.mark.parametrize('corr_passes', [0, 3], ids=['simtcorr', 'tccorr'])
 def test_coarse_stages_vs_oracle(nets, seeded_sd, pair_idx, H, W, corr_passes):
@@ -122,22 +146,26 @@ def test_coarse_stages_vs_oracle(nets, seeded_sd, pair_idx, H, W, corr_passes):
             corr4d, delta4d, stages = net.forward_coarse_match(f1[-1], f2[-1], ksize=2, return_stages=True)
             torch.cuda.synchronize()
             assert corr4d.shape == o_corr.shape and len(delta4d) == 4 and delta4d[0].dtype == torch.int64
-            np.testing.assert_allclose(stages['pooled'].cpu().numpy(), st['pooled'].numpy(), rtol=2e-5, atol=2e-6)
-            for d, od in zip(delta4d, o_delta):
-                assert torch.equal(d.cpu(), od)
+            np.testing.assert_allclose(stages['pooled'].cpu().numpy(), st['pooled'].numpy(), rtol=0, atol=1e-6)
+            n_bad, n_unexplained = _delta_mismatch_report(delta4d, o_delta, c1[-1], c2[-1])
+            assert n_unexplained == 0 and n_bad <= max(2, delta4d[0].numel() // 500), (n_bad, n_unexplained)
             np.testing.assert_allclose(stages['ncn'].cpu().numpy(), st['ncn'].numpy(), rtol=2e-4, atol=2e-6)
             np.testing.assert_allclose(corr4d.cpu().numpy(), o_corr.numpy(), rtol=5e-4, atol=1e-7)
+            # proposal kernels on reference-shaped inputs from outside (the ORACLE's corr4d/delta): exact
             o_m, o_s = O.cal_coarse_matches(o_corr, o_delta, ksize=2, upsample=8, center=True)
-            m, s = net.cal_coarse_matches(corr4d, delta4d, ksize=2, upsample=net.upsample, center=True)
-            assert m.dtype == torch.int64 and torch.equal(m.cpu(), o_m)
-            np.testing.assert_allclose(s.cpu().numpy(), o_s.numpy(), rtol=1e-4)
-            fm, fs = filter_coarse(m, s, 0.0, True)
+            m2, s2 = net.cal_coarse_matches(o_corr.cuda(), tuple(d.cuda() for d in o_delta), ksize=2, upsample=8)
+            assert m2.dtype == torch.int64 and torch.equal(m2.cpu(), o_m)
+            np.testing.assert_allclose(s2.cpu().numpy(), o_s.numpy(), rtol=1e-4)
+            fm, fs = filter_coarse(m2, s2, 0.0, True)
             ofm, ofs = O.filter_coarse(o_m, o_s, 0.0, True)
             assert torch.equal(fm[0].cpu(), ofm[0])
             np.testing.assert_allclose(fs[0].cpu().numpy(), ofs[0].numpy(), rtol=1e-4)
-            # same kernels fed with the ORACLE's corr4d/delta (reference-shaped inputs from outside)
-            m2, s2 = net.cal_coarse_matches(o_corr.cuda(), tuple(d.cuda() for d in o_delta), ksize=2, upsample=8)
-            assert torch.equal(m2.cpu(), o_m)
+            # our own corr4d/delta: identical rows except where a pooling-window tie was broken differently
+            m, s = net.cal_coarse_matches(corr4d, delta4d, ksize=2, upsample=net.upsample, center=True)
+            diff_rows = int((m.cpu() != o_m).any(-1).sum())
+            assert diff_rows <= 2 * n_bad, (diff_rows, n_bad)
+            _report(f'coarse_{H}x{W}_{"tc" if corr_passes else "simt"}', {'delta_cells_differing': n_bad,
+                    'unexplained': n_unexplained, 'proposal_rows_differing': diff_rows, 'cells': int(delta4d[0].numel())})
     finally:
         net.set_option('corr_passes', 0)
 

@@ -20,9 +20,10 @@ for (M, N, K) in [(128, 256, 64), (128, 256, 128), (256, 512, 256)]:
     a[torch.arange(M), torch.arange(M) % K] = 1.0            # C[i][j] = B[j][i % K]
     b = (torch.arange(N).view(-1, 1) * 64 + torch.arange(K).view(1, -1)).float() / 64.0
     ref = a @ b.t()
+    ad, bd = a.cuda(), b.cuda()
     for passes, seg in ((1, 0), (3, 0), (3, 1)):
         c = torch.full((M, N), -7.0, device='cuda')
-        rc = h.lib.p2p_test_gemm(h.h, _lib.ptr(a.cuda()), _lib.ptr(b.cuda()), _lib.ptr(c), M, N, K, passes, seg, 8.0, h.stream())
+        rc = h.lib.p2p_test_gemm(h.h, _lib.ptr(ad), _lib.ptr(bd), _lib.ptr(c), M, N, K, passes, seg, 8.0, h.stream())
         key = f'{M}x{N}x{K}_p{passes}_s{seg}'
         if rc != 0:
             rep[key] = {'rc': rc, 'err': h.lib.p2p_last_error().decode()}
