@@ -58,7 +58,7 @@ using namespace p2p;
 struct p2p_handle_s {
   int device = 0;
   int num_sms = 148;
-  int opt_mid_passes = 3, opt_fine_passes = 1, opt_corr_passes = 0, opt_seg_len = 3, opt_gemm_impl = 0, opt_num_sms = 0;
+  int opt_mid_passes = 3, opt_fine_passes = 1, opt_corr_passes = 3, opt_seg_len = 3, opt_gemm_impl = 0, opt_num_sms = 0;
   bool nc_set = false;
   float *nc_w1p = nullptr, *nc_b1p = nullptr, *nc_w2p = nullptr;
   float nc_b2 = 0.f;

@@ -376,72 +376,114 @@ __global__ void __launch_bounds__(512) nc_layer1_kernel(const float* __restrict_
   }
 }
 
-// layer 2: grid (nA), block (ceil(wB/4), ceil(hB/2)); thread = 2x4 B cells; loops 9 A-neighbours x
-// 4-channel groups, staging hidden planes (with halo) through shared memory.
+// layer 2: grid (nA), block (ceil(wB/4), ceil(hB/2)); thread = 2x4 B cells.  The work list is
+// (net, valid A-neighbour, 4-channel group); each item stages 4 hidden planes (zero halo kept from
+// initialisation) through a double-buffered cp.async pipeline and costs 288 FMAs per thread.
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kNc2MaxCopies = 12;   // ceil(hB*wB / threads) <= 8 for 2x4 cells per thread (+ slack)
+
 __global__ void __launch_bounds__(512) nc_layer2_kernel(const float* __restrict__ hidden, int hA, int wA, int hB,
-                                                        int wB, const float* __restrict__ w2p, float b2,
-                                                        float* __restrict__ out) {
+                                                       int wB, const float* __restrict__ w2p, float b2,
+                                                       float* __restrict__ out) {
   extern __shared__ __align__(16) float smem[];
   const int PW = ((wB + 2 + 3) / 4) * 4 + 4;  // pitch: multiple of 4 floats, covers 4*tl+5
   const int PH = hB + 2 + 1;                  // covers 2*tk+3
+  const int plane = PH * PW;
   float* w2s = smem;                          // [81][32]
-  float* tile = smem + 81 * 32;               // [4][PH][PW]
+  float* tile = smem + 81 * 32;               // [2 buffers][4 planes][PH][PW]
+  __shared__ int s_ab[9];
+  __shared__ int s_nab;
   const int nthreads = blockDim.x * blockDim.y;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const int a = blockIdx.x, ia = a / wA, ja = a - ia * wA;
   const int nB = hB * wB;
   for (int i = tid; i < 81 * 32; i += nthreads) w2s[i] = w2p[i];
-  const int tl = threadIdx.x, tk = threadIdx.y;
-  float total[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) total[i] = 0.f;
-  const int plane = PH * PW;
-  for (int net = 0; net < 2; ++net) {
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = b2;
+  for (int i = tid; i < 8 * plane; i += nthreads) tile[i] = 0.f;   // halo stays zero for the whole kernel
+  if (tid == 0) {
+    int n = 0;
     for (int ab = 0; ab < 9; ++ab) {
       const int si = ia + ab / 3 - 1, sj = ja + ab % 3 - 1;
-      if (si < 0 || si >= hA || sj < 0 || sj >= wA) continue;  // uniform across the block
-      const float* src = hidden + (size_t)(si * wA + sj) * 32 * nB;
-      for (int cg = 0; cg < 4; ++cg) {
-        const int c0 = net * 16 + cg * 4;
-        __syncthreads();
-        for (int i = tid; i < 4 * plane; i += nthreads) {
-          const int cc = i / plane;
-          const int rem = i - cc * plane;
-          const int kk = rem / PW, ll = rem - kk * PW;
-          const int sk = kk - 1, sl = ll - 1;
-          float v = 0.f;
-          if (sk >= 0 && sk < hB && sl >= 0 && sl < wB) v = __ldg(src + (size_t)(c0 + cc) * nB + sk * wB + sl);
-          tile[i] = v;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          float r[4][6];
-#pragma unroll
-          for (int rr = 0; rr < 4; ++rr) {
-            const float* p = tile + cc * plane + (2 * tk + rr) * PW + 4 * tl;
-            const float4 q = *reinterpret_cast<const float4*>(p);
-            const float2 q2 = *reinterpret_cast<const float2*>(p + 4);
-            r[rr][0] = q.x; r[rr][1] = q.y; r[rr][2] = q.z; r[rr][3] = q.w; r[rr][4] = q2.x; r[rr][5] = q2.y;
-          }
-#pragma unroll
-          for (int d = 0; d < 3; ++d)
-#pragma unroll
-            for (int e = 0; e < 3; ++e) {
-              const float wv = w2s[(ab * 9 + d * 3 + e) * 32 + c0 + cc];
-#pragma unroll
-              for (int kk = 0; kk < 2; ++kk)
-#pragma unroll
-                for (int ll = 0; ll < 4; ++ll) acc[kk * 4 + ll] = fmaf(r[kk + d][ll + e], wv, acc[kk * 4 + ll]);
-            }
-        }
-      }
+      if (si >= 0 && si < hA && sj >= 0 && sj < wA) s_ab[n++] = ab;
     }
+    s_nab = n;
+  }
+  // per-thread copy slots: element e = tid + j*nthreads of a plane -> (src offset, smem offset)
+  int src_off[kNc2MaxCopies], dst_off[kNc2MaxCopies];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) total[i] += fmaxf(acc[i], 0.f);
+  for (int j = 0; j < kNc2MaxCopies; ++j) {
+    const int e = tid + j * nthreads;
+    const int k = e / wB, l = e - k * wB;
+    src_off[j] = e < nB ? e : -1;
+    dst_off[j] = (k + 1) * PW + l + 1;
+  }
+  __syncthreads();
+  const int nab = s_nab;
+  const int nitems = 2 * nab * 4;
+  auto issue = [&](int item) {
+    const int net = item / (nab * 4);
+    const int rem = item - net * nab * 4;
+    const int ab = s_ab[rem >> 2], cg = rem & 3;
+    const int si = ia + ab / 3 - 1, sj = ja + ab % 3 - 1;
+    const float* src = hidden + ((size_t)(si * wA + sj) * 32 + net * 16 + cg * 4) * nB;
+    float* dst = tile + (item & 1) * 4 * plane;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc)
+#pragma unroll
+      for (int j = 0; j < kNc2MaxCopies; ++j)
+        if (src_off[j] >= 0) cp_async4(dst + cc * plane + dst_off[j], src + (size_t)cc * nB + src_off[j]);
+    cp_async_commit();
+  };
+  const int tl = threadIdx.x, tk = threadIdx.y;
+  float total[8], acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { total[i] = 0.f; acc[i] = b2; }
+  issue(0);
+  for (int item = 0; item < nitems; ++item) {
+    if (item + 1 < nitems) {
+      issue(item + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const int net = item / (nab * 4);
+    const int rem = item - net * nab * 4;
+    const int ab = s_ab[rem >> 2], c0 = net * 16 + (rem & 3) * 4;
+    const float* buf = tile + (item & 1) * 4 * plane;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      float r[4][6];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const float* p = buf + cc * plane + (2 * tk + rr) * PW + 4 * tl;
+        const float4 q = *reinterpret_cast<const float4*>(p);
+        const float2 q2 = *reinterpret_cast<const float2*>(p + 4);
+        r[rr][0] = q.x; r[rr][1] = q.y; r[rr][2] = q.z; r[rr][3] = q.w; r[rr][4] = q2.x; r[rr][5] = q2.y;
+      }
+      const float* wrow = w2s + ab * 9 * 32 + c0 + cc;
+#pragma unroll
+      for (int d = 0; d < 3; ++d)
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+          const float wv = wrow[(d * 3 + e) * 32];
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+            for (int ll = 0; ll < 4; ++ll) acc[kk * 4 + ll] = fmaf(r[kk + d][ll + e], wv, acc[kk * 4 + ll]);
+        }
+    }
+    if (rem == nab * 4 - 1) {   // last item of this net: ReLU and fold into the total
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { total[i] += fmaxf(acc[i], 0.f); acc[i] = b2; }
+    }
+    __syncthreads();             // everyone is done with this buffer before it is refilled
   }
 #pragma unroll
   for (int kk = 0; kk < 2; ++kk)
@@ -467,8 +509,9 @@ int launch_neigh_consensus(const float* x, int hA, int wA, int hB, int wB, const
   {
     dim3 block(cdiv(wB, 4), cdiv(hB, 2));
     P2P_REQUIRE(block.x * block.y <= 512, "NC layer 2: pooled B grid too large (hB*wB <= 4096)");
+    P2P_REQUIRE(cdiv(hB * wB, (int)(block.x * block.y)) <= kNc2MaxCopies, "NC layer 2: copy slots exhausted");
     const int PW = ((wB + 2 + 3) / 4) * 4 + 4, PH = hB + 3;
-    const size_t smem = sizeof(float) * (81 * 32 + 4 * PH * PW);
+    const size_t smem = sizeof(float) * (81 * 32 + 8 * PH * PW);
     P2P_REQUIRE(smem <= 200 * 1024, "NC layer 2: pooled B grid does not fit shared memory");
     P2P_CUDA_OK(cudaFuncSetAttribute(nc_layer2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nc_layer2_kernel<<<nA, block, smem, st>>>(hidden, hA, wA, hB, wB, w2p, b2, out);

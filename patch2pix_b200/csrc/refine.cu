@@ -151,22 +151,35 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(GatherArgs g, const v
   const int coff = (jj == 3 ? 64 : 0) + sub * 16;
   const float* fmap = g.nhwc[s][lvl];
   const int wl = g.W[s] / ds;
-  for (int pos = wid; pos < kPatchPos; pos += 8) {
-    const int plane = pos >> 6, iy = (pos >> 3) & 7, ix = pos & 7;
-    const int wx = (plane & 1) ? 2 * ix : 2 * ix + 1;
-    const int wy = (plane & 2) ? 2 * iy : 2 * iy + 1;
-    const int xi = clamp_idx(org[2 * s] + wx, ds, g.W[s]), yi = clamp_idx(org[2 * s + 1] + wy, ds, g.H[s]);
-    const float sc = dinv[s][wy][wx];
-    const float4* src = reinterpret_cast<const float4*>(fmap + ((size_t)yi * wl + xi) * C + coff);
-    float v[16];
+  // 4 window positions per warp iteration: all 16 loads are issued before the first store
+  for (int pos0 = wid; pos0 < kPatchPos; pos0 += 32) {
+    float4 t[4][4];
+    float sc[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 t = __ldg(src + q);
-      v[q * 4 + 0] = t.x * sc; v[q * 4 + 1] = t.y * sc; v[q * 4 + 2] = t.z * sc; v[q * 4 + 3] = t.w * sc;
+    for (int u = 0; u < 4; ++u) {
+      const int pos = pos0 + 8 * u;
+      const int plane = pos >> 6, iy = (pos >> 3) & 7, ix = pos & 7;
+      const int wx = (plane & 1) ? 2 * ix : 2 * ix + 1;
+      const int wy = (plane & 2) ? 2 * iy : 2 * iy + 1;
+      const int xi = clamp_idx(org[2 * s] + wx, ds, g.W[s]), yi = clamp_idx(org[2 * s + 1] + wy, ds, g.H[s]);
+      sc[u] = dinv[s][wy][wx];
+      const float4* src = reinterpret_cast<const float4*>(fmap + ((size_t)yi * wl + xi) * C + coff);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) t[u][q] = __ldg(src + q);
     }
-    const size_t o = ((size_t)n * kPatchPos + pos) * kMainCh + j * 64 + sub * 16;
-    split_store8(v, p_hi + o, p_lo ? p_lo + o : nullptr);
-    split_store8(v + 8, p_hi + o + 8, p_lo ? p_lo + o + 8 : nullptr);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int pos = pos0 + 8 * u;
+      float v[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        v[q * 4 + 0] = t[u][q].x * sc[u]; v[q * 4 + 1] = t[u][q].y * sc[u];
+        v[q * 4 + 2] = t[u][q].z * sc[u]; v[q * 4 + 3] = t[u][q].w * sc[u];
+      }
+      const size_t o = ((size_t)n * kPatchPos + pos) * kMainCh + j * 64 + sub * 16;
+      split_store8(v, p_hi + o, p_lo ? p_lo + o : nullptr);
+      split_store8(v + 8, p_hi + o + 8, p_lo ? p_lo + o + 8 : nullptr);
+    }
   }
   // rgb im2col: 64 output pixels x 64 k
   for (int e = tid; e < 64 * 64; e += 256) {

@@ -149,7 +149,7 @@ def test_coarse_stages_vs_oracle(nets, seeded_sd, pair_idx, H, W, corr_passes):
             np.testing.assert_allclose(stages['pooled'].cpu().numpy(), st['pooled'].numpy(), rtol=0, atol=1e-6)
             n_bad, n_unexplained = _delta_mismatch_report(delta4d, o_delta, c1[-1], c2[-1])
             assert n_unexplained == 0 and n_bad <= max(2, delta4d[0].numel() // 500), (n_bad, n_unexplained)
-            np.testing.assert_allclose(stages['ncn'].cpu().numpy(), st['ncn'].numpy(), rtol=2e-4, atol=2e-6)
+            np.testing.assert_allclose(stages['ncn'].cpu().numpy(), st['ncn'].numpy(), rtol=2e-4, atol=5e-6)
             np.testing.assert_allclose(corr4d.cpu().numpy(), o_corr.numpy(), rtol=5e-4, atol=1e-7)
             # proposal kernels on reference-shaped inputs from outside (the ORACLE's corr4d/delta): exact
             o_m, o_s = O.cal_coarse_matches(o_corr, o_delta, ksize=2, upsample=8, center=True)
@@ -167,7 +167,7 @@ def test_coarse_stages_vs_oracle(nets, seeded_sd, pair_idx, H, W, corr_passes):
             _report(f'coarse_{H}x{W}_{"tc" if corr_passes else "simt"}', {'delta_cells_differing': n_bad,
                     'unexplained': n_unexplained, 'proposal_rows_differing': diff_rows, 'cells': int(delta4d[0].numel())})
     finally:
-        net.set_option('corr_passes', 0)
+        net.set_option('corr_passes', 3)
 
 
 def test_coarse_ksize1_vs_oracle(nets, seeded_sd):
