@@ -36,7 +36,7 @@ MAC_CONV1, MAC_CONV2 = 152764416, 150994944        # per patch, dense count (SUR
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--height', type=int, default=H_DEF)
@@ -46,6 +46,8 @@ def parse():
     ap.add_argument('--fine-passes', type=int, default=None)
     ap.add_argument('--corr-passes', type=int, default=None)
     ap.add_argument('--seg-len', type=int, default=None)
+    ap.add_argument('--mid-band', type=int, default=None)
+    ap.add_argument('--backbone-fp32', action='store_true', help='keep cuDNN TF32 off in the e2e backbone')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-sample-patches', type=int, default=200)
     return ap.parse_args()
@@ -188,10 +190,10 @@ def run_ours(args):
     cfg.weights_dict = make_seeded_state_dict(0)
     net = Patch2PixB200(cfg)
     for key, v in (('mid_passes', args.mid_passes), ('fine_passes', args.fine_passes), ('corr_passes', args.corr_passes),
-                   ('seg_len', args.seg_len)):
+                   ('seg_len', args.seg_len), ('mid_band', args.mid_band)):
         if v is not None:
             net.set_option(key, v)
-    opts = {k: net._handle.get_option(k) for k in ('mid_passes', 'fine_passes', 'corr_passes', 'seg_len')}
+    opts = {k: net._handle.get_option(k) for k in ('mid_passes', 'fine_passes', 'corr_passes', 'seg_len', 'mid_band')}
 
     # pair indices: rank 0 decides, NCCL broadcasts (the "scatter pair indices" step)
     total_steps = K + Wm
@@ -265,7 +267,11 @@ def run_ours(args):
         prof = net._handle.profile_read()
         net.set_option('profile', 0)
 
+        band_rows = net._handle.get_option('band_rows')
         # ---- end to end: pinned host images -> matches on the host ------------------------------
+        # backbone in PyTorch's default cuDNN mode (TF32 convolutions allowed, as the reference would run)
+        torch.backends.cudnn.allow_tf32 = not args.backbone_fp32
+        torch.backends.cudnn.benchmark = True
         host_out = torch.empty(n_patches, 5).pin_memory()
         for i in range(min(Wm, 3)):
             e2e_step(i, host_out)
@@ -281,27 +287,32 @@ def run_ours(args):
         value = pairs / (ms_hot / 1e3)
         # dominant kernel: the conv implicit GEMMs of the refine stage
         kern = {k: {'ms_per_launch': v[0] / v[1], 'launches': v[1]} for k, v in prof.items() if v[1] > 0}
-        gemm_names = ['conv1_mid', 'conv2_mid', 'conv1_fine', 'conv2_fine']
-        macs = {'conv1_mid': MAC_CONV1, 'conv2_mid': MAC_CONV2, 'conv1_fine': MAC_CONV1, 'conv2_fine': MAC_CONV2}
-        passes = {'conv1_mid': opts['mid_passes'], 'conv2_mid': opts['mid_passes'], 'conv1_fine': opts['fine_passes'],
-                  'conv2_fine': opts['fine_passes']}
-        for k in gemm_names:
-            if k in kern:
-                fl = 2.0 * macs[k] * n_patches
-                kern[k]['algorithmic_tflops'] = fl / (kern[k]['ms_per_launch'] * 1e-3) / 1e12
-                kern[k]['tensor_passes'] = passes[k]
-                kern[k]['issued_tflops'] = kern[k]['algorithmic_tflops'] * passes[k]
-        dom = max((k for k in gemm_names if k in kern), key=lambda k: kern[k]['ms_per_launch'] * kern[k]['launches'],
-                  default=None)
+        banded = opts['mid_passes'] == 3 and opts['mid_band'] > 0
+        macs = {'conv1': MAC_CONV1, 'conv2': MAC_CONV2}
+        for k in list(kern):
+            base, _, stage = k.partition('_')
+            if base not in macs:
+                continue
+            rows = band_rows if stage == 'band' else n_patches
+            ps = 3 if stage == 'band' else (opts['fine_passes'] if stage == 'fine' else (1 if banded else opts['mid_passes']))
+            fl = 2.0 * macs[base] * rows
+            kern[k].update({'rows': rows, 'tensor_passes': ps,
+                            'algorithmic_tflops': fl / (kern[k]['ms_per_launch'] * 1e-3) / 1e12})
+            kern[k]['issued_tflops'] = kern[k]['algorithmic_tflops'] * ps
+        gemm_names = [k for k in kern if k.startswith('conv')]
+        dom = max(gemm_names, key=lambda k: kern[k]['ms_per_launch'] * kern[k]['launches'], default=None)
         roofline = None
         if dom:
             ach = kern[dom]['algorithmic_tflops']
+            gemm_ms = sum(kern[k]['ms_per_launch'] * kern[k]['launches'] for k in gemm_names)
             roofline = {'kernel': f'umma_gemm_kernel ({dom})', 'bound': 'tensor', 'achieved': ach, 'peak': peaks['tflops'],
                         'unit': 'TFLOP/s', 'frac': ach / peaks['tflops'], 'traffic': None,
                         'peak_source': peaks['src'] + ' bf16 sustained (fp16 runs at the same tensor rate)',
                         'tensor_passes': kern[dom]['tensor_passes'],
                         'issued_frac': kern[dom]['issued_tflops'] / peaks['tflops'],
-                        'share_of_step': kern[dom]['ms_per_launch'] * kern[dom]['launches'] / ms_hot}
+                        'share_of_step': kern[dom]['ms_per_launch'] * kern[dom]['launches'] / ms_hot,
+                        'all_umma_gemm_share_of_step': gemm_ms / ms_hot,
+                        'band_rows_recomputed_3pass': band_rows if banded else None}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             from oracle import p2p_oracle as O
@@ -317,8 +328,9 @@ def run_ours(args):
         line = {
             'metric': 'image-pairs/sec', 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': K, 'warmup': Wm,
             'ms_per_step': ms_hot / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': f'f16 tensor-core operands (mid: {opts["mid_passes"]}-pass hi/lo split, fine: {opts["fine_passes"]}-pass), '
-                     f'f32 accumulate; f32 coarse stage',
+            'dtype': f'f16 tensor-core operands (mid: {opts["mid_passes"]}-pass hi/lo split'
+                     f'{" on the risk band, 1-pass elsewhere" if opts["mid_band"] and opts["mid_passes"] == 3 else ""}, '
+                     f'fine: {opts["fine_passes"]}-pass, correlation: {opts["corr_passes"]}-pass), f32 accumulate; f32 NC conv',
             'data': 'synthetic',
             'config': {'workload': f'{W}x{H} pair, ptmax={args.ptmax} panc={PANC_DEF} -> {n_patches} patches/stage '
                                    f'(BASELINE configs[2]); hot path = correlation .. fine matches, features resident in HBM',
@@ -327,7 +339,7 @@ def run_ours(args):
                        'options': opts},
             'e2e': {'value': pairs / (ms_e2e / 1e3), 'unit': 'pairs/s', 'ms_per_step': ms_e2e / K,
                     'h2d_bytes_per_step': 2 * 3 * H * W * 4, 'd2h_bytes_per_step': n_patches * 5 * 4,
-                    'path': 'pinned host images -> H2D -> cuDNN fp32 ResNet34 pyramid -> hot path -> D2H matches+scores'},
+                    'path': 'pinned host images -> H2D -> cuDNN ResNet34 pyramid (' + ('fp32' if args.backbone_fp32 else 'TF32 convs, PyTorch default') + ') -> hot path -> D2H matches+scores'},
             'gpu_launches': launches, 'roofline': roofline, 'kernels': kern, 'clocks': clocks, 'cpu_baseline': cpu,
         }
         print(json.dumps(line), flush=True)

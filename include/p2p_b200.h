@@ -73,7 +73,10 @@ P2P_API int p2p_set_regressor_weights(p2p_handle_t h, int which, const p2p_regre
 /* Options: "mid_passes"/"fine_passes" (1 = fp16 operands, 3 = fp16 hi/lo split, fp32-grade),
  * "corr_passes" (0 = CUDA-core fp32 correlation, 1/3 = tensor-core), "seg_len" (k-steps per
  * TMEM accumulation segment, 0 = whole K), "gemm_impl" (0 = tcgen05, 1 = CUDA-core checker),
- * "num_sms" (persistent grid size, 0 = all), "profile" (1 = record per-kernel CUDA events). */
+ * "num_sms" (persistent grid size, 0 = all), "profile" (1 = record per-kernel CUDA events),
+ * "mid_band" (thousandths of a pixel, default 40; with mid_passes = 3 every row is first computed 1-pass and
+ * only rows with a coordinate within the band of an integer -- where trunc(mid) could differ from the
+ * reference -- are re-computed 3-pass; 0 = 3-pass for every row). */
 P2P_API int p2p_set_option(p2p_handle_t h, const char* key, int value);
 P2P_API int p2p_get_option(p2p_handle_t h, const char* key, int* value);
 /* Number of kernel launches enqueued by this handle since creation (bench.py's gpu_launches). */
@@ -86,7 +89,8 @@ enum {
   P2P_PROF_L2NORM = 0, P2P_PROF_CORR = 1, P2P_PROF_MUTUAL = 2, P2P_PROF_NC = 3, P2P_PROF_PROPOSALS = 4,
   P2P_PROF_PREP = 5, P2P_PROF_GATHER_MID = 6, P2P_PROF_CONV1_MID = 7, P2P_PROF_CONV2_MID = 8, P2P_PROF_FC_MID = 9,
   P2P_PROF_GATHER_FINE = 10, P2P_PROF_CONV1_FINE = 11, P2P_PROF_CONV2_FINE = 12, P2P_PROF_FC_FINE = 13,
-  P2P_PROF_KINDS = 14
+  P2P_PROF_GATHER_BAND = 14, P2P_PROF_CONV1_BAND = 15, P2P_PROF_CONV2_BAND = 16, P2P_PROF_FC_BAND = 17,
+  P2P_PROF_FLAG = 18, P2P_PROF_KINDS = 19
 };
 P2P_API int p2p_profile_read(p2p_handle_t h, float* ms_by_kind, int* count_by_kind, int nkinds);
 

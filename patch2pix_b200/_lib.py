@@ -50,7 +50,8 @@ _SIGNATURES = {
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 PROF_KINDS = ('l2norm', 'corr', 'mutual', 'nc', 'proposals', 'prep', 'gather_mid', 'conv1_mid', 'conv2_mid', 'fc_mid',
-              'gather_fine', 'conv1_fine', 'conv2_fine', 'fc_fine')
+              'gather_fine', 'conv1_fine', 'conv2_fine', 'fc_fine', 'gather_band', 'conv1_band', 'conv2_band', 'fc_band',
+              'flag')
 
 
 def load():

@@ -59,6 +59,8 @@ struct p2p_handle_s {
   int device = 0;
   int num_sms = 148;
   int opt_mid_passes = 3, opt_fine_passes = 1, opt_corr_passes = 3, opt_seg_len = 3, opt_gemm_impl = 0, opt_num_sms = 0;
+  int opt_mid_band = 40;  // thousandths of a pixel; 0 = pure 3-pass mid stage
+  const int* last_band_count = nullptr;  // device counter of the last risk-band subset
   bool nc_set = false;
   float *nc_w1p = nullptr, *nc_b1p = nullptr, *nc_w2p = nullptr;
   float nc_b2 = 0.f;
@@ -390,6 +392,7 @@ static int* option_slot(p2p_handle_t h, const char* key) {
   if (!strcmp(key, "gemm_impl")) return &h->opt_gemm_impl;
   if (!strcmp(key, "num_sms")) return &h->opt_num_sms;
   if (!strcmp(key, "profile")) return &h->opt_profile;
+  if (!strcmp(key, "mid_band")) return &h->opt_mid_band;
   return nullptr;
 }
 
@@ -406,6 +409,15 @@ int p2p_set_option(p2p_handle_t h, const char* key, int value) {
 
 int p2p_get_option(p2p_handle_t h, const char* key, int* value) {
   P2P_REQUIRE(h != nullptr && key != nullptr && value != nullptr, "null argument");
+  if (!strcmp(key, "band_rows")) {  // rows re-computed 3-pass by the last mid-stage call (synchronises)
+    *value = 0;
+    if (h->last_band_count != nullptr) {
+      DeviceGuard g(h->device);
+      P2P_CUDA_OK(cudaDeviceSynchronize());
+      P2P_CUDA_OK(cudaMemcpy(value, h->last_band_count, sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    return 0;
+  }
   int* s = option_slot(h, key);
   P2P_REQUIRE(s != nullptr, std::string("unknown option ") + key);
   *value = *s;
@@ -653,6 +665,104 @@ int p2p_refine_prepare(p2p_handle_t h, const float* const* feats1, const float* 
   return 0;
 }
 
+namespace {
+
+struct RefineBuffers {
+  __half *p_hi, *p_lo, *r_hi, *r_lo, *y_hi, *y_lo;
+  float *pooled, *raw;
+  int *rowmap, *d_count;
+  int npad;
+};
+
+// gather -> conv1 -> conv2 -> fc/parse for the rows selected by (rowmap, d_count) [all rows if null]
+int run_regressor(p2p_handle_s* h, Regressor& R, int which, int passes, const RefineBuffers& B, const void* matches_in,
+                  int is_float, int n, const int* rowmap, const int* d_count, float* matches_out, float* probs_out,
+                  float* raw_out, cudaStream_t st) {
+  const bool lo = passes == 3;
+  const int kb = rowmap != nullptr ? P2P_PROF_GATHER_BAND : (which == 0 ? P2P_PROF_GATHER_MID : P2P_PROF_GATHER_FINE);
+  int rc;
+  {
+    ProfScope ps(h, kb, st);
+    if ((rc = launch_patch_gather(h->pf[0], h->pf[1], matches_in, is_float, n, B.p_hi, lo ? B.p_lo : nullptr, B.r_hi,
+                                  lo ? B.r_lo : nullptr, rowmap, d_count, st)))
+      return rc;
+  }
+  const size_t qbytes = (size_t)B.npad * 512 * 4;
+  if (h->opt_gemm_impl == 1) {
+    P2P_REQUIRE(rowmap == nullptr, "the CUDA-core checker GEMM does not support row subsets");
+    GemmOperands g1 = {B.p_hi, B.p_lo, B.r_hi, B.r_lo, R.w1_hi, R.w1_lo, 4, kConv1Steps * 64, n, passes, R.d_steps1, kConv1Steps};
+    ConvEpilogue e1 = {R.scale1, R.bias1, 0, R.y_scale, B.y_hi, lo ? B.y_lo : nullptr, nullptr};
+    {
+      ProfScope ps(h, kb + 1, st);
+      if ((rc = launch_conv_gemm_simt(g1, e1, st))) return rc;
+    }
+    ProfScope ps(h, kb + 2, st);
+    GemmOperands g2 = {B.y_hi, B.y_lo, nullptr, nullptr, R.w2_hi, R.w2_lo, 1, kConv2Steps * 64, n, passes, R.d_steps2, kConv2Steps};
+    ConvEpilogue e2 = {R.scale2, R.bias2, 1, 1.f, nullptr, nullptr, B.pooled};
+    if ((rc = launch_conv_gemm_simt(g2, e2, st))) return rc;
+  } else {
+    UmmaGemmParams p;
+    memset(&p, 0, sizeof(p));
+    const uint32_t abox[5] = {64, 8, 8, 1, 2};
+    const uint32_t bbox[2] = {64, 256};
+    const uint64_t npad = (uint64_t)B.npad;
+    {  // conv1
+      const uint64_t ad[5] = {512, 8, 8, 4, npad};
+      const uint64_t as[4] = {1024, 8192, 65536, 262144};
+      const uint64_t rd[5] = {64, 8, 8, 1, npad};
+      const uint64_t rs[4] = {128, 1024, 8192, 8192};
+      const uint64_t bd[2] = {(uint64_t)kConv1Steps * 64, 512};
+      const uint64_t bs[1] = {(uint64_t)kConv1Steps * 64 * 2};
+      if ((rc = make_tmap_fp16(&p.a_main_hi, B.p_hi, 5, ad, as, abox))) return rc;
+      if ((rc = make_tmap_fp16(&p.a_rgb_hi, B.r_hi, 5, rd, rs, abox))) return rc;
+      if ((rc = make_tmap_fp16(&p.b_hi, R.w1_hi, 2, bd, bs, bbox))) return rc;
+      if ((rc = make_tmap_fp16(&p.a_main_lo, lo ? B.p_lo : B.p_hi, 5, ad, as, abox))) return rc;
+      if ((rc = make_tmap_fp16(&p.a_rgb_lo, lo ? B.r_lo : B.r_hi, 5, rd, rs, abox))) return rc;
+      if ((rc = make_tmap_fp16(&p.b_lo, R.w1_lo, 2, bd, bs, bbox))) return rc;
+      p.nsteps = kConv1Steps;
+      memcpy(p.steps, R.steps1, sizeof(R.steps1));
+      p.m_tiles = (n + 1) / 2;
+      p.n_tiles = 2;
+      p.a_units_per_tile = 2;
+      p.seg_len = lo ? h->opt_seg_len : 0;
+      p.d_units = d_count;
+      p.epi.scale = R.scale1;
+      p.epi.bias = R.bias1;
+      p.epi.y_scale = R.y_scale;
+      p.epi.y_hi = B.y_hi;
+      p.epi.y_lo = lo ? B.y_lo : nullptr;
+      p.epi.n_patches = n;
+      ProfScope ps(h, kb + 1, st);
+      if ((rc = launch_umma_gemm(p, EPI_CONV1, passes, sms(h), st))) return rc;
+    }
+    {  // conv2
+      const uint64_t ad[5] = {512, 8, 8, 1, npad};
+      const uint64_t as[4] = {1024, 8192, 65536, 65536};
+      const uint64_t bd[2] = {(uint64_t)kConv2Steps * 64, 512};
+      const uint64_t bs[1] = {(uint64_t)kConv2Steps * 64 * 2};
+      if ((rc = make_tmap_fp16(&p.a_main_hi, B.y_hi, 5, ad, as, abox))) return rc;
+      if ((rc = make_tmap_fp16(&p.a_main_lo, lo ? B.y_lo : B.y_hi, 5, ad, as, abox))) return rc;
+      if ((rc = make_tmap_fp16(&p.b_hi, R.w2_hi, 2, bd, bs, bbox))) return rc;
+      if ((rc = make_tmap_fp16(&p.b_lo, R.w2_lo, 2, bd, bs, bbox))) return rc;
+      p.a_rgb_hi = p.a_main_hi;
+      p.a_rgb_lo = p.a_main_lo;
+      p.nsteps = kConv2Steps;
+      memcpy(p.steps, R.steps2, sizeof(R.steps2));
+      p.epi.scale = R.scale2;
+      p.epi.bias = R.bias2;
+      p.epi.pooled = B.pooled;
+      P2P_CUDA_OK(cudaMemsetAsync(B.pooled, 0, qbytes, st));
+      ProfScope ps(h, kb + 2, st);
+      if ((rc = launch_umma_gemm(p, EPI_CONV2, passes, sms(h), st))) return rc;
+    }
+  }
+  ProfScope ps(h, kb + 3, st);
+  return launch_fc_parse(B.pooled, R.fc, matches_in, is_float, n, h->pf[0].W, h->pf[0].H, h->pf[1].W, h->pf[1].H,
+                         matches_out, probs_out, raw_out, rowmap, d_count, st);
+}
+
+}  // namespace
+
 int p2p_refine(p2p_handle_t h, int which, const void* matches_in, int is_float, int n, float* matches_out,
                float* probs_out, void* stream) {
   P2P_ENTER(h);
@@ -665,96 +775,43 @@ int p2p_refine(p2p_handle_t h, int which, const void* matches_in, int is_float, 
   P2P_REQUIRE(matches_in && matches_out && probs_out, "null tensor pointer");
   Regressor& R = h->reg[which];
   const int passes = which == 0 ? h->opt_mid_passes : h->opt_fine_passes;
-  const bool lo = passes == 3;
+  // Risk band (mid stage only): 1-pass for every row, fp32-grade 3-pass re-computation only for the
+  // rows whose coordinates sit within mid_band/1000 px of an integer (trunc() must match the reference).
+  const bool band = which == 0 && passes == 3 && h->opt_mid_band > 0 && h->opt_gemm_impl == 0;
   const int npad = (int)align_up(n, 2);
   const size_t pbytes = (size_t)npad * kPatchPos * kMainCh * 2, rbytes = (size_t)npad * 4096 * 2,
                ybytes = (size_t)npad * 64 * 512 * 2, qbytes = (size_t)npad * 512 * 4;
-  int rc = h->refine.reserve(2 * (pbytes + rbytes + ybytes) + qbytes + (1 << 16));
+  int rc = h->refine.reserve(2 * (pbytes + rbytes + ybytes) + qbytes + (size_t)n * 24 + (1 << 16));
   if (rc) return rc;
   Arena& A = h->refine;
-  __half* p_hi = (__half*)A.take(pbytes);
-  __half* p_lo = (__half*)A.take(pbytes);
-  __half* r_hi = (__half*)A.take(rbytes);
-  __half* r_lo = (__half*)A.take(rbytes);
-  __half* y_hi = (__half*)A.take(ybytes);
-  __half* y_lo = (__half*)A.take(ybytes);
-  float* pooled = (float*)A.take(qbytes);
-  P2P_REQUIRE(p_hi && p_lo && r_hi && r_lo && y_hi && y_lo && pooled, "scratch carve failed");
-  const int kb = which == 0 ? P2P_PROF_GATHER_MID : P2P_PROF_GATHER_FINE;  // gather, conv1, conv2, fc
+  RefineBuffers B;
+  B.npad = npad;
+  B.p_hi = (__half*)A.take(pbytes);
+  B.p_lo = (__half*)A.take(pbytes);
+  B.r_hi = (__half*)A.take(rbytes);
+  B.r_lo = (__half*)A.take(rbytes);
+  B.y_hi = (__half*)A.take(ybytes);
+  B.y_lo = (__half*)A.take(ybytes);
+  B.pooled = (float*)A.take(qbytes);
+  B.raw = (float*)A.take((size_t)n * 5 * 4);
+  B.rowmap = (int*)A.take((size_t)n * 4 + 16);
+  P2P_REQUIRE(B.p_hi && B.p_lo && B.r_hi && B.r_lo && B.y_hi && B.y_lo && B.pooled && B.raw && B.rowmap,
+              "scratch carve failed");
+  B.d_count = B.rowmap + n;
+  h->last_band_count = band ? B.d_count : nullptr;
+  if (!band)
+    return run_regressor(h, R, which, passes, B, matches_in, is_float, n, nullptr, nullptr, matches_out, probs_out,
+                         nullptr, st);
+  if ((rc = run_regressor(h, R, which, 1, B, matches_in, is_float, n, nullptr, nullptr, matches_out, probs_out, B.raw,
+                          st)))
+    return rc;
   {
-    ProfScope ps(h, kb, st);
-    if ((rc = launch_patch_gather(h->pf[0], h->pf[1], matches_in, is_float, n, p_hi, lo ? p_lo : nullptr, r_hi,
-                                  lo ? r_lo : nullptr, st)))
+    ProfScope ps(h, P2P_PROF_FLAG, st);
+    if ((rc = launch_flag_risky(matches_out, B.raw, n, h->opt_mid_band * 1e-3f, 0.02f, B.rowmap, B.d_count, st)))
       return rc;
   }
-  if (h->opt_gemm_impl == 1) {
-    GemmOperands g1 = {p_hi, p_lo, r_hi, r_lo, R.w1_hi, R.w1_lo, 4, kConv1Steps * 64, n, passes, R.d_steps1, kConv1Steps};
-    ConvEpilogue e1 = {R.scale1, R.bias1, 0, R.y_scale, y_hi, lo ? y_lo : nullptr, nullptr};
-    {
-      ProfScope ps(h, kb + 1, st);
-      if ((rc = launch_conv_gemm_simt(g1, e1, st))) return rc;
-    }
-    ProfScope ps(h, kb + 2, st);
-    GemmOperands g2 = {y_hi, y_lo, nullptr, nullptr, R.w2_hi, R.w2_lo, 1, kConv2Steps * 64, n, passes, R.d_steps2, kConv2Steps};
-    ConvEpilogue e2 = {R.scale2, R.bias2, 1, 1.f, nullptr, nullptr, pooled};
-    if ((rc = launch_conv_gemm_simt(g2, e2, st))) return rc;
-  } else {
-    UmmaGemmParams p;
-    memset(&p, 0, sizeof(p));
-    const uint32_t abox[5] = {64, 8, 8, 1, 2};
-    const uint32_t bbox[2] = {64, 256};
-    {  // conv1
-      const uint64_t ad[5] = {512, 8, 8, 4, (uint64_t)npad};
-      const uint64_t as[4] = {1024, 8192, 65536, 262144};
-      const uint64_t rd[5] = {64, 8, 8, 1, (uint64_t)npad};
-      const uint64_t rs[4] = {128, 1024, 8192, 8192};
-      const uint64_t bd[2] = {(uint64_t)kConv1Steps * 64, 512};
-      const uint64_t bs[1] = {(uint64_t)kConv1Steps * 64 * 2};
-      if ((rc = make_tmap_fp16(&p.a_main_hi, p_hi, 5, ad, as, abox))) return rc;
-      if ((rc = make_tmap_fp16(&p.a_rgb_hi, r_hi, 5, rd, rs, abox))) return rc;
-      if ((rc = make_tmap_fp16(&p.b_hi, R.w1_hi, 2, bd, bs, bbox))) return rc;
-      if ((rc = make_tmap_fp16(&p.a_main_lo, lo ? p_lo : p_hi, 5, ad, as, abox))) return rc;
-      if ((rc = make_tmap_fp16(&p.a_rgb_lo, lo ? r_lo : r_hi, 5, rd, rs, abox))) return rc;
-      if ((rc = make_tmap_fp16(&p.b_lo, R.w1_lo, 2, bd, bs, bbox))) return rc;
-      p.nsteps = kConv1Steps;
-      memcpy(p.steps, R.steps1, sizeof(R.steps1));
-      p.m_tiles = npad / 2;
-      p.n_tiles = 2;
-      p.a_units_per_tile = 2;
-      p.seg_len = lo ? h->opt_seg_len : 0;
-      p.epi.scale = R.scale1;
-      p.epi.bias = R.bias1;
-      p.epi.y_scale = R.y_scale;
-      p.epi.y_hi = y_hi;
-      p.epi.y_lo = lo ? y_lo : nullptr;
-      p.epi.n_patches = n;
-      ProfScope ps(h, kb + 1, st);
-      if ((rc = launch_umma_gemm(p, EPI_CONV1, passes, sms(h), st))) return rc;
-    }
-    {  // conv2
-      const uint64_t ad[5] = {512, 8, 8, 1, (uint64_t)npad};
-      const uint64_t as[4] = {1024, 8192, 65536, 65536};
-      const uint64_t bd[2] = {(uint64_t)kConv2Steps * 64, 512};
-      const uint64_t bs[1] = {(uint64_t)kConv2Steps * 64 * 2};
-      if ((rc = make_tmap_fp16(&p.a_main_hi, y_hi, 5, ad, as, abox))) return rc;
-      if ((rc = make_tmap_fp16(&p.a_main_lo, lo ? y_lo : y_hi, 5, ad, as, abox))) return rc;
-      if ((rc = make_tmap_fp16(&p.b_hi, R.w2_hi, 2, bd, bs, bbox))) return rc;
-      if ((rc = make_tmap_fp16(&p.b_lo, R.w2_lo, 2, bd, bs, bbox))) return rc;
-      p.a_rgb_hi = p.a_main_hi;
-      p.a_rgb_lo = p.a_main_lo;
-      p.nsteps = kConv2Steps;
-      memcpy(p.steps, R.steps2, sizeof(R.steps2));
-      p.epi.scale = R.scale2;
-      p.epi.bias = R.bias2;
-      p.epi.pooled = pooled;
-      P2P_CUDA_OK(cudaMemsetAsync(pooled, 0, qbytes, st));
-      ProfScope ps(h, kb + 2, st);
-      if ((rc = launch_umma_gemm(p, EPI_CONV2, passes, sms(h), st))) return rc;
-    }
-  }
-  ProfScope ps(h, kb + 3, st);
-  return launch_fc_parse(pooled, R.fc, matches_in, is_float, n, h->pf[0].W, h->pf[0].H, h->pf[1].W, h->pf[1].H,
-                         matches_out, probs_out, st);
+  return run_regressor(h, R, which, 3, B, matches_in, is_float, n, B.rowmap, B.d_count, matches_out, probs_out,
+                       nullptr, st);
 }
 
 int p2p_test_gemm(p2p_handle_t h, const float* a, const float* b, float* c, int M, int N, int K, int passes,

@@ -40,14 +40,21 @@ struct PairFeatures {             // per image: channels-last copies + squared-n
 };
 
 int launch_feature_prep(const float* const feats[4], int H, int W, PairFeatures& out, cudaStream_t st);
+// rowmap/d_count (optional, device): process only rows rowmap[0..*d_count) (patch slot b <- row rowmap[b]).
 int launch_patch_gather(const PairFeatures& f1, const PairFeatures& f2, const void* matches, int is_float, int N,
-                        __half* p_hi, __half* p_lo, __half* rgb_hi, __half* rgb_lo, cudaStream_t st);
+                        __half* p_hi, __half* p_lo, __half* rgb_hi, __half* rgb_lo, const int* rowmap,
+                        const int* d_count, cudaStream_t st);
+// Rows whose refined coordinates sit within `tau` px of an integer (and whose offset is not the exact
+// relu-clamped -8) are collected, in ascending order, into rowmap / d_count.
+int launch_flag_risky(const float* matches_out, const float* raw, int N, float tau, float eps_o, int* rowmap,
+                      int* d_count, cudaStream_t st);
 
 struct FcWeights {                // BN folded, transposed to [in][out] for coalesced reads
   float *w1t, *b1, *w2t, *b2, *w3t, *b3;
 };
 int launch_fc_parse(const float* pooled, const FcWeights& fc, const void* matches_in, int is_float, int N, int W1,
-                    int H1, int W2, int H2, float* matches_out, float* probs_out, cudaStream_t st);
+                    int H1, int W2, int H2, float* matches_out, float* probs_out, float* raw_out, const int* rowmap,
+                    const int* d_count, cudaStream_t st);
 
 // One k-step of an implicit GEMM: where the [128 rows x 64 ch] A box starts and which K offset of
 // the K-major weight matrix it multiplies.

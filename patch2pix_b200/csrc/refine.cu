@@ -114,17 +114,21 @@ __device__ __forceinline__ void split_store8(const float* v, __half* hi, __half*
 template <bool IS_FLOAT>
 __global__ void __launch_bounds__(256) patch_gather_kernel(GatherArgs g, const void* __restrict__ matches, int N,
                                                           __half* __restrict__ p_hi, __half* __restrict__ p_lo,
-                                                          __half* __restrict__ rgb_hi, __half* __restrict__ rgb_lo) {
+                                                          __half* __restrict__ rgb_hi, __half* __restrict__ rgb_lo,
+                                                          const int* __restrict__ rowmap,
+                                                          const int* __restrict__ d_count) {
   __shared__ float dinv[2][16][16];  // act_scale / sqrt(sum_c f^2 + 1e-6) per window pixel
   __shared__ int org[4];
-  const int n = blockIdx.x;
+  const int n = blockIdx.x;          // patch slot
+  if (d_count != nullptr && n >= *d_count) return;
+  const int row = rowmap != nullptr ? rowmap[n] : n;
   const int tid = threadIdx.x;
   if (tid < 4) {
     int v;
     if (IS_FLOAT)
-      v = (int)reinterpret_cast<const float*>(matches)[(size_t)n * 4 + tid];  // .long(): truncation
+      v = (int)reinterpret_cast<const float*>(matches)[(size_t)row * 4 + tid];  // .long(): truncation
     else
-      v = (int)reinterpret_cast<const long long*>(matches)[(size_t)n * 4 + tid];
+      v = (int)reinterpret_cast<const long long*>(matches)[(size_t)row * 4 + tid];
     org[tid] = v - 8;
   }
   __syncthreads();
@@ -141,44 +145,44 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(GatherArgs g, const v
     dinv[s][wy][wx] = __fdiv_rn(kActScale, sqrtf(t + 1e-6f));
   }
   __syncthreads();
-  // main channels: one warp per window position, lane = 16 consecutive channels of the 512
+  // main channels: one warp per window position.  Lane l owns channels [8l, 8l+8) of image 1 AND
+  // of image 2, so every warp store instruction covers one contiguous 512-byte row segment.
   const int lane = tid & 31, wid = tid >> 5;
-  const int j = lane >> 2, sub = lane & 3;     // 64-channel chunk, 16-channel quarter
-  const int s = j >> 2, jj = j & 3;
-  const int lvl = jj == 0 ? 0 : (jj == 1 ? 1 : 2);  // index into nhwc[] (feature levels 1..3)
+  const int jj = lane >> 3;                          // 64-channel chunk inside one image's 256
+  const int lvl = jj == 0 ? 0 : (jj == 1 ? 1 : 2);   // index into nhwc[] (feature levels 1..3)
   const int ds = 2 << lvl;
   const int C = lvl == 2 ? 128 : 64;
-  const int coff = (jj == 3 ? 64 : 0) + sub * 16;
-  const float* fmap = g.nhwc[s][lvl];
-  const int wl = g.W[s] / ds;
-  // 4 window positions per warp iteration: all 16 loads are issued before the first store
-  for (int pos0 = wid; pos0 < kPatchPos; pos0 += 32) {
-    float4 t[4][4];
-    float sc[4];
+  const int coff = (jj == 3 ? 64 : 0) + (lane & 7) * 8;
+  for (int pos0 = wid; pos0 < kPatchPos; pos0 += 16) {
+    float4 t[2][2][2];
+    float sc[2][2];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 2; ++u) {
       const int pos = pos0 + 8 * u;
       const int plane = pos >> 6, iy = (pos >> 3) & 7, ix = pos & 7;
       const int wx = (plane & 1) ? 2 * ix : 2 * ix + 1;
       const int wy = (plane & 2) ? 2 * iy : 2 * iy + 1;
-      const int xi = clamp_idx(org[2 * s] + wx, ds, g.W[s]), yi = clamp_idx(org[2 * s + 1] + wy, ds, g.H[s]);
-      sc[u] = dinv[s][wy][wx];
-      const float4* src = reinterpret_cast<const float4*>(fmap + ((size_t)yi * wl + xi) * C + coff);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) t[u][q] = __ldg(src + q);
+      for (int s = 0; s < 2; ++s) {
+        const int xi = clamp_idx(org[2 * s] + wx, ds, g.W[s]), yi = clamp_idx(org[2 * s + 1] + wy, ds, g.H[s]);
+        sc[u][s] = dinv[s][wy][wx];
+        const float4* src =
+            reinterpret_cast<const float4*>(g.nhwc[s][lvl] + ((size_t)yi * (g.W[s] / ds) + xi) * C + coff);
+        t[u][s][0] = __ldg(src);
+        t[u][s][1] = __ldg(src + 1);
+      }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 2; ++u) {
       const int pos = pos0 + 8 * u;
-      float v[16];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        v[q * 4 + 0] = t[u][q].x * sc[u]; v[q * 4 + 1] = t[u][q].y * sc[u];
-        v[q * 4 + 2] = t[u][q].z * sc[u]; v[q * 4 + 3] = t[u][q].w * sc[u];
+      for (int s = 0; s < 2; ++s) {
+        const float k = sc[u][s];
+        const float v[8] = {t[u][s][0].x * k, t[u][s][0].y * k, t[u][s][0].z * k, t[u][s][0].w * k,
+                            t[u][s][1].x * k, t[u][s][1].y * k, t[u][s][1].z * k, t[u][s][1].w * k};
+        const size_t o = ((size_t)n * kPatchPos + pos) * kMainCh + s * 256 + lane * 8;
+        split_store8(v, p_hi + o, p_lo ? p_lo + o : nullptr);
       }
-      const size_t o = ((size_t)n * kPatchPos + pos) * kMainCh + j * 64 + sub * 16;
-      split_store8(v, p_hi + o, p_lo ? p_lo + o : nullptr);
-      split_store8(v + 8, p_hi + o + 8, p_lo ? p_lo + o + 8 : nullptr);
     }
   }
   // rgb im2col: 64 output pixels x 64 k
@@ -202,7 +206,8 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(GatherArgs g, const v
 }
 
 int launch_patch_gather(const PairFeatures& f1, const PairFeatures& f2, const void* matches, int is_float, int N,
-                        __half* p_hi, __half* p_lo, __half* rgb_hi, __half* rgb_lo, cudaStream_t st) {
+                        __half* p_hi, __half* p_lo, __half* rgb_hi, __half* rgb_lo, const int* rowmap,
+                        const int* d_count, cudaStream_t st) {
   if (N == 0) return 0;
   GatherArgs g;
   const PairFeatures* f[2] = {&f1, &f2};
@@ -214,9 +219,9 @@ int launch_patch_gather(const PairFeatures& f1, const PairFeatures& f2, const vo
     g.W[s] = f[s]->W;
   }
   if (is_float)
-    patch_gather_kernel<true><<<N, 256, 0, st>>>(g, matches, N, p_hi, p_lo, rgb_hi, rgb_lo);
+    patch_gather_kernel<true><<<N, 256, 0, st>>>(g, matches, N, p_hi, p_lo, rgb_hi, rgb_lo, rowmap, d_count);
   else
-    patch_gather_kernel<false><<<N, 256, 0, st>>>(g, matches, N, p_hi, p_lo, rgb_hi, rgb_lo);
+    patch_gather_kernel<false><<<N, 256, 0, st>>>(g, matches, N, p_hi, p_lo, rgb_hi, rgb_lo, rowmap, d_count);
   P2P_LAUNCH_OK();
   return 0;
 }
@@ -228,8 +233,13 @@ template <bool IS_FLOAT>
 __global__ void __launch_bounds__(256) fc_parse_kernel(const float* __restrict__ pooled, FcWeights fc,
                                                       const void* __restrict__ matches_in, int N, float W1, float H1,
                                                       float W2, float H2, float* __restrict__ matches_out,
-                                                      float* __restrict__ probs_out) {
+                                                      float* __restrict__ probs_out, float* __restrict__ raw_out,
+                                                      const int* __restrict__ rowmap, const int* __restrict__ d_count) {
   constexpr int PB = 8;
+  if (d_count != nullptr) {
+    N = *d_count;
+    if ((int)blockIdx.x * PB >= N) return;
+  }
   __shared__ __align__(16) float xs[512][PB];
   __shared__ __align__(16) float h1[512][PB];
   __shared__ __align__(16) float h2[256][PB];
@@ -284,9 +294,10 @@ __global__ void __launch_bounds__(256) fc_parse_kernel(const float* __restrict__
   __syncthreads();
   if (t < 5 * PB) {
     const int j = t / PB, p = t - j * PB;
-    const int n = n0 + p;
-    if (n < N) {
+    if (n0 + p < N) {
+      const int n = rowmap != nullptr ? rowmap[n0 + p] : n0 + p;   // output row
       const float o = o5[j][p];
+      if (raw_out != nullptr) raw_out[(size_t)n * 5 + j] = o;
       if (j < 4) {
         float m;
         if (IS_FLOAT)
@@ -304,14 +315,64 @@ __global__ void __launch_bounds__(256) fc_parse_kernel(const float* __restrict__
 }
 
 int launch_fc_parse(const float* pooled, const FcWeights& fc, const void* matches_in, int is_float, int N, int W1,
-                    int H1, int W2, int H2, float* matches_out, float* probs_out, cudaStream_t st) {
+                    int H1, int W2, int H2, float* matches_out, float* probs_out, float* raw_out, const int* rowmap,
+                    const int* d_count, cudaStream_t st) {
   if (N == 0) return 0;
   if (is_float)
     fc_parse_kernel<true><<<cdiv(N, 8), 256, 0, st>>>(pooled, fc, matches_in, N, (float)W1, (float)H1, (float)W2,
-                                                     (float)H2, matches_out, probs_out);
+                                                     (float)H2, matches_out, probs_out, raw_out, rowmap, d_count);
   else
     fc_parse_kernel<false><<<cdiv(N, 8), 256, 0, st>>>(pooled, fc, matches_in, N, (float)W1, (float)H1, (float)W2,
-                                                      (float)H2, matches_out, probs_out);
+                                                      (float)H2, matches_out, probs_out, raw_out, rowmap, d_count);
+  P2P_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Risk band: the fine stage gathers around trunc(mid).  A row needs fp32-grade mid arithmetic only
+// if one of its coordinates lies within tau px of an integer; coordinates whose raw output is
+// clearly negative get the exact offset -8 in any precision and are never at risk.
+// Single block, order-preserving compaction.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) flag_risky_kernel(const float* __restrict__ m, const float* __restrict__ raw,
+                                                         int N, float tau, float eps_o, int* __restrict__ rowmap,
+                                                         int* __restrict__ d_count) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int r0 = 0; r0 < N; r0 += 1024) {
+    const int r = r0 + tid;
+    int risky = 0;
+    if (r < N) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float v = m[(size_t)r * 4 + j];
+        if (raw[(size_t)r * 5 + j] > -eps_o && fabsf(v - rintf(v)) < tau) risky = 1;
+      }
+    }
+    const unsigned int ball = __ballot_sync(0xffffffffu, risky);
+    if (lane == 0) s_warp[wid] = __popc(ball);
+    __syncthreads();
+    int woff = 0, tot = 0;
+    for (int w = 0; w < 32; ++w) {
+      const int c = s_warp[w];
+      if (w < wid) woff += c;
+      tot += c;
+    }
+    const int base = s_base;
+    if (risky) rowmap[base + woff + __popc(ball & ((1u << lane) - 1u))] = r;
+    __syncthreads();
+    if (tid == 0) s_base = base + tot;
+    __syncthreads();
+  }
+  if (tid == 0) *d_count = s_base;
+}
+
+int launch_flag_risky(const float* matches_out, const float* raw, int N, float tau, float eps_o, int* rowmap,
+                      int* d_count, cudaStream_t st) {
+  flag_risky_kernel<<<1, 1024, 0, st>>>(matches_out, raw, N, tau, eps_o, rowmap, d_count);
   P2P_LAUNCH_OK();
   return 0;
 }

@@ -146,7 +146,8 @@ __device__ __forceinline__ constexpr uint32_t make_idesc_f16(int m, int n) {
 // epilogues: consume one piece of 32 accumulator columns of one row
 // ------------------------------------------------------------------------------------------------
 template <int EPI>
-__device__ __forceinline__ void epilogue_piece(const UmmaEpilogue& e, int m_tile, int row, int col0, const float* v) {
+__device__ __forceinline__ void epilogue_piece(const UmmaEpilogue& e, int n_patches, int m_tile, int row, int col0,
+                                               const float* v) {
   if (EPI == EPI_PLAIN) {
     const int r = m_tile * 128 + row;
     if (r < e.m_rows) {
@@ -157,7 +158,7 @@ __device__ __forceinline__ void epilogue_piece(const UmmaEpilogue& e, int m_tile
     }
   } else if (EPI == EPI_CONV1) {
     const int n = m_tile * 2 + (row >> 6);
-    if (n < e.n_patches) {
+    if (n < n_patches) {
       __align__(16) __half h[32];
       __align__(16) __half l[32];
 #pragma unroll
@@ -185,7 +186,7 @@ __device__ __forceinline__ void epilogue_piece(const UmmaEpilogue& e, int m_tile
       const unsigned int m = __reduce_max_sync(0xffffffffu, __float_as_uint(y));
       if (lane == i) mine = m;
     }
-    if (n < e.n_patches) atomicMax(reinterpret_cast<unsigned int*>(e.pooled) + (size_t)n * 512 + col0 + lane, mine);
+    if (n < n_patches) atomicMax(reinterpret_cast<unsigned int*>(e.pooled) + (size_t)n * 512 + col0 + lane, mine);
   } else if (EPI == EPI_CORR) {
     // rows/cols are in pooling-window order: 4 rows x 4 cols = one 4D window
     const int lane = threadIdx.x & 31;
@@ -241,7 +242,13 @@ __global__ void __launch_bounds__(384, 1) umma_gemm_kernel(const __grid_constant
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  int m_tiles = p.m_tiles;
+  int n_units = p.epi.n_patches;
+  if (p.d_units != nullptr) {
+    n_units = __ldg(p.d_units);
+    m_tiles = (n_units + p.a_units_per_tile - 1) / p.a_units_per_tile;
+  }
+  const int total_tiles = m_tiles * p.n_tiles;
   const int nsteps = p.nsteps;
   const int seg_len = SEGMENTED ? p.seg_len : nsteps;
   const int nseg = (nsteps + seg_len - 1) / seg_len;
@@ -379,7 +386,7 @@ __global__ void __launch_bounds__(384, 1) umma_gemm_kernel(const __grid_constant
           if (lane == 0) mbar_arrive(&tempty_bar[slot]);
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) epilogue_piece<EPI>(p.epi, m_tile, row, colbase + c * 32, tot + c * 32);
+        for (int c = 0; c < 4; ++c) epilogue_piece<EPI>(p.epi, n_units, m_tile, row, colbase + c * 32, tot + c * 32);
       } else {
         const int slot = seg & 1;
         const uint32_t sph = (uint32_t)(seg >> 1) & 1u;
@@ -390,7 +397,7 @@ __global__ void __launch_bounds__(384, 1) umma_gemm_kernel(const __grid_constant
         for (int c = 0; c < 4; ++c) {
           float v[32];
           tmem_ld32(taddr + c * 32, v);
-          epilogue_piece<EPI>(p.epi, m_tile, row, colbase + c * 32, v);
+          epilogue_piece<EPI>(p.epi, n_units, m_tile, row, colbase + c * 32, v);
         }
         tc_fence_before();
         __syncwarp();

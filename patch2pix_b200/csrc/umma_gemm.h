@@ -35,6 +35,7 @@ struct UmmaGemmParams {
   int n_tiles;           // 256-column tiles
   int a_units_per_tile;  // step of the outermost A coordinate per m-tile (2 patches, or 128 rows)
   int seg_len;           // k-steps accumulated in TMEM before a drain (0 / >= nsteps: whole K)
+  const int* d_units;    // optional device count of A units (patches): m_tiles = ceil(*d_units / a_units_per_tile)
   UmmaEpilogue epi;
 };
 

@@ -206,12 +206,13 @@ def test_mutual_matching_and_unique_rows_ops():
 # ------------------------------------------------------------------------------------------------
 # refine stage
 # ------------------------------------------------------------------------------------------------
-def _refine_case(net, sd, pair_idx, H, W, matches, impl, mid_passes, fine_passes):
+def _refine_case(net, sd, pair_idx, H, W, matches, impl, mid_passes, fine_passes, mid_band=0):
     from oracle import p2p_oracle as O
     f1, f2, c1, c2 = _feats(net, pair_idx, H, W)
     net.set_option('gemm_impl', impl)
     net.set_option('mid_passes', mid_passes)
     net.set_option('fine_passes', fine_passes)
+    net.set_option('mid_band', mid_band)
     try:
         with torch.no_grad():
             o_mid, o_midp = O.forward_fine_match(c1, c2, [matches], sd, 'regress_mid.')
@@ -224,6 +225,7 @@ def _refine_case(net, sd, pair_idx, H, W, matches, impl, mid_passes, fine_passes
         net.set_option('gemm_impl', 0)
         net.set_option('mid_passes', 3)
         net.set_option('fine_passes', 1)
+        net.set_option('mid_band', 40)
     r = {
         'mid_err': (mid[0].cpu() - o_mid[0]).abs().max().item(),
         'mid_p_err': (midp[0].cpu() - o_midp[0]).abs().max().item(),
@@ -248,15 +250,16 @@ def _random_matches(n, H, W, seed, integer):
     return m.long() if integer else m
 
 
-@pytest.mark.parametrize('impl,mid_passes,fine_passes', [(1, 3, 3), (0, 3, 3), (0, 3, 1), (0, 1, 1)],
-                         ids=['simt33', 'tc33', 'tc31', 'tc11'])
+@pytest.mark.parametrize('impl,mid_passes,fine_passes,band', [(1, 3, 3, 0), (0, 3, 3, 0), (0, 3, 1, 0), (0, 1, 1, 0), (0, 3, 1, 40)],
+                         ids=['simt33', 'tc33', 'tc31', 'tc11', 'band31'])
 @pytest.mark.parametrize('integer', [True, False])
-def test_refine_vs_oracle(nets, seeded_sd, impl, mid_passes, fine_passes, integer):
+def test_refine_vs_oracle(nets, seeded_sd, impl, mid_passes, fine_passes, band, integer):
     net = nets[1]
     H, W = 128, 160
-    r = _refine_case(net, seeded_sd, 9, H, W, _random_matches(77, H, W, 3, integer), impl, mid_passes, fine_passes)
-    _report(f'refine_impl{impl}_m{mid_passes}_f{fine_passes}_{"i" if integer else "f"}', r)
-    mid_tol = 2e-4 if mid_passes == 3 else 0.05
+    n = 77 if band == 0 else 777
+    r = _refine_case(net, seeded_sd, 9, H, W, _random_matches(n, H, W, 3, integer), impl, mid_passes, fine_passes, band)
+    _report(f'refine_impl{impl}_m{mid_passes}_f{fine_passes}_b{band}_{"i" if integer else "f"}', r)
+    mid_tol = 2e-4 if (mid_passes == 3 and band == 0) else 0.05
     fine_tol = 2e-4 if fine_passes == 3 else 0.05
     assert r['mid_err'] < mid_tol, r
     assert r['fine_same_err'] < fine_tol, r
@@ -272,6 +275,8 @@ def test_refine_ragged_sizes(nets, seeded_sd, n):
     H, W = 96, 128
     r = _refine_case(net, seeded_sd, 4, H, W, _random_matches(n, H, W, n, True), 0, 3, 1)
     assert r['mid_err'] < 2e-4 and r['fine_same_err'] < 0.05 and r['fine_same_p_err'] < 1e-3, r
+    r = _refine_case(net, seeded_sd, 4, H, W, _random_matches(n, H, W, n, True), 0, 3, 1, 40)
+    assert r['mid_err'] < 0.05 and r['straddle_rows'] == 0 and r['fine_same_err'] < 0.05, r
 
 
 def test_refine_empty_and_errors(nets):
