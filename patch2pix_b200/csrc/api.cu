@@ -798,7 +798,7 @@ int p2p_refine(p2p_handle_t h, int which, const void* matches_in, int is_float, 
   P2P_REQUIRE(B.p_hi && B.p_lo && B.r_hi && B.r_lo && B.y_hi && B.y_lo && B.pooled && B.raw && B.rowmap,
               "scratch carve failed");
   B.d_count = B.rowmap + n;
-  h->last_band_count = band ? B.d_count : nullptr;
+  if (which == 0) h->last_band_count = band ? B.d_count : nullptr;
   if (!band)
     return run_regressor(h, R, which, passes, B, matches_in, is_float, n, nullptr, nullptr, matches_out, probs_out,
                          nullptr, st);
@@ -807,7 +807,8 @@ int p2p_refine(p2p_handle_t h, int which, const void* matches_in, int is_float, 
     return rc;
   {
     ProfScope ps(h, P2P_PROF_FLAG, st);
-    if ((rc = launch_flag_risky(matches_out, B.raw, n, h->opt_mid_band * 1e-3f, 0.02f, B.rowmap, B.d_count, st)))
+    if ((rc = launch_flag_risky(matches_in, is_float, B.raw, n, h->opt_mid_band * 1e-3f, 0.02f, h->pf[0].W, h->pf[0].H,
+                                h->pf[1].W, h->pf[1].H, B.rowmap, B.d_count, st)))
       return rc;
   }
   return run_regressor(h, R, which, 3, B, matches_in, is_float, n, B.rowmap, B.d_count, matches_out, probs_out,

@@ -467,12 +467,13 @@ __global__ void __launch_bounds__(512) nc_layer2_kernel(const float* __restrict_
         const float2 q2 = *reinterpret_cast<const float2*>(p + 4);
         r[rr][0] = q.x; r[rr][1] = q.y; r[rr][2] = q.z; r[rr][3] = q.w; r[rr][4] = q2.x; r[rr][5] = q2.y;
       }
-      const float* wrow = w2s + ab * 9 * 32 + c0 + cc;
+      const float* wrow = w2s + ab * 9 * 32 + c0;
 #pragma unroll
       for (int d = 0; d < 3; ++d)
 #pragma unroll
         for (int e = 0; e < 3; ++e) {
-          const float wv = wrow[(d * 3 + e) * 32];
+          const float4 w4 = *reinterpret_cast<const float4*>(wrow + (d * 3 + e) * 32);
+          const float wv = cc == 0 ? w4.x : (cc == 1 ? w4.y : (cc == 2 ? w4.z : w4.w));
 #pragma unroll
           for (int kk = 0; kk < 2; ++kk)
 #pragma unroll

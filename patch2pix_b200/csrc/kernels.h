@@ -46,8 +46,8 @@ int launch_patch_gather(const PairFeatures& f1, const PairFeatures& f2, const vo
                         const int* d_count, cudaStream_t st);
 // Rows whose refined coordinates sit within `tau` px of an integer (and whose offset is not the exact
 // relu-clamped -8) are collected, in ascending order, into rowmap / d_count.
-int launch_flag_risky(const float* matches_out, const float* raw, int N, float tau, float eps_o, int* rowmap,
-                      int* d_count, cudaStream_t st);
+int launch_flag_risky(const void* matches_in, int is_float, const float* raw, int N, float tau, float eps_o, int W1,
+                      int H1, int W2, int H2, int* rowmap, int* d_count, cudaStream_t st);
 
 struct FcWeights {                // BN folded, transposed to [in][out] for coalesced reads
   float *w1t, *b1, *w2t, *b2, *w3t, *b3;

@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(256) fc_parse_kernel(const float* __restrict__
     float a0[PB], a1[PB];
 #pragma unroll
     for (int p = 0; p < PB; ++p) { a0[p] = 0.f; a1[p] = 0.f; }
+#pragma unroll 8
     for (int k = 0; k < 512; ++k) {
       const float w0 = __ldg(fc.w1t + (size_t)k * 512 + t), w1 = __ldg(fc.w1t + (size_t)k * 512 + t + 256);
       const float4 xa = *reinterpret_cast<const float4*>(&xs[k][0]);
@@ -272,6 +273,7 @@ __global__ void __launch_bounds__(256) fc_parse_kernel(const float* __restrict__
     float a[PB];
 #pragma unroll
     for (int p = 0; p < PB; ++p) a[p] = 0.f;
+#pragma unroll 8
     for (int k = 0; k < 512; ++k) {
       const float w = __ldg(fc.w2t + (size_t)k * 256 + t);
       const float4 xa = *reinterpret_cast<const float4*>(&h1[k][0]);
@@ -334,9 +336,11 @@ int launch_fc_parse(const float* pooled, const FcWeights& fc, const void* matche
 // clearly negative get the exact offset -8 in any precision and are never at risk.
 // Single block, order-preserving compaction.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) flag_risky_kernel(const float* __restrict__ m, const float* __restrict__ raw,
-                                                         int N, float tau, float eps_o, int* __restrict__ rowmap,
-                                                         int* __restrict__ d_count) {
+template <bool IS_FLOAT>
+__global__ void __launch_bounds__(1024) flag_risky_kernel(const void* __restrict__ matches_in,
+                                                         const float* __restrict__ raw, int N, float tau, float eps_o,
+                                                         float W1, float H1, float W2, float H2,
+                                                         int* __restrict__ rowmap, int* __restrict__ d_count) {
   __shared__ int s_warp[32];
   __shared__ int s_base;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -348,8 +352,17 @@ __global__ void __launch_bounds__(1024) flag_risky_kernel(const float* __restric
     if (r < N) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float v = m[(size_t)r * 4 + j];
-        if (raw[(size_t)r * 5 + j] > -eps_o && fabsf(v - rintf(v)) < tau) risky = 1;
+        const float o = raw[(size_t)r * 5 + j];
+        if (o <= -eps_o) continue;                       // offset is exactly -8 in any precision
+        float m;
+        if (IS_FLOAT)
+          m = reinterpret_cast<const float*>(matches_in)[(size_t)r * 4 + j];
+        else
+          m = (float)reinterpret_cast<const long long*>(matches_in)[(size_t)r * 4 + j];
+        const float v = m + (16.f * tanhf(fmaxf(o, 0.f)) - 8.f);   // un-clamped coordinate
+        const float hi = (j == 0) ? W1 : (j == 1) ? H1 : (j == 2) ? W2 : H2;
+        if (v <= -tau || v >= hi + tau) continue;        // clamped to the same bound on both sides
+        if (fabsf(v - rintf(v)) < tau) risky = 1;
       }
     }
     const unsigned int ball = __ballot_sync(0xffffffffu, risky);
@@ -370,9 +383,14 @@ __global__ void __launch_bounds__(1024) flag_risky_kernel(const float* __restric
   if (tid == 0) *d_count = s_base;
 }
 
-int launch_flag_risky(const float* matches_out, const float* raw, int N, float tau, float eps_o, int* rowmap,
-                      int* d_count, cudaStream_t st) {
-  flag_risky_kernel<<<1, 1024, 0, st>>>(matches_out, raw, N, tau, eps_o, rowmap, d_count);
+int launch_flag_risky(const void* matches_in, int is_float, const float* raw, int N, float tau, float eps_o, int W1,
+                      int H1, int W2, int H2, int* rowmap, int* d_count, cudaStream_t st) {
+  if (is_float)
+    flag_risky_kernel<true><<<1, 1024, 0, st>>>(matches_in, raw, N, tau, eps_o, (float)W1, (float)H1, (float)W2,
+                                                (float)H2, rowmap, d_count);
+  else
+    flag_risky_kernel<false><<<1, 1024, 0, st>>>(matches_in, raw, N, tau, eps_o, (float)W1, (float)H1, (float)W2,
+                                                 (float)H2, rowmap, d_count);
   P2P_LAUNCH_OK();
   return 0;
 }
