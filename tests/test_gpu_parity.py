@@ -406,3 +406,59 @@ def test_full_size_640x480(nets, seeded_sd):
                'mid_err': (mid[0].cpu()[idx] - o_mid[0]).abs().max().item()}
         _report('full_640x480', rep)
         assert rep['max_err_px_nonstraddle'] < 0.5 and rep['max_conf_err'] < 1e-3 and rep['straddle_rows'] <= 1, rep
+
+
+# ------------------------------------------------------------------------------------------------
+# other BASELINE.json configurations
+# ------------------------------------------------------------------------------------------------
+def test_config1_480x320_ptmax200(nets, seeded_sd):
+    """BASELINE configs[1]: single 480x320 pair, full coarse+mid+fine, ptmax=200 panc=8 (1600 patches/stage);
+    the whole sequence is compared with the oracle (proposals exact, refine on every row)."""
+    o, g = _e2e(nets[8], seeded_sd, 21, 320, 480, 200, 8)
+    o_fine, o_finep, o_mid, o_midp, o_cm = o
+    fine, finep, mid, midp, cm = g
+    assert cm[0].shape == (1600, 4) and torch.equal(cm[0].cpu(), o_cm[0])
+    strad = (mid[0].cpu().long() != o_mid[0].long()).any(1)
+    err = (fine[0].cpu() - o_fine[0]).abs().max(1)[0]
+    perr = (finep[0].cpu() - o_finep[0]).abs()
+    rep = {'n': 1600, 'straddle_rows': int(strad.sum()), 'max_err_px_nonstraddle': err[~strad].max().item(),
+           'max_conf_err': perr[~strad].max().item(), 'mid_err': (mid[0].cpu() - o_mid[0]).abs().max().item()}
+    _report('config1_480x320', rep)
+    assert rep['max_err_px_nonstraddle'] < 0.5 and rep['max_conf_err'] < 1e-3 and rep['straddle_rows'] <= 2, rep
+
+
+def test_config3_1024x768_ptmax1000_memory_path(nets, seeded_sd):
+    """BASELINE configs[3]: 1024x768, ptmax=1000 (x8 anchors = 8000 patches/stage): stresses the 4D-volume
+    memory path (V = 9.4 M cells, un-pooled volume 604 MB never materialised, NC hidden 1.2 GB).
+    Size-independent properties + oracle on the pooled correlation of a strip and on a patch subsample."""
+    from oracle import p2p_oracle as O
+    net = nets[8]
+    H, W = 768, 1024
+    f1, f2, c1, c2 = _feats(net, 1, H, W)
+    with torch.no_grad():
+        corr4d, delta4d, st = net.forward_coarse_match(f1[-1], f2[-1], ksize=2, return_stages=True)
+        assert corr4d.shape == (1, 1, 48, 64, 48, 64)
+        a = O.l2_normalize(c1[-1], 1)[:, :, :8]           # first 8 feature rows of image 1 = 4 pooled rows
+        b = O.l2_normalize(c2[-1], 1)
+        pooled_ref = O.maxpool4d(O.feat_correlation_4d(a, b), 2)[0]
+        np.testing.assert_allclose(st['pooled'][:, :, :4].cpu().numpy(), pooled_ref.numpy(), rtol=0, atol=1e-6)
+        # MutualMatching is symmetric under swapping the images: corr(B,A) == corr(A,B)^T
+        corr_t, _ = net.forward_coarse_match(f2[-1], f1[-1], ksize=2)
+        np.testing.assert_allclose(corr_t.cpu().numpy(), corr4d.permute(0, 1, 4, 5, 2, 3).cpu().numpy(), rtol=2e-3, atol=1e-6)
+        assert float(corr4d.min()) >= 0.0 and torch.isfinite(corr4d).all()
+        np.random.seed(5)
+        fine, finep, mid, midp, anch = net.match_from_feats(f1, f2, 2, ptmax=1000, return_all=True)
+        torch.cuda.synchronize()
+        assert anch[0].shape == (8000, 4) and fine[0].shape == (8000, 4) and finep[0].shape == (8000,)
+        fm = fine[0].cpu()
+        assert (fm[:, 0::2] >= 0).all() and (fm[:, 0::2] <= W).all() and (fm[:, 1::2] >= 0).all() and (fm[:, 1::2] <= H).all()
+        assert ((mid[0].cpu() - anch[0].cpu().float()).abs() <= 8.0 + 1e-4).all()
+        idx = torch.arange(0, 8000, 100)
+        o_mid, _ = O.forward_fine_match(c1, c2, [anch[0].cpu()[idx]], seeded_sd, 'regress_mid.')
+        o_fine, o_fp = O.forward_fine_match(c1, c2, o_mid, seeded_sd, 'regress_fine.')
+        strad = (mid[0].cpu()[idx].long() != o_mid[0].long()).any(1)
+        err = (fm[idx] - o_fine[0]).abs().max(1)[0]
+        rep = {'n_sub': int(idx.numel()), 'straddle_rows': int(strad.sum()), 'max_err_px_nonstraddle': err[~strad].max().item(),
+               'max_conf_err': (finep[0].cpu()[idx] - o_fp[0]).abs()[~strad].max().item()}
+        _report('config3_1024x768', rep)
+        assert rep['max_err_px_nonstraddle'] < 0.5 and rep['max_conf_err'] < 1e-3 and rep['straddle_rows'] <= 1, rep
