@@ -109,28 +109,51 @@ class ClockSampler(threading.Thread):
 # cannot travel to the GPU box).  One step = the full coarse stage of one pair + the two refine
 # stages on a bounded subset of the 3200 patches, extrapolated to the full pair.
 # --------------------------------------------------------------------------------------------------
-def cpu_step(O, sd, im1, im2, ptmax, panc, n_sample, with_backbone=True):
+def cpu_threads():
+    """Threads for the CPU arm: every host core up to 32 (torch's CPU kernels for this path -- hundreds of
+    small conv3d / index ops -- get slower, not faster, beyond that; measured on the 128-core GPU box).
+    Override with P2P_CPU_THREADS."""
+    cores = os.cpu_count() or 1
+    return int(os.environ.get('P2P_CPU_THREADS', min(cores, 32)))
+
+
+def cpu_step(O, sd, im1, im2, ptmax, panc, n_sample, nc_slices=None):
+    """One bounded sample of the reference algorithm on the CPU for one pair: full backbone, full
+    correlation / max-pool / mutual matching / proposals, the NC 4D conv on `nc_slices` of its
+    first-dimension output slices (all if None) and the two refine stages on `n_sample` patches;
+    the sampled parts are scaled to the full pair."""
     t0 = time.perf_counter()
     with torch.no_grad():
         f1 = O.backbone_forward_all(im1, sd)
         f2 = O.backbone_forward_all(im2, sd)
         t1 = time.perf_counter()
-        corr4d, delta4d = O.forward_coarse_match(f1[-1], f2[-1], sd, 2)
-        cm, sc = O.cal_coarse_matches(corr4d, delta4d, 2, upsample=O.UPSAMPLE, center=True)
+        a, b = O.l2_normalize(f1[-1], 1), O.l2_normalize(f2[-1], 1)
+        corr, mi, mj, mk, ml = O.maxpool4d(O.feat_correlation_4d(a, b), 2)
+        corr = O.mutual_matching(corr)
+        t2 = time.perf_counter()
+        hA = corr.shape[2]
+        sl = None if (nc_slices is None or nc_slices >= hA) else list(range(0, hA, max(1, hA // nc_slices)))[:nc_slices]
+        nc = O.neigh_consensus(corr, sd, sl)
+        t3 = time.perf_counter()
+        nc_scale = 1.0 if sl is None else hA / len(sl)
+        corr4d = O.mutual_matching(nc if sl is None else corr)
+        cm, sc = O.cal_coarse_matches(corr4d, (mi, mj, mk, ml), 2, upsample=O.UPSAMPLE, center=True)
         np.random.seed(0)
         cm, sc = O.filter_coarse(cm, sc, 0.0, True, ptmax=ptmax)
         anch = O.shift_to_anchors(cm, panc)
-        t2 = time.perf_counter()
+        t4 = time.perf_counter()
         n_full = anch[0].shape[0]
         sub = [anch[0][:n_sample]]
         mid, _ = O.forward_fine_match(f1, f2, sub, sd, 'regress_mid.')
         fine, _ = O.forward_fine_match(f1, f2, mid, sd, 'regress_fine.')
-        t3 = time.perf_counter()
+        t5 = time.perf_counter()
     n_sub = sub[0].shape[0]
-    t_refine_full = (t3 - t2) * n_full / max(n_sub, 1)
-    return {'backbone_s': t1 - t0, 'coarse_s': t2 - t1, 'refine_s_extrapolated': t_refine_full,
-            'hot_path_s': (t2 - t1) + t_refine_full, 'e2e_s': (t1 - t0) + (t2 - t1) + t_refine_full,
-            'n_sample': n_sub, 'n_full': n_full}
+    t_nc = (t3 - t2) * nc_scale
+    t_refine = (t5 - t4) * n_full / max(n_sub, 1)
+    hot = (t2 - t1) + t_nc + (t4 - t3) + t_refine
+    return {'backbone_s': t1 - t0, 'coarse_s': (t2 - t1) + t_nc + (t4 - t3), 'nc_s_extrapolated': t_nc,
+            'refine_s_extrapolated': t_refine, 'hot_path_s': hot, 'e2e_s': (t1 - t0) + hot, 'wall_s': t5 - t0,
+            'n_sample': n_sub, 'n_full': n_full, 'nc_slices': 'all' if sl is None else f'{len(sl)}/{hA}'}
 
 
 def run_reference(args):
@@ -139,25 +162,29 @@ def run_reference(args):
         return
     from oracle import p2p_oracle as O
     from patch2pix_b200.synth import make_seeded_state_dict, synthetic_pair
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    threads = cpu_threads()
+    torch.set_num_threads(threads)
     sd = make_seeded_state_dict(0)
     H, W = args.height, args.width
     pairs = [synthetic_pair(p, H, W) for p in range(2)]
+    # size the per-step sample so that the whole run stays within ~3 minutes
+    budget = 150.0 / max(args.steps + min(args.warmup, 1), 1)
+    nc_slices, n_sample = (None, args.cpu_sample_patches) if budget > 12 else ((8, 96) if budget > 4 else (3, 32))
     for i in range(min(args.warmup, 1)):
-        cpu_step(O, sd, *pairs[i % 2], args.ptmax, PANC_DEF, min(args.cpu_sample_patches, 64))
-    rs = [cpu_step(O, sd, *pairs[i % 2], args.ptmax, PANC_DEF, args.cpu_sample_patches) for i in range(args.steps)]
+        cpu_step(O, sd, *pairs[i % 2], args.ptmax, PANC_DEF, n_sample, nc_slices)
+    rs = [cpu_step(O, sd, *pairs[i % 2], args.ptmax, PANC_DEF, n_sample, nc_slices) for i in range(args.steps)]
     hot = sum(r['hot_path_s'] for r in rs) / len(rs)
     e2e = sum(r['e2e_s'] for r in rs) / len(rs)
-    sample = (f'per step: backbone + full coarse stage of one {W}x{H} pair + mid/fine refine on {rs[0]["n_sample"]} of '
-              f'{rs[0]["n_full"]} patches, refine time scaled by {rs[0]["n_full"]}/{rs[0]["n_sample"]}')
+    sample = (f'per step, one {W}x{H} pair: full backbone + correlation/max-pool/mutual/proposals, NC 4D conv on '
+              f'{rs[0]["nc_slices"]} output slices, mid+fine refine on {rs[0]["n_sample"]} of {rs[0]["n_full"]} patches; '
+              f'sampled parts scaled to the full pair (mean wall {sum(r["wall_s"] for r in rs) / len(rs):.2f} s/step)')
     line = {'impl': 'reference', 'metric': 'image-pairs/sec', 'value': 1.0 / e2e, 'unit': 'pairs/s', 'n_gpus': 0,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': e2e * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': f'{W}x{H} pair, ptmax={args.ptmax} panc={PANC_DEF} (BASELINE configs[2])',
                        'sequence': 'train_patch2pix.py:97-118 under eval/no_grad', 'includes_backbone': True},
-            'cpu_baseline': {'value': 1.0 / e2e, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port', 'sample': sample,
-                             'hot_path_only_pairs_per_s': 1.0 / hot},
+            'cpu_baseline': {'value': 1.0 / e2e, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port', 'sample': sample,
+                             'host_cores': os.cpu_count(), 'hot_path_only_pairs_per_s': 1.0 / hot},
             'e2e': {'value': 1.0 / e2e, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line), flush=True)
@@ -210,22 +237,52 @@ def run_ours(args):
     n_patches = args.ptmax * PANC_DEF
     results = torch.zeros(K, n_patches, 5, device=dev)
 
-    def hot_step(i, out_slot=None):
+    # Two pairs are kept in flight: the coarse stage of pair i is enqueued before the host waits for the
+    # mutual-match count of pair i-1 (filter_coarse's host sync), so the GPU never idles on that sync.
+    def hot_submit(i):
         f1, f2 = feats[i % n_distinct]
+        return (i, net.submit_coarse(f1, f2, 2, True))
+
+    def hot_finish(tk, out_slot=None):
+        i, ticket = tk
         np.random.seed(i)
-        fine, fine_p, _ = net.match_from_feats(f1, f2, 2, ptmax=args.ptmax)
+        fine, fine_p, _ = net.finish_match(ticket, 0.0, args.ptmax)
         if out_slot is not None:
             results[out_slot, :, :4] = fine[0]
             results[out_slot, :, 4] = fine_p[0]
 
-    def e2e_step(i, host_out):
+    def hot_loop(first, steps, record):
+        prev = None
+        for j in range(steps):
+            tk = hot_submit(first + j)
+            if prev is not None:
+                hot_finish(prev[0], prev[1])
+            prev = (tk, j if record else None)
+        hot_finish(prev[0], prev[1])
+
+    def e2e_submit(i):
         a, b = pinned[i % n_distinct]
         im1 = a.to(dev, non_blocking=True)
         im2 = b.to(dev, non_blocking=True)
+        f1 = net.extract.forward_all(im1, [], True)
+        f2 = net.extract.forward_all(im2, [], True)
+        return (i, net.submit_coarse(f1, f2, 2, True))
+
+    def e2e_finish(tk, host_out):
+        i, ticket = tk
         np.random.seed(i)
-        fine, fine_p, _ = net.predict_train_sequence(im1, im2, ptmax=args.ptmax)
-        host_out[:, :4].copy_(fine[0], non_blocking=True)
+        fine, fine_p, _ = net.finish_match(ticket, 0.0, args.ptmax)
+        host_out[:, :4].copy_(fine[0], non_blocking=True)          # D2H read of this step's result
         host_out[:, 4].copy_(fine_p[0], non_blocking=True)
+
+    def e2e_loop(first, steps, host_outs):
+        prev = None
+        for j in range(steps):
+            tk = e2e_submit(first + j)
+            if prev is not None:
+                e2e_finish(prev, host_outs[(j - 1) % len(host_outs)])
+            prev = tk
+        e2e_finish(prev, host_outs[(steps - 1) % len(host_outs)])
         torch.cuda.current_stream().synchronize()
 
     def barrier():
@@ -250,16 +307,14 @@ def run_ours(args):
 
     with torch.no_grad():
         # ---- hot path, features resident in HBM -------------------------------------------------
-        for i in range(Wm):
-            hot_step(i)
+        hot_loop(0, Wm, False)
         net.set_option('profile', 1)
         net._handle.profile_read()
         l0 = net._handle.launch_count()
         sampler = ClockSampler(local) if rank == 0 else None
 
         def hot_region(steps):
-            for i in range(steps):
-                hot_step(Wm + i, i)
+            hot_loop(Wm, steps, True)
             sharder.gather_results(results)              # NCCL gather of the matches (inside the timed region)
         ms_hot = timed(hot_region, K, sampler)
         launches = net._handle.launch_count() - l0
@@ -272,13 +327,11 @@ def run_ours(args):
         # backbone in PyTorch's default cuDNN mode (TF32 convolutions allowed, as the reference would run)
         torch.backends.cudnn.allow_tf32 = not args.backbone_fp32
         torch.backends.cudnn.benchmark = True
-        host_out = torch.empty(n_patches, 5).pin_memory()
-        for i in range(min(Wm, 3)):
-            e2e_step(i, host_out)
+        host_outs = [torch.empty(n_patches, 5).pin_memory() for _ in range(2)]
+        e2e_loop(0, max(min(Wm, 3), 1), host_outs)
 
         def e2e_region(steps):
-            for i in range(steps):
-                e2e_step(Wm + i, host_out)
+            e2e_loop(Wm, steps, host_outs)
         ms_e2e = timed(e2e_region, K)
 
     if rank == 0:
@@ -316,12 +369,14 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             from oracle import p2p_oracle as O
-            cores = os.cpu_count() or 1
-            torch.set_num_threads(cores)
+            threads = cpu_threads()
+            torch.set_num_threads(threads)
             sd_cpu = make_seeded_state_dict(0)
-            r = cpu_step(O, sd_cpu, *imgs[0], args.ptmax, PANC_DEF, args.cpu_sample_patches)
-            cpu = {'value': 1.0 / r['hot_path_s'], 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
-                   'sample': (f'oracle port of the reference on host cores: full coarse stage of one {W}x{H} pair '
+            cpu_step(O, sd_cpu, *imgs[0], args.ptmax, PANC_DEF, 16, 2)          # warm-up
+            r = cpu_step(O, sd_cpu, *imgs[0], args.ptmax, PANC_DEF, args.cpu_sample_patches, None)
+            cpu = {'value': 1.0 / r['hot_path_s'], 'unit': 'pairs/s', 'cores': threads, 'host_cores': os.cpu_count(),
+                   'kind': 'port',
+                   'sample': (f'oracle port of the reference, {threads} threads: full coarse stage of one {W}x{H} pair '
                               f'({r["coarse_s"]:.2f} s) + mid/fine refine on {r["n_sample"]} of {r["n_full"]} patches scaled to '
                               f'the full pair ({r["refine_s_extrapolated"]:.2f} s); backbone excluded ({r["backbone_s"]:.2f} s)'),
                    'with_backbone_pairs_per_s': 1.0 / r['e2e_s']}
@@ -336,6 +391,7 @@ def run_ours(args):
                                    f'(BASELINE configs[2]); hot path = correlation .. fine matches, features resident in HBM',
                        'sequence': 'train_patch2pix.py:97-118 under eval/no_grad', 'pairs_per_step': world,
                        'l2': 'distinct pair per step, per-step working set (~3 GB) >> 126 MB L2',
+                       'pipelining': 'two pairs in flight per GPU (coarse of pair i is enqueued before the host sync of pair i-1)',
                        'options': opts},
             'e2e': {'value': pairs / (ms_e2e / 1e3), 'unit': 'pairs/s', 'ms_per_step': ms_e2e / K,
                     'h2d_bytes_per_step': 2 * 3 * H * W * 4, 'd2h_bytes_per_step': n_patches * 5 * 4,

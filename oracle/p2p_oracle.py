@@ -119,17 +119,18 @@ def mutual_matching(corr):
     return corr * (ca * cb)
 
 
-def conv4d(x, w, bias):
+def conv4d(x, w, bias, out_slices=None):
     """networks/ncn/conv4d.py:12-74 with pre-permuted filters [k1,Cout,Cin,k2,k3,k4]
     (conv4d.py:118-120): loop over the first spatial dim, three conv3d per slice,
-    bias added with the centre tap only."""
+    bias added with the centre tap only.  `out_slices` (timing samples only, bench.py's CPU
+    baseline) restricts the loop to a subset of output slices; the other slices stay zero."""
     b, c, h, ww, d, t = x.shape
     xp = x.permute(2, 0, 1, 3, 4, 5).contiguous()
     pad = w.shape[0] // 2
     z = torch.zeros(pad, b, c, ww, d, t)
     xp = torch.cat((z, xp, z), 0)
     out = torch.zeros(h, b, w.shape[1], ww, d, t)
-    for i in range(h):
+    for i in (range(h) if out_slices is None else out_slices):
         out[i] = F.conv3d(xp[i + pad], w[pad], bias=bias, stride=1, padding=pad)
         for p in range(1, pad + 1):
             out[i] = out[i] + F.conv3d(xp[i + pad - p], w[pad - p], bias=None, stride=1, padding=pad)
@@ -137,11 +138,11 @@ def conv4d(x, w, bias):
     return out.permute(1, 2, 0, 3, 4, 5).contiguous()
 
 
-def neigh_consensus(x, sd):
+def neigh_consensus(x, sd, out_slices=None):
     """networks/ncn/model.py:124-155 (symmetric mode, 2 layers 1->16->1, ReLU after each)."""
     def net(y):
-        y = F.relu(conv4d(y, sd['ncn.conv.0.weight'], sd['ncn.conv.0.bias']))
-        return F.relu(conv4d(y, sd['ncn.conv.2.weight'], sd['ncn.conv.2.bias']))
+        y = F.relu(conv4d(y, sd['ncn.conv.0.weight'], sd['ncn.conv.0.bias'], out_slices))
+        return F.relu(conv4d(y, sd['ncn.conv.2.weight'], sd['ncn.conv.2.bias'], out_slices))
     return net(x) + net(x.permute(0, 1, 4, 5, 2, 3)).permute(0, 1, 4, 5, 2, 3)
 
 

@@ -36,9 +36,34 @@ def _check_cuda_f32(t, name):
     return t.contiguous()
 
 
-def unique_rows(rows, mutual=True, handle=None):
-    """Device-side np.unique(rows, axis=0, return_index, return_counts): lexicographically ordered
-    first-occurrence indices of distinct rows (mutual: rows seen more than once)."""
+class _UniqueTicket:
+    """unique_rows in flight: ids buffer on the device, count on its way to pinned host memory."""
+
+    def __init__(self, ids, cnt_host, event):
+        self.ids, self.cnt_host, self.event = ids, cnt_host, event
+
+    def wait(self):
+        self.event.synchronize()   # the one host sync of filter_coarse (the reference syncs here too: utils.py:42)
+        n, bad = self.cnt_host.tolist()
+        if bad:
+            raise RuntimeError('filter_coarse: match coordinates must lie in [0, 65535]')
+        return self.ids[:n].long()
+
+
+_pinned_ring = []
+_pinned_next = [0]
+
+
+def _pinned_count_buffer():
+    """Small ring of pinned int32[2] buffers (cudaHostAlloc per call would cost more than the kernel)."""
+    if len(_pinned_ring) < 16:
+        _pinned_ring.append(torch.empty(2, dtype=torch.int32).pin_memory())
+        return _pinned_ring[-1]
+    _pinned_next[0] = (_pinned_next[0] + 1) % len(_pinned_ring)
+    return _pinned_ring[_pinned_next[0]]
+
+
+def unique_rows_submit(rows, mutual=True, handle=None):
     if not (rows.is_cuda and rows.dtype == torch.int64 and rows.dim() == 2 and rows.shape[1] == 4):
         raise RuntimeError('unique_rows expects a CUDA int64 [n,4] tensor')
     rows = rows.contiguous()
@@ -46,22 +71,29 @@ def unique_rows(rows, mutual=True, handle=None):
     h = handle or _lib.default_handle(rows.device)
     ids = torch.empty(max(n, 1), dtype=torch.int32, device=rows.device)
     cnt = torch.empty(2, dtype=torch.int32, device=rows.device)
+    cnt_host = _pinned_count_buffer()
     with torch.cuda.device(rows.device):
         _lib.check(h.lib.p2p_unique_rows(h.h, _lib.ptr(rows), n, int(bool(mutual)), _lib.ptr(ids), _lib.ptr(cnt),
                                          h.stream()))
-    c = cnt.tolist()       # the one host sync of filter_coarse (the reference syncs here too: utils.py:42)
-    if c[1]:
-        raise RuntimeError('filter_coarse: match coordinates must lie in [0, 65535]')
-    return ids[:c[0]].long()
+        cnt_host.copy_(cnt, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(rows.device))
+    return _UniqueTicket(ids, cnt_host, ev)
 
 
-def filter_coarse(coarse_matches, match_scores, ncn_thres=0.0, mutual=True, ptmax=None):
+def unique_rows(rows, mutual=True, handle=None):
+    """Device-side np.unique(rows, axis=0, return_index, return_counts): lexicographically ordered
+    first-occurrence indices of distinct rows (mutual: rows seen more than once)."""
+    return unique_rows_submit(rows, mutual, handle).wait()
+
+
+def filter_coarse(coarse_matches, match_scores, ncn_thres=0.0, mutual=True, ptmax=None, _tickets=None):
     """networks/utils.py:38-72 with the np.unique step on the device.  Quirks kept: lexicographic
     output order, first-occurrence scores, 'skip a filter that would empty the set', degenerate
     [0,0,0,0] ids and global-numpy-RNG shuffle/tile for ptmax."""
     matches, scores = [], []
-    for imatches, iscores in zip(coarse_matches, match_scores):
-        ids = unique_rows(imatches, mutual)
+    for ib, (imatches, iscores) in enumerate(zip(coarse_matches, match_scores)):
+        ids = _tickets[ib].wait() if _tickets is not None else unique_rows(imatches, mutual)
         if len(ids) > 0:
             iscores = iscores[ids]
             imatches = imatches[ids]
@@ -262,8 +294,7 @@ class Patch2PixB200(nn.Module):
         return self._handle
 
     # -- coarse --------------------------------------------------------------------------------
-    def forward_coarse_match(self, feat1, feat2, ksize=1, return_stages=False):
-        """networks/patch2pix.py:120-136 -> (corr4d [b,1,hA,wA,hB,wB] f32, delta4d 4 x int64 | None)."""
+    def _coarse_raw(self, feat1, feat2, ksize, return_stages=False):
         h = self._ready()
         feat1 = _check_cuda_f32(feat1, 'feat1')
         feat2 = _check_cuda_f32(feat2, 'feat2')
@@ -281,15 +312,25 @@ class Patch2PixB200(nn.Module):
                                             _lib.ptr(corr4d[i]), _lib.ptr(code[i]) if code is not None else None,
                                             _lib.ptr(pooled[i]) if pooled is not None else None,
                                             _lib.ptr(ncn[i]) if ncn is not None else None, h.stream()))
-            delta4d = None
-            if ksize > 1:
-                ds = [torch.empty(b, 1, hA, wA, hB, wB, dtype=torch.int64, device=dev) for _ in range(4)]
+        if return_stages:
+            return corr4d, code, {'pooled': pooled, 'ncn': ncn}
+        return corr4d, code
+
+    def forward_coarse_match(self, feat1, feat2, ksize=1, return_stages=False):
+        """networks/patch2pix.py:120-136 -> (corr4d [b,1,hA,wA,hB,wB] f32, delta4d 4 x int64 | None)."""
+        r = self._coarse_raw(feat1, feat2, ksize, return_stages)
+        corr4d, code = r[0], r[1]
+        h = self._handle
+        delta4d = None
+        if ksize > 1:
+            with torch.cuda.device(corr4d.device):
+                ds = [torch.empty(code.shape, dtype=torch.int64, device=code.device) for _ in range(4)]
                 _lib.check(h.lib.p2p_delta_unpack(h.h, _lib.ptr(code), code.numel(), ksize, *[_lib.ptr(d) for d in ds],
                                                   h.stream()))
-                delta4d = _DeltaTuple(ds)
-                delta4d.code = code
+            delta4d = _DeltaTuple(ds)
+            delta4d.code = code
         if return_stages:
-            return corr4d, delta4d, {'pooled': pooled, 'ncn': ncn}
+            return corr4d, delta4d, r[2]
         return corr4d, delta4d
 
     def cal_coarse_matches(self, corr4d, delta4d, ksize=1, do_softmax=True, upsample=16, sort=False, center=True,
@@ -380,17 +421,28 @@ class Patch2PixB200(nn.Module):
         cm, sc = self.cal_coarse_matches(corr4d, delta4d, ksize=ksize, upsample=self.upsample, center=center)
         return filter_coarse(cm, sc, ncn_thres, mutual)
 
-    def match_from_feats(self, feats1, feats2, ksize=2, ncn_thres=0.0, mutual=True, ptmax=None, return_all=False):
-        """Everything after the backbone.  ptmax=None: the predict_fine sequence
-        (networks/patch2pix.py:250-276); ptmax>0 with panc>1: the training-loop forward sequence
-        (train_patch2pix.py:97-118), i.e. the 'ptmax=400 panc=8' benchmark configuration."""
-        corr4d, delta4d = self.forward_coarse_match(feats1[-1], feats2[-1], ksize=ksize)
-        cm, sc = self.cal_coarse_matches(corr4d, delta4d, ksize=ksize, upsample=self.upsample, center=True)
+    def submit_coarse(self, feats1, feats2, ksize=2, mutual=True):
+        """First half of match_from_feats: enqueue correlation .. proposals and the device-side
+        unique/mutual pass, start the asynchronous read-back of the mutual-match count and return a
+        ticket.  Nothing here waits for the GPU, so the caller can keep a second pair in flight."""
+        corr4d, code = self._coarse_raw(feats1[-1], feats2[-1], ksize)
+        delta = None
+        if code is not None:
+            delta = _DeltaTuple(())
+            delta.code = code
+        cm, sc = self.cal_coarse_matches(corr4d, delta, ksize=ksize, upsample=self.upsample, center=True)
+        tickets = [unique_rows_submit(m, mutual, self._handle) for m in cm]
+        return {'feats1': feats1, 'feats2': feats2, 'cm': cm, 'sc': sc, 'tickets': tickets, 'mutual': mutual}
+
+    def finish_match(self, ticket, ncn_thres=0.0, ptmax=None, return_all=False):
+        """Second half: wait for the count, run filter_coarse's host logic (numpy RNG sampling for
+        ptmax exactly as the reference), shift to anchors, mid and fine refine."""
+        feats1, feats2, cm, sc = ticket['feats1'], ticket['feats2'], ticket['cm'], ticket['sc']
         if ptmax:
             if self.panc > 1 and ptmax > 0:
-                cm, sc = filter_coarse(cm, sc, 0.0, True, ptmax=ptmax)
+                cm, sc = filter_coarse(cm, sc, 0.0, True, ptmax=ptmax, _tickets=ticket['tickets'] if ticket['mutual'] else None)
         else:
-            cm, sc = filter_coarse(cm, sc, ncn_thres, mutual)
+            cm, sc = filter_coarse(cm, sc, ncn_thres, ticket['mutual'], _tickets=ticket['tickets'])
         cm = self.shift_to_anchors(cm)
         single = len(cm) == 1
         if single:
@@ -406,6 +458,14 @@ class Patch2PixB200(nn.Module):
         if return_all:
             return fine, fine_p, mid, mid_p, cm
         return fine, fine_p, cm
+
+    def match_from_feats(self, feats1, feats2, ksize=2, ncn_thres=0.0, mutual=True, ptmax=None, return_all=False):
+        """Everything after the backbone.  ptmax=None: the predict_fine sequence
+        (networks/patch2pix.py:250-276); ptmax>0 with panc>1: the training-loop forward sequence
+        (train_patch2pix.py:97-118), i.e. the 'ptmax=400 panc=8' benchmark configuration (which always
+        filters with mutual=True, train_patch2pix.py:100-101)."""
+        ticket = self.submit_coarse(feats1, feats2, ksize, True if ptmax else mutual)
+        return self.finish_match(ticket, ncn_thres, ptmax, return_all)
 
     def predict_fine(self, im1, im2, ksize=2, ncn_thres=0.0, mutual=True, return_all=False):
         """networks/patch2pix.py:250-276."""

@@ -441,7 +441,7 @@ def test_config3_1024x768_ptmax1000_memory_path(nets, seeded_sd):
         a = O.l2_normalize(c1[-1], 1)[:, :, :8]           # first 8 feature rows of image 1 = 4 pooled rows
         b = O.l2_normalize(c2[-1], 1)
         pooled_ref = O.maxpool4d(O.feat_correlation_4d(a, b), 2)[0]
-        np.testing.assert_allclose(st['pooled'][:, :, :4].cpu().numpy(), pooled_ref.numpy(), rtol=0, atol=1e-6)
+        np.testing.assert_allclose(st['pooled'][:, :, :4].cpu().numpy(), pooled_ref.numpy(), rtol=0, atol=3e-6)
         # MutualMatching is symmetric under swapping the images: corr(B,A) == corr(A,B)^T
         corr_t, _ = net.forward_coarse_match(f2[-1], f1[-1], ksize=2)
         np.testing.assert_allclose(corr_t.cpu().numpy(), corr4d.permute(0, 1, 4, 5, 2, 3).cpu().numpy(), rtol=2e-3, atol=1e-6)
