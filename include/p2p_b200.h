@@ -127,10 +127,12 @@ P2P_API int p2p_proposals(p2p_handle_t h, const float* corr4d, const uint8_t* de
 
 /* ---- the np.unique part of filter_coarse (networks/utils.py:38-50): lexicographically sorted
  * first-occurrence indices of the distinct rows (mutual != 0: only rows occurring more than once).
- * rows int64 [n,4] with coordinates in [0,65535]; ids_out int32 [n]; count_out int32 [2] =
- * {number of ids, 1 if a coordinate was out of range}. */
-P2P_API int p2p_unique_rows(p2p_handle_t h, const int64_t* rows, int n, int mutual, int32_t* ids_out, int32_t* count_out,
-                    void* stream);
+ * rows int64 [n,4] with coordinates in [0,65535]; ids_out int32 [n]; count_out int32 [4] =
+ * {number of ids, 1 if a coordinate was out of range, number of those ids whose score > thres,
+ * number of ALL rows whose score > thres}; the last two (scores may be NULL -> 0) let the caller
+ * evaluate filter_coarse's score threshold (utils.py:53) without a second device sync. */
+P2P_API int p2p_unique_rows(p2p_handle_t h, const int64_t* rows, int n, int mutual, const float* scores, float thres,
+                    int32_t* ids_out, int32_t* count_out, void* stream);
 
 /* ---- refine: Patch2Pix.forward_fine_match for one batch item (networks/patch2pix.py:157-218):
  * select_local_patch_feats + L2 normalise + FeatRegressNet + parse_regressor_out.

@@ -617,12 +617,12 @@ int p2p_proposals(p2p_handle_t h, const float* corr4d, const uint8_t* delta_code
                           do_softmax, (long long*)matches_out, scores_out, reinterpret_cast<cudaStream_t>(stream));
 }
 
-int p2p_unique_rows(p2p_handle_t h, const int64_t* rows, int n, int mutual, int32_t* ids_out, int32_t* count_out,
-                    void* stream) {
+int p2p_unique_rows(p2p_handle_t h, const int64_t* rows, int n, int mutual, const float* scores, float thres,
+                    int32_t* ids_out, int32_t* count_out, void* stream) {
   P2P_ENTER(h);
   P2P_REQUIRE(rows && ids_out && count_out, "null tensor pointer");
   ProfScope ps(h, P2P_PROF_PROPOSALS, reinterpret_cast<cudaStream_t>(stream));
-  return launch_unique_rows((const long long*)rows, n, mutual, ids_out, count_out,
+  return launch_unique_rows((const long long*)rows, n, mutual, scores, thres, ids_out, count_out,
                             reinterpret_cast<cudaStream_t>(stream));
 }
 

@@ -634,6 +634,7 @@ int launch_proposals(const float* corr, const uint8_t* code, int hA, int wA, int
 // count_out[0] = number of ids written, count_out[1] = 1 if a coordinate was out of [0,65535].
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) unique_rows_kernel(const long long* __restrict__ rows, int n, int P, int mutual,
+                                                          const float* __restrict__ scores, float thres,
                                                           int* __restrict__ ids_out, int* __restrict__ count_out) {
   extern __shared__ __align__(16) unsigned char smraw[];
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smraw);
@@ -641,8 +642,9 @@ __global__ void __launch_bounds__(1024) unique_rows_kernel(const long long* __re
   __shared__ int s_bad;
   __shared__ int s_warp[32];
   __shared__ int s_base;
+  __shared__ int s_pass_sel, s_pass_all;
   const int tid = threadIdx.x, T = blockDim.x;
-  if (tid == 0) { s_bad = 0; s_base = 0; }
+  if (tid == 0) { s_bad = 0; s_base = 0; s_pass_sel = 0; s_pass_all = 0; }
   __syncthreads();
   for (int i = tid; i < P; i += T) {
     unsigned long long k = ~0ull;
@@ -697,28 +699,40 @@ __global__ void __launch_bounds__(1024) unique_rows_kernel(const long long* __re
       tot += cnt;
     }
     const int base = s_base;
-    if (sel) ids_out[base + woff + wpre] = idx[p];
+    if (sel) {
+      ids_out[base + woff + wpre] = idx[p];
+      if (scores != nullptr && scores[idx[p]] > thres) atomicAdd(&s_pass_sel, 1);
+    }
     __syncthreads();
     if (tid == 0) s_base = base + tot;
     __syncthreads();
   }
+  if (scores != nullptr) {
+    int c = 0;
+    for (int i = tid; i < n; i += T) c += scores[i] > thres;
+    if (c) atomicAdd(&s_pass_all, c);
+  }
+  __syncthreads();
   if (tid == 0) {
     count_out[0] = s_base;
     count_out[1] = s_bad;
+    count_out[2] = s_pass_sel;   // selected rows whose score exceeds thres
+    count_out[3] = s_pass_all;   // all rows whose score exceeds thres
   }
 }
 
-int launch_unique_rows(const long long* rows, int n, int mutual, int* ids_out, int* count_out, cudaStream_t st) {
+int launch_unique_rows(const long long* rows, int n, int mutual, const float* scores, float thres, int* ids_out,
+                       int* count_out, cudaStream_t st) {
   P2P_REQUIRE(n >= 0 && n <= 16384, "unique_rows: at most 16384 candidate rows");
   if (n == 0) {
-    P2P_CUDA_OK(cudaMemsetAsync(count_out, 0, 2 * sizeof(int), st));
+    P2P_CUDA_OK(cudaMemsetAsync(count_out, 0, 4 * sizeof(int), st));
     return 0;
   }
   int P = 2;
   while (P < n) P <<= 1;
   const size_t smem = (size_t)P * 12;
   P2P_CUDA_OK(cudaFuncSetAttribute(unique_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  unique_rows_kernel<<<1, 1024, smem, st>>>(rows, n, P, mutual, ids_out, count_out);
+  unique_rows_kernel<<<1, 1024, smem, st>>>(rows, n, P, mutual, scores, thres, ids_out, count_out);
   P2P_LAUNCH_OK();
   return 0;
 }

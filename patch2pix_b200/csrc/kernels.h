@@ -21,7 +21,8 @@ int launch_neigh_consensus(const float* x, int hA, int wA, int hB, int wB, const
                            const float* w2p, float b2, float* hidden, float* out, cudaStream_t st);
 int launch_proposals(const float* corr, const uint8_t* code, int hA, int wA, int hB, int wB, int ksize, int upsample,
                      int center, int do_softmax, long long* matches, float* scores, cudaStream_t st);
-int launch_unique_rows(const long long* rows, int n, int mutual, int* ids_out, int* count_out, cudaStream_t st);
+int launch_unique_rows(const long long* rows, int n, int mutual, const float* scores, float thres, int* ids_out,
+                       int* count_out, cudaStream_t st);
 
 // ---- refine.cu ---------------------------------------------------------------------------------
 // Activation scale applied before the fp16 hi/lo split of the L2-normalised patch features.

@@ -239,8 +239,8 @@ __device__ __forceinline__ void cp_async_commit_fc() { asm volatile("cp.async.co
 template <int N>
 __device__ __forceinline__ void cp_async_wait_fc() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int kFcChunk = 32;   // weight rows (k) per staged chunk
-constexpr int kFcPB = 16;      // patches per block (weight traffic from L2 = N/16 x 1.5 MB)
+constexpr int kFcChunk = 16;   // weight rows (k) per staged chunk (2 blocks per SM fit)
+constexpr int kFcPB = 8;       // patches per block (16/block measured slower: 200 blocks do not fill 148 SMs evenly)
 
 // acc[o][p] += sum_k x[k][p] * wt[k][o] for the thread's NO outputs (o = t + i*256), K rows, OUT columns
 template <int NO, int OUT, int PB>

@@ -37,14 +37,15 @@ def _check_cuda_f32(t, name):
 
 
 class _UniqueTicket:
-    """unique_rows in flight: ids buffer on the device, count on its way to pinned host memory."""
+    """unique_rows in flight: ids buffer on the device, counters on their way to pinned host memory."""
 
-    def __init__(self, ids, cnt_host, event):
-        self.ids, self.cnt_host, self.event = ids, cnt_host, event
+    def __init__(self, ids, cnt_host, event, thres):
+        self.ids, self.cnt_host, self.event, self.thres = ids, cnt_host, event, thres
+        self.n_pass_selected = self.n_pass_all = None
 
     def wait(self):
         self.event.synchronize()   # the one host sync of filter_coarse (the reference syncs here too: utils.py:42)
-        n, bad = self.cnt_host.tolist()
+        n, bad, self.n_pass_selected, self.n_pass_all = self.cnt_host.tolist()
         if bad:
             raise RuntimeError('filter_coarse: match coordinates must lie in [0, 65535]')
         return self.ids[:n].long()
@@ -55,30 +56,32 @@ _pinned_next = [0]
 
 
 def _pinned_count_buffer():
-    """Small ring of pinned int32[2] buffers (cudaHostAlloc per call would cost more than the kernel)."""
+    """Small ring of pinned int32[4] buffers (cudaHostAlloc per call would cost more than the kernel)."""
     if len(_pinned_ring) < 16:
-        _pinned_ring.append(torch.empty(2, dtype=torch.int32).pin_memory())
+        _pinned_ring.append(torch.empty(4, dtype=torch.int32).pin_memory())
         return _pinned_ring[-1]
     _pinned_next[0] = (_pinned_next[0] + 1) % len(_pinned_ring)
     return _pinned_ring[_pinned_next[0]]
 
 
-def unique_rows_submit(rows, mutual=True, handle=None):
+def unique_rows_submit(rows, mutual=True, handle=None, scores=None, thres=0.0):
     if not (rows.is_cuda and rows.dtype == torch.int64 and rows.dim() == 2 and rows.shape[1] == 4):
         raise RuntimeError('unique_rows expects a CUDA int64 [n,4] tensor')
     rows = rows.contiguous()
     n = rows.shape[0]
     h = handle or _lib.default_handle(rows.device)
     ids = torch.empty(max(n, 1), dtype=torch.int32, device=rows.device)
-    cnt = torch.empty(2, dtype=torch.int32, device=rows.device)
+    cnt = torch.empty(4, dtype=torch.int32, device=rows.device)
     cnt_host = _pinned_count_buffer()
+    if scores is not None:
+        scores = _check_cuda_f32(scores.flatten(), 'scores')
     with torch.cuda.device(rows.device):
-        _lib.check(h.lib.p2p_unique_rows(h.h, _lib.ptr(rows), n, int(bool(mutual)), _lib.ptr(ids), _lib.ptr(cnt),
-                                         h.stream()))
+        _lib.check(h.lib.p2p_unique_rows(h.h, _lib.ptr(rows), n, int(bool(mutual)), _lib.ptr(scores), float(thres),
+                                         _lib.ptr(ids), _lib.ptr(cnt), h.stream()))
         cnt_host.copy_(cnt, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(rows.device))
-    return _UniqueTicket(ids, cnt_host, ev)
+    return _UniqueTicket(ids, cnt_host, ev, float(thres) if scores is not None else None)
 
 
 def unique_rows(rows, mutual=True, handle=None):
@@ -93,11 +96,16 @@ def filter_coarse(coarse_matches, match_scores, ncn_thres=0.0, mutual=True, ptma
     [0,0,0,0] ids and global-numpy-RNG shuffle/tile for ptmax."""
     matches, scores = [], []
     for ib, (imatches, iscores) in enumerate(zip(coarse_matches, match_scores)):
-        ids = _tickets[ib].wait() if _tickets is not None else unique_rows(imatches, mutual)
+        tk = _tickets[ib] if _tickets is not None else unique_rows_submit(imatches, mutual, None, iscores, ncn_thres)
+        ids = tk.wait()
+        n_pass = tk.n_pass_selected if len(ids) > 0 else tk.n_pass_all
         if len(ids) > 0:
             iscores = iscores[ids]
             imatches = imatches[ids]
-        ids = torch.nonzero(iscores.flatten() > ncn_thres, as_tuple=False).flatten()
+        if tk.thres == float(ncn_thres) and n_pass == iscores.numel():
+            ids = torch.arange(iscores.numel(), device=iscores.device)   # every row passes: no second sync
+        else:
+            ids = torch.nonzero(iscores.flatten() > ncn_thres, as_tuple=False).flatten()
         if ptmax:
             if len(ids) == 0:
                 ids = torch.tensor([0, 0, 0, 0]).long()
@@ -421,7 +429,7 @@ class Patch2PixB200(nn.Module):
         cm, sc = self.cal_coarse_matches(corr4d, delta4d, ksize=ksize, upsample=self.upsample, center=center)
         return filter_coarse(cm, sc, ncn_thres, mutual)
 
-    def submit_coarse(self, feats1, feats2, ksize=2, mutual=True):
+    def submit_coarse(self, feats1, feats2, ksize=2, mutual=True, ncn_thres=0.0):
         """First half of match_from_feats: enqueue correlation .. proposals and the device-side
         unique/mutual pass, start the asynchronous read-back of the mutual-match count and return a
         ticket.  Nothing here waits for the GPU, so the caller can keep a second pair in flight."""
@@ -431,7 +439,7 @@ class Patch2PixB200(nn.Module):
             delta = _DeltaTuple(())
             delta.code = code
         cm, sc = self.cal_coarse_matches(corr4d, delta, ksize=ksize, upsample=self.upsample, center=True)
-        tickets = [unique_rows_submit(m, mutual, self._handle) for m in cm]
+        tickets = [unique_rows_submit(m, mutual, self._handle, sc_i, ncn_thres) for m, sc_i in zip(cm, sc)]
         return {'feats1': feats1, 'feats2': feats2, 'cm': cm, 'sc': sc, 'tickets': tickets, 'mutual': mutual}
 
     def finish_match(self, ticket, ncn_thres=0.0, ptmax=None, return_all=False):
@@ -464,7 +472,7 @@ class Patch2PixB200(nn.Module):
         (networks/patch2pix.py:250-276); ptmax>0 with panc>1: the training-loop forward sequence
         (train_patch2pix.py:97-118), i.e. the 'ptmax=400 panc=8' benchmark configuration (which always
         filters with mutual=True, train_patch2pix.py:100-101)."""
-        ticket = self.submit_coarse(feats1, feats2, ksize, True if ptmax else mutual)
+        ticket = self.submit_coarse(feats1, feats2, ksize, True if ptmax else mutual, 0.0 if ptmax else ncn_thres)
         return self.finish_match(ticket, ncn_thres, ptmax, return_all)
 
     def predict_fine(self, im1, im2, ksize=2, ncn_thres=0.0, mutual=True, return_all=False):
