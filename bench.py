@@ -262,10 +262,7 @@ def run_ours(args):
 
     def e2e_submit(i):
         a, b = pinned[i % n_distinct]
-        im1 = a.to(dev, non_blocking=True)
-        im2 = b.to(dev, non_blocking=True)
-        f1 = net.extract.forward_all(im1, [], True)
-        f2 = net.extract.forward_all(im2, [], True)
+        f1, f2 = net.extract_pair(a, b, slot=i)    # pinned host images: H2D into the graph's input, then the backbone
         return (i, net.submit_coarse(f1, f2, 2, True))
 
     def e2e_finish(tk, host_out):
@@ -327,6 +324,7 @@ def run_ours(args):
         # backbone in PyTorch's default cuDNN mode (TF32 convolutions allowed, as the reference would run)
         torch.backends.cudnn.allow_tf32 = not args.backbone_fp32
         torch.backends.cudnn.benchmark = True
+        net.enable_backbone_graphs(H, W, instances=2)
         host_outs = [torch.empty(n_patches, 5).pin_memory() for _ in range(2)]
         e2e_loop(0, max(min(Wm, 3), 1), host_outs)
 
@@ -395,7 +393,7 @@ def run_ours(args):
                        'options': opts},
             'e2e': {'value': pairs / (ms_e2e / 1e3), 'unit': 'pairs/s', 'ms_per_step': ms_e2e / K,
                     'h2d_bytes_per_step': 2 * 3 * H * W * 4, 'd2h_bytes_per_step': n_patches * 5 * 4,
-                    'path': 'pinned host images -> H2D -> cuDNN ResNet34 pyramid (' + ('fp32' if args.backbone_fp32 else 'TF32 convs, PyTorch default') + ') -> hot path -> D2H matches+scores'},
+                    'path': 'pinned host images -> H2D -> cuDNN ResNet34 pyramid, both images as one batch, CUDA graph (' + ('fp32' if args.backbone_fp32 else 'TF32 convs, PyTorch default') + ') -> hot path -> D2H matches+scores'},
             'gpu_launches': launches, 'roofline': roofline, 'kernels': kern, 'clocks': clocks, 'cpu_baseline': cpu,
         }
         print(json.dumps(line), flush=True)

@@ -387,17 +387,25 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int kNc2MaxCopies = 12;   // ceil(hB*wB / threads) <= 8 for 2x4 cells per thread (+ slack)
+constexpr int kNc2MaxCopies = 12;   // per-thread copy slots per plane (4-byte path: ceil(hB*wB/threads) <= 8)
+constexpr int kNc2Left = 4;         // interior starts at column 4 so that 16-byte cp.async rows stay aligned
 
-__global__ void __launch_bounds__(512) nc_layer2_kernel(const float* __restrict__ hidden, int hA, int wA, int hB,
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src)
+               : "memory");
+}
+
+// VEC: wB % 4 == 0 -> planes are staged with 16-byte copies (4x fewer copy instructions).
+template <bool VEC>
+__global__ void __launch_bounds__(384) nc_layer2_kernel(const float* __restrict__ hidden, int hA, int wA, int hB,
                                                        int wB, const float* __restrict__ w2p, float b2,
                                                        float* __restrict__ out) {
   extern __shared__ __align__(16) float smem[];
-  const int PW = ((wB + 2 + 3) / 4) * 4 + 4;  // pitch: multiple of 4 floats, covers 4*tl+5
-  const int PH = hB + 2 + 1;                  // covers 2*tk+3
+  const int PW = kNc2Left + ((wB + 3) / 4) * 4 + 4;   // [3 unused | left halo | interior | right halo ...]
+  const int PH = hB + 2 + 1;                          // covers 2*tk+3
   const int plane = PH * PW;
-  float* w2s = smem;                          // [81][32]
-  float* tile = smem + 81 * 32;               // [2 buffers][4 planes][PH][PW]
+  float* w2s = smem;                                  // [81][32]
+  float* tile = smem + 81 * 32;                       // [2 buffers][4 planes][PH][PW]
   __shared__ int s_ab[9];
   __shared__ int s_nab;
   const int nthreads = blockDim.x * blockDim.y;
@@ -405,7 +413,7 @@ __global__ void __launch_bounds__(512) nc_layer2_kernel(const float* __restrict_
   const int a = blockIdx.x, ia = a / wA, ja = a - ia * wA;
   const int nB = hB * wB;
   for (int i = tid; i < 81 * 32; i += nthreads) w2s[i] = w2p[i];
-  for (int i = tid; i < 8 * plane; i += nthreads) tile[i] = 0.f;   // halo stays zero for the whole kernel
+  for (int i = tid; i < 8 * plane + 16; i += nthreads) tile[i] = 0.f;   // halo stays zero for the whole kernel
   if (tid == 0) {
     int n = 0;
     for (int ab = 0; ab < 9; ++ab) {
@@ -414,15 +422,23 @@ __global__ void __launch_bounds__(512) nc_layer2_kernel(const float* __restrict_
     }
     s_nab = n;
   }
-  // per-thread copy slots: element e = tid + j*nthreads of a plane -> (src offset, smem offset)
-  int src_off[kNc2MaxCopies], dst_off[kNc2MaxCopies];
+  // per-thread copy slots (units: 4 floats if VEC else 1 float).  Slots past the end of the plane
+  // re-copy the last unit into a scratch area behind the tiles, so the copy loop needs no predicates.
+  const int unit = VEC ? 4 : 1;
+  const int nunits = nB / unit;
+  const int wunits = wB / unit;
+  const int nslots = (nunits + nthreads - 1) / nthreads;   // <= kNc2MaxCopies (checked on the host)
+  constexpr int MAXS = VEC ? 3 : kNc2MaxCopies;
+  int src_off[MAXS], dst_off[MAXS];
 #pragma unroll
-  for (int j = 0; j < kNc2MaxCopies; ++j) {
+  for (int j = 0; j < MAXS; ++j) {
     const int e = tid + j * nthreads;
-    const int k = e / wB, l = e - k * wB;
-    src_off[j] = e < nB ? e : -1;
-    dst_off[j] = (k + 1) * PW + l + 1;
+    const int ec = e < nunits ? e : nunits - 1;
+    const int k = ec / wunits, l = (ec - k * wunits) * unit;
+    src_off[j] = ec * unit;
+    dst_off[j] = e < nunits ? (k + 1) * PW + kNc2Left + l : -1;
   }
+  float* scratch = tile + 8 * plane;   // 16 floats
   __syncthreads();
   const int nab = s_nab;
   const int nitems = 2 * nab * 4;
@@ -434,10 +450,18 @@ __global__ void __launch_bounds__(512) nc_layer2_kernel(const float* __restrict_
     const float* src = hidden + ((size_t)(si * wA + sj) * 32 + net * 16 + cg * 4) * nB;
     float* dst = tile + (item & 1) * 4 * plane;
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc)
+    for (int j = 0; j < MAXS; ++j) {
+      if (j < nslots) {
 #pragma unroll
-      for (int j = 0; j < kNc2MaxCopies; ++j)
-        if (src_off[j] >= 0) cp_async4(dst + cc * plane + dst_off[j], src + (size_t)cc * nB + src_off[j]);
+        for (int cc = 0; cc < 4; ++cc) {
+          float* d = dst_off[j] >= 0 ? dst + cc * plane + dst_off[j] : scratch;
+          if (VEC)
+            cp_async16(d, src + (size_t)cc * nB + src_off[j]);
+          else
+            cp_async4(d, src + (size_t)cc * nB + src_off[j]);
+        }
+      }
+    }
     cp_async_commit();
   };
   const int tl = threadIdx.x, tk = threadIdx.y;
@@ -462,10 +486,9 @@ __global__ void __launch_bounds__(512) nc_layer2_kernel(const float* __restrict_
       float r[4][6];
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) {
-        const float* p = buf + cc * plane + (2 * tk + rr) * PW + 4 * tl;
-        const float4 q = *reinterpret_cast<const float4*>(p);
-        const float2 q2 = *reinterpret_cast<const float2*>(p + 4);
-        r[rr][0] = q.x; r[rr][1] = q.y; r[rr][2] = q.z; r[rr][3] = q.w; r[rr][4] = q2.x; r[rr][5] = q2.y;
+        const float* p = buf + cc * plane + (2 * tk + rr) * PW + 4 * tl + kNc2Left - 1;   // B column 4*tl-1
+        const float4 q = *reinterpret_cast<const float4*>(p + 1);
+        r[rr][0] = p[0]; r[rr][1] = q.x; r[rr][2] = q.y; r[rr][3] = q.z; r[rr][4] = q.w; r[rr][5] = p[5];
       }
       const float* wrow = w2s + ab * 9 * 32 + c0;
 #pragma unroll
@@ -509,13 +532,19 @@ int launch_neigh_consensus(const float* x, int hA, int wA, int hB, int wB, const
   }
   {
     dim3 block(cdiv(wB, 4), cdiv(hB, 2));
-    P2P_REQUIRE(block.x * block.y <= 512, "NC layer 2: pooled B grid too large (hB*wB <= 4096)");
+    P2P_REQUIRE(block.x * block.y <= 384, "NC layer 2: pooled B grid too large (hB*wB <= 3072)");
     P2P_REQUIRE(cdiv(hB * wB, (int)(block.x * block.y)) <= kNc2MaxCopies, "NC layer 2: copy slots exhausted");
-    const int PW = ((wB + 2 + 3) / 4) * 4 + 4, PH = hB + 3;
-    const size_t smem = sizeof(float) * (81 * 32 + 8 * PH * PW);
+    P2P_REQUIRE(wB % 4 != 0 || cdiv(hB * wB / 4, (int)(block.x * block.y)) <= 3, "NC layer 2: vector copy slots exhausted");
+    const int PW = kNc2Left + ((wB + 3) / 4) * 4 + 4, PH = hB + 3;
+    const size_t smem = sizeof(float) * (81 * 32 + 8 * PH * PW + 16);
     P2P_REQUIRE(smem <= 200 * 1024, "NC layer 2: pooled B grid does not fit shared memory");
-    P2P_CUDA_OK(cudaFuncSetAttribute(nc_layer2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nc_layer2_kernel<<<nA, block, smem, st>>>(hidden, hA, wA, hB, wB, w2p, b2, out);
+    if (wB % 4 == 0) {
+      P2P_CUDA_OK(cudaFuncSetAttribute(nc_layer2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      nc_layer2_kernel<true><<<nA, block, smem, st>>>(hidden, hA, wA, hB, wB, w2p, b2, out);
+    } else {
+      P2P_CUDA_OK(cudaFuncSetAttribute(nc_layer2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      nc_layer2_kernel<false><<<nA, block, smem, st>>>(hidden, hA, wA, hB, wB, w2p, b2, out);
+    }
     P2P_LAUNCH_OK();
   }
   return 0;

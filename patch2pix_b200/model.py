@@ -477,15 +477,51 @@ class Patch2PixB200(nn.Module):
 
     def predict_fine(self, im1, im2, ksize=2, ncn_thres=0.0, mutual=True, return_all=False):
         """networks/patch2pix.py:250-276."""
-        feats1 = self.extract.forward_all(im1, [], early_feat=True)
-        feats2 = self.extract.forward_all(im2, [], early_feat=True)
+        feats1, feats2 = self.extract_pair(im1, im2)
         return self.match_from_feats(feats1, feats2, ksize, ncn_thres, mutual, None, return_all)
+
+    # -- backbone (feeds the path) ---------------------------------------------------------------
+    def extract_pair(self, im1, im2, slot=0):
+        """ResNet34 pyramids of both images (networks/patch2pix.py:222-226).  Equal-sized images go
+        through the extractor as one batch of 2; with `enable_backbone_graphs` the batch runs as a
+        captured CUDA graph (one of two alternating instances, so two pairs can be in flight)."""
+        if im1.shape != im2.shape:
+            return (self.extract.forward_all(im1, [], early_feat=True), self.extract.forward_all(im2, [], early_feat=True))
+        g = getattr(self, '_bb_graphs', None)
+        if g is not None and tuple(im1.shape) == g['shape'] and im1.shape[0] == 1:
+            inst = g['inst'][slot % len(g['inst'])]
+            inst['inp'][0:1].copy_(im1, non_blocking=True)
+            inst['inp'][1:2].copy_(im2, non_blocking=True)
+            inst['graph'].replay()
+            feats = inst['out']
+        else:
+            feats = self.extract.forward_all(torch.cat([im1, im2], 0), [], early_feat=True)
+        b = im1.shape[0]
+        return [f[:b] for f in feats], [f[b:] for f in feats]
+
+    def enable_backbone_graphs(self, height, width, instances=2):
+        """Capture the (launch-bound) backbone for a fixed image size into CUDA graphs."""
+        shape = (1, 3, height, width)
+        insts = []
+        with torch.no_grad(), torch.cuda.device(self.device):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(instances):
+                    inp = torch.zeros(2, 3, height, width, device=self.device)
+                    for _ in range(3):
+                        self.extract.forward_all(inp, [], early_feat=True)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, stream=side):
+                        out = self.extract.forward_all(inp, [], early_feat=True)
+                    insts.append({'inp': inp, 'graph': graph, 'out': out})
+            torch.cuda.current_stream().wait_stream(side)
+        self._bb_graphs = {'shape': shape, 'inst': insts}
 
     def predict_train_sequence(self, im1, im2, ksize=2, ptmax=400, return_all=False):
         """train_patch2pix.py:97-118 under eval()/no_grad: forward -> cal_coarse_matches ->
         filter_coarse(ptmax) -> shift_to_anchors -> mid -> fine (the benchmark configuration)."""
-        feats1 = self.extract.forward_all(im1, [], early_feat=True)
-        feats2 = self.extract.forward_all(im2, [], early_feat=True)
+        feats1, feats2 = self.extract_pair(im1, im2)
         return self.match_from_feats(feats1, feats2, ksize, 0.0, True, ptmax, return_all)
 
     def refine_matches(self, im1, im2, coarse_matches, io_thres):
