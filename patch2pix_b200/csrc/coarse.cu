@@ -396,9 +396,12 @@ __device__ __forceinline__ void cp_async16(float* dst_smem, const float* src) {
 }
 
 // VEC: wB % 4 == 0 -> planes are staged with 16-byte copies (4x fewer copy instructions).
+// One block owns JB (<= 4) consecutive A cells of one A row: the 3 x (JB+2) neighbouring A cells'
+// hidden planes are staged once and every staged plane feeds up to 3 of the JB outputs from the
+// same registers (about 2x the FMAs per shared-memory load of a one-cell block).
 template <bool VEC>
 __global__ void __launch_bounds__(384) nc_layer2_kernel(const float* __restrict__ hidden, int hA, int wA, int hB,
-                                                       int wB, const float* __restrict__ w2p, float b2,
+                                                       int wB, int JB, const float* __restrict__ w2p, float b2,
                                                        float* __restrict__ out) {
   extern __shared__ __align__(16) float smem[];
   const int PW = kNc2Left + ((wB + 3) / 4) * 4 + 4;   // [3 unused | left halo | interior | right halo ...]
@@ -406,28 +409,30 @@ __global__ void __launch_bounds__(384) nc_layer2_kernel(const float* __restrict_
   const int plane = PH * PW;
   float* w2s = smem;                                  // [81][32]
   float* tile = smem + 81 * 32;                       // [2 buffers][4 planes][PH][PW]
-  __shared__ int s_ab[9];
-  __shared__ int s_nab;
+  __shared__ int s_nb[18];
+  __shared__ int s_nnb;
   const int nthreads = blockDim.x * blockDim.y;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  const int a = blockIdx.x, ia = a / wA, ja = a - ia * wA;
+  const int nJ = (wA + JB - 1) / JB;
+  const int ia = blockIdx.x / nJ, j0 = (blockIdx.x - ia * nJ) * JB;
   const int nB = hB * wB;
   for (int i = tid; i < 81 * 32; i += nthreads) w2s[i] = w2p[i];
   for (int i = tid; i < 8 * plane + 16; i += nthreads) tile[i] = 0.f;   // halo stays zero for the whole kernel
   if (tid == 0) {
     int n = 0;
-    for (int ab = 0; ab < 9; ++ab) {
-      const int si = ia + ab / 3 - 1, sj = ja + ab % 3 - 1;
-      if (si >= 0 && si < hA && sj >= 0 && sj < wA) s_ab[n++] = ab;
-    }
-    s_nab = n;
+    for (int di = 0; di < 3; ++di)
+      for (int dj = 0; dj < JB + 2; ++dj) {
+        const int si = ia + di - 1, sj = j0 + dj - 1;
+        if (si >= 0 && si < hA && sj >= 0 && sj < wA) s_nb[n++] = di * 6 + dj;
+      }
+    s_nnb = n;
   }
   // per-thread copy slots (units: 4 floats if VEC else 1 float).  Slots past the end of the plane
   // re-copy the last unit into a scratch area behind the tiles, so the copy loop needs no predicates.
   const int unit = VEC ? 4 : 1;
   const int nunits = nB / unit;
   const int wunits = wB / unit;
-  const int nslots = (nunits + nthreads - 1) / nthreads;   // <= kNc2MaxCopies (checked on the host)
+  const int nslots = (nunits + nthreads - 1) / nthreads;   // checked on the host
   constexpr int MAXS = VEC ? 3 : kNc2MaxCopies;
   int src_off[MAXS], dst_off[MAXS];
 #pragma unroll
@@ -440,13 +445,14 @@ __global__ void __launch_bounds__(384) nc_layer2_kernel(const float* __restrict_
   }
   float* scratch = tile + 8 * plane;   // 16 floats
   __syncthreads();
-  const int nab = s_nab;
-  const int nitems = 2 * nab * 4;
+  const int nnb = s_nnb;
+  const int per_net = nnb * 4;
+  const int nitems = 2 * per_net;
   auto issue = [&](int item) {
-    const int net = item / (nab * 4);
-    const int rem = item - net * nab * 4;
-    const int ab = s_ab[rem >> 2], cg = rem & 3;
-    const int si = ia + ab / 3 - 1, sj = ja + ab % 3 - 1;
+    const int net = item / per_net;
+    const int rem = item - net * per_net;
+    const int nb = s_nb[rem >> 2], cg = rem & 3;
+    const int si = ia + nb / 6 - 1, sj = j0 + nb % 6 - 1;
     const float* src = hidden + ((size_t)(si * wA + sj) * 32 + net * 16 + cg * 4) * nB;
     float* dst = tile + (item & 1) * 4 * plane;
 #pragma unroll
@@ -465,9 +471,11 @@ __global__ void __launch_bounds__(384) nc_layer2_kernel(const float* __restrict_
     cp_async_commit();
   };
   const int tl = threadIdx.x, tk = threadIdx.y;
-  float total[8], acc[8];
+  float total[4][8], acc[4][8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { total[i] = 0.f; acc[i] = b2; }
+  for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { total[jj][i] = 0.f; acc[jj][i] = b2; }
   issue(0);
   for (int item = 0; item < nitems; ++item) {
     if (item + 1 < nitems) {
@@ -477,9 +485,10 @@ __global__ void __launch_bounds__(384) nc_layer2_kernel(const float* __restrict_
       cp_async_wait<0>();
     }
     __syncthreads();
-    const int net = item / (nab * 4);
-    const int rem = item - net * nab * 4;
-    const int ab = s_ab[rem >> 2], c0 = net * 16 + (rem & 3) * 4;
+    const int net = item / per_net;
+    const int rem = item - net * per_net;
+    const int nb = s_nb[rem >> 2], c0 = net * 16 + (rem & 3) * 4;
+    const int di = nb / 6, dj = nb - di * 6;
     const float* buf = tile + (item & 1) * 4 * plane;
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {
@@ -490,32 +499,45 @@ __global__ void __launch_bounds__(384) nc_layer2_kernel(const float* __restrict_
         const float4 q = *reinterpret_cast<const float4*>(p + 1);
         r[rr][0] = p[0]; r[rr][1] = q.x; r[rr][2] = q.y; r[rr][3] = q.z; r[rr][4] = q.w; r[rr][5] = p[5];
       }
-      const float* wrow = w2s + ab * 9 * 32 + c0;
 #pragma unroll
-      for (int d = 0; d < 3; ++d)
+      for (int jj = 0; jj < 4; ++jj) {
+        const int b = dj - jj;                       // A-column tap of output jj for this neighbour
+        if (jj < JB && b >= 0 && b <= 2) {           // block-uniform
+          const float* wrow = w2s + (di * 3 + b) * 9 * 32 + c0 + cc;
 #pragma unroll
-        for (int e = 0; e < 3; ++e) {
-          const float4 w4 = *reinterpret_cast<const float4*>(wrow + (d * 3 + e) * 32);
-          const float wv = cc == 0 ? w4.x : (cc == 1 ? w4.y : (cc == 2 ? w4.z : w4.w));
+          for (int d = 0; d < 3; ++d)
 #pragma unroll
-          for (int kk = 0; kk < 2; ++kk)
+            for (int e = 0; e < 3; ++e) {
+              const float wv = wrow[(d * 3 + e) * 32];
 #pragma unroll
-            for (int ll = 0; ll < 4; ++ll) acc[kk * 4 + ll] = fmaf(r[kk + d][ll + e], wv, acc[kk * 4 + ll]);
+              for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+                for (int ll = 0; ll < 4; ++ll)
+                  acc[jj][kk * 4 + ll] = fmaf(r[kk + d][ll + e], wv, acc[jj][kk * 4 + ll]);
+            }
         }
+      }
     }
-    if (rem == nab * 4 - 1) {   // last item of this net: ReLU and fold into the total
+    if (rem == per_net - 1) {   // last item of this net: ReLU and fold into the total
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { total[i] += fmaxf(acc[i], 0.f); acc[i] = b2; }
+      for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { total[jj][i] += fmaxf(acc[jj][i], 0.f); acc[jj][i] = b2; }
     }
     __syncthreads();             // everyone is done with this buffer before it is refilled
   }
 #pragma unroll
-  for (int kk = 0; kk < 2; ++kk)
+  for (int jj = 0; jj < 4; ++jj) {
+    if (jj >= JB || j0 + jj >= wA) continue;
+    const size_t a = (size_t)ia * wA + j0 + jj;
 #pragma unroll
-    for (int ll = 0; ll < 4; ++ll) {
-      const int k = 2 * tk + kk, l = 4 * tl + ll;
-      if (k < hB && l < wB) out[(size_t)a * nB + k * wB + l] = total[kk * 4 + ll];
-    }
+    for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+      for (int ll = 0; ll < 4; ++ll) {
+        const int k = 2 * tk + kk, l = 4 * tl + ll;
+        if (k < hB && l < wB) out[a * nB + k * wB + l] = total[jj][kk * 4 + ll];
+      }
+  }
 }
 
 int launch_neigh_consensus(const float* x, int hA, int wA, int hB, int wB, const float* w1p, const float* b1p,
@@ -538,12 +560,27 @@ int launch_neigh_consensus(const float* x, int hA, int wA, int hB, int wB, const
     const int PW = kNc2Left + ((wB + 3) / 4) * 4 + 4, PH = hB + 3;
     const size_t smem = sizeof(float) * (81 * 32 + 8 * PH * PW + 16);
     P2P_REQUIRE(smem <= 200 * 1024, "NC layer 2: pooled B grid does not fit shared memory");
+    // A cells per block: the choice with the least wave-quantisation waste on this device
+    int JB = 2, nsm = 148;
+    {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+      double best = 1e30;
+      for (int jb = 2; jb <= 4; ++jb) {
+        const int blocks = hA * cdiv(wA, jb);
+        const double per_sm = (double)blocks / nsm;
+        const double waste = (double)cdiv(blocks, nsm) / per_sm * (1.0 + 0.35 / jb);   // small bonus for reuse
+        if (waste < best) { best = waste; JB = jb; }
+      }
+    }
+    const int grid = hA * cdiv(wA, JB);
     if (wB % 4 == 0) {
       P2P_CUDA_OK(cudaFuncSetAttribute(nc_layer2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      nc_layer2_kernel<true><<<nA, block, smem, st>>>(hidden, hA, wA, hB, wB, w2p, b2, out);
+      nc_layer2_kernel<true><<<grid, block, smem, st>>>(hidden, hA, wA, hB, wB, JB, w2p, b2, out);
     } else {
       P2P_CUDA_OK(cudaFuncSetAttribute(nc_layer2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      nc_layer2_kernel<false><<<nA, block, smem, st>>>(hidden, hA, wA, hB, wB, w2p, b2, out);
+      nc_layer2_kernel<false><<<grid, block, smem, st>>>(hidden, hA, wA, hB, wB, JB, w2p, b2, out);
     }
     P2P_LAUNCH_OK();
   }
