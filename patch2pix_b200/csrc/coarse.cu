@@ -311,7 +311,8 @@ int launch_mutual_matching(const float* x, int nA, int nB, float* rowmax, unsign
 // hidden layout: [A cell][32][hB][wB] fp32 (HBM round trip: 2*32*V*4 B, << the FMA time).
 // ------------------------------------------------------------------------------------------------
 // layer 1: grid (ceil(hB/8), nA), block (ceil(wB/2), 8); thread = 2 adjacent B cells x 32 channels.
-__global__ void __launch_bounds__(512) nc_layer1_kernel(const float* __restrict__ x, int hA, int wA, int hB, int wB,
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) nc_layer1_kernel(const float* __restrict__ x, int hA, int wA, int hB, int wB,
                                                        const float* __restrict__ w1p, const float* __restrict__ b1p,
                                                        float* __restrict__ hidden) {
   extern __shared__ __align__(16) float smem[];
@@ -548,8 +549,17 @@ int launch_neigh_consensus(const float* x, int hA, int wA, int hB, int wB, const
     P2P_REQUIRE(block.x * block.y <= 512, "NC layer 1: pooled width too large (wB <= 128)");
     dim3 grid(cdiv(hB, 8), nA);
     const size_t smem = sizeof(float) * (81 * 32 + 9 * 10 * (wB + 4));
-    P2P_CUDA_OK(cudaFuncSetAttribute(nc_layer1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nc_layer1_kernel<<<grid, block, smem, st>>>(x, hA, wA, hB, wB, w1p, b1p, hidden);
+    if (block.x * block.y <= 160) {   // small B grids: cap registers so that 4 blocks share an SM
+      auto k = nc_layer1_kernel<160, 4>;
+      P2P_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      P2P_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      k<<<grid, block, smem, st>>>(x, hA, wA, hB, wB, w1p, b1p, hidden);
+    } else {
+      auto k = nc_layer1_kernel<512, 1>;
+      P2P_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      P2P_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      k<<<grid, block, smem, st>>>(x, hA, wA, hB, wB, w1p, b1p, hidden);
+    }
     P2P_LAUNCH_OK();
   }
   {
@@ -577,9 +587,11 @@ int launch_neigh_consensus(const float* x, int hA, int wA, int hB, int wB, const
     const int grid = hA * cdiv(wA, JB);
     if (wB % 4 == 0) {
       P2P_CUDA_OK(cudaFuncSetAttribute(nc_layer2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      P2P_CUDA_OK(cudaFuncSetAttribute(nc_layer2_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       nc_layer2_kernel<true><<<grid, block, smem, st>>>(hidden, hA, wA, hB, wB, JB, w2p, b2, out);
     } else {
       P2P_CUDA_OK(cudaFuncSetAttribute(nc_layer2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      P2P_CUDA_OK(cudaFuncSetAttribute(nc_layer2_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       nc_layer2_kernel<false><<<grid, block, smem, st>>>(hidden, hA, wA, hB, wB, JB, w2p, b2, out);
     }
     P2P_LAUNCH_OK();

@@ -1,0 +1,40 @@
+"""How far can a 1-pass (fp16 operand) mid coordinate be from the fp32-grade 3-pass one?
+Evidence for the default risk band (mid_band = 40 thousandths of a pixel)."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bench import model_config  # noqa: E402
+from patch2pix_b200.model import Patch2PixB200  # noqa: E402
+from patch2pix_b200.synth import make_seeded_state_dict, synthetic_pair  # noqa: E402
+
+torch.backends.cudnn.allow_tf32 = False
+cfg = model_config(torch.device('cuda:0'), 8)
+cfg.weights_dict = make_seeded_state_dict(0)
+net = Patch2PixB200(cfg)
+diffs = []
+with torch.no_grad():
+    for p in range(6):
+        im1, im2 = synthetic_pair(p, 480, 640)
+        f1, f2 = net.extract_pair(im1.cuda(), im2.cuda())
+        np.random.seed(p)
+        t = net.submit_coarse(f1, f2, 2, True)
+        net.set_option('mid_band', 0)
+        net.set_option('mid_passes', 3)
+        fine, fp, mid3, mp, cm = net.finish_match(t, 0.0, 400, return_all=True)
+        net.set_option('mid_passes', 1)
+        mid1, _ = net.forward_fine_match(f1, f2, cm, 16, 'center', net.regress_mid)
+        diffs.append((mid1[0] - mid3[0]).abs().flatten().cpu())
+        net.set_option('mid_passes', 3)
+d = torch.cat(diffs).double()
+q = torch.quantile(d, torch.tensor([0.5, 0.99, 0.9999], dtype=torch.float64)).tolist()
+rep = {'coords': int(d.numel()), 'max': d.max().item(), 'median': q[0], 'p99': q[1], 'p99.99': q[2],
+       'frac_above_0.02': (d > 0.02).double().mean().item(), 'frac_above_0.04': (d > 0.04).double().mean().item()}
+print(json.dumps(rep, indent=1))
+os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+json.dump(rep, open(os.path.join(ROOT, 'gpurun_out', 'band_stats.json'), 'w'), indent=1)
