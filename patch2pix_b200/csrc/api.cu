@@ -59,7 +59,7 @@ struct p2p_handle_s {
   int device = 0;
   int num_sms = 148;
   int opt_mid_passes = 3, opt_fine_passes = 1, opt_corr_passes = 3, opt_seg_len = 3, opt_gemm_impl = 0, opt_num_sms = 0;
-  int opt_mid_band = 40;  // thousandths of a pixel; 0 = pure 3-pass mid stage
+  int opt_mid_band = 30;  // thousandths of a pixel; 0 = pure 3-pass mid stage
   const int* last_band_count = nullptr;  // device counter of the last risk-band subset
   bool nc_set = false;
   float *nc_w1p = nullptr, *nc_b1p = nullptr, *nc_w2p = nullptr;
