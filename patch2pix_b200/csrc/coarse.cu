@@ -396,6 +396,14 @@ __device__ __forceinline__ void cp_async16(float* dst_smem, const float* src) {
                : "memory");
 }
 
+// Row pitch of the staged planes: a multiple of 4 floats with 2*pitch = 8 (mod 32), so that the
+// float4 reads of consecutive thread rows (2 plane rows apart) fall into disjoint banks.
+__host__ __device__ inline int nc2_pitch(int wB) {
+  int pw = kNc2Left + ((wB + 3) / 4) * 4 + 4;
+  while ((2 * pw) % 32 != 8) pw += 4;
+  return pw;
+}
+
 // VEC: wB % 4 == 0 -> planes are staged with 16-byte copies (4x fewer copy instructions).
 // One block owns JB (<= 4) consecutive A cells of one A row: the 3 x (JB+2) neighbouring A cells'
 // hidden planes are staged once and every staged plane feeds up to 3 of the JB outputs from the
@@ -405,7 +413,7 @@ __global__ void __launch_bounds__(384) nc_layer2_kernel(const float* __restrict_
                                                        int wB, int JB, const float* __restrict__ w2p, float b2,
                                                        float* __restrict__ out) {
   extern __shared__ __align__(16) float smem[];
-  const int PW = kNc2Left + ((wB + 3) / 4) * 4 + 4;   // [3 unused | left halo | interior | right halo ...]
+  const int PW = nc2_pitch(wB);                       // [3 unused | left halo | interior | right halo ...]
   const int PH = hB + 2 + 1;                          // covers 2*tk+3
   const int plane = PH * PW;
   float* w2s = smem;                                  // [81][32]
@@ -567,7 +575,7 @@ int launch_neigh_consensus(const float* x, int hA, int wA, int hB, int wB, const
     P2P_REQUIRE(block.x * block.y <= 384, "NC layer 2: pooled B grid too large (hB*wB <= 3072)");
     P2P_REQUIRE(cdiv(hB * wB, (int)(block.x * block.y)) <= kNc2MaxCopies, "NC layer 2: copy slots exhausted");
     P2P_REQUIRE(wB % 4 != 0 || cdiv(hB * wB / 4, (int)(block.x * block.y)) <= 3, "NC layer 2: vector copy slots exhausted");
-    const int PW = kNc2Left + ((wB + 3) / 4) * 4 + 4, PH = hB + 3;
+    const int PW = nc2_pitch(wB), PH = hB + 3;
     const size_t smem = sizeof(float) * (81 * 32 + 8 * PH * PW + 16);
     P2P_REQUIRE(smem <= 200 * 1024, "NC layer 2: pooled B grid does not fit shared memory");
     // A cells per block: the choice with the least wave-quantisation waste on this device
@@ -628,36 +636,37 @@ __device__ __forceinline__ void emit_match(long long* m, float* sc, int row, int
   sc[row] = score;
 }
 
-// best A for every B cell: block (32 columns) x (8 row phases)
-__global__ void __launch_bounds__(256) proposals_dir1_kernel(const float* __restrict__ x, int nA, int nB, int wA, int wB,
-                                                            const uint8_t* __restrict__ code, int ks, int upsample,
-                                                            int shift, int do_softmax, long long* __restrict__ m,
-                                                            float* __restrict__ sc) {
-  __shared__ float sv[8][33];
-  __shared__ int si[8][33];
+// best A for every B cell: block = 32 columns x 32 row phases (each thread scans nA/32 rows)
+__global__ void __launch_bounds__(1024) proposals_dir1_kernel(const float* __restrict__ x, int nA, int nB, int wA, int wB,
+                                                             const uint8_t* __restrict__ code, int ks, int upsample,
+                                                             int shift, int do_softmax, long long* __restrict__ m,
+                                                             float* __restrict__ sc) {
+  constexpr int R = 32;
+  __shared__ float sv[R][33];
+  __shared__ int si[R][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int b = blockIdx.x * 32 + tx;
   float best = -INFINITY;
   int bi = 0x7fffffff;
   if (b < nB)
-    for (int a = ty; a < nA; a += 8) better(best, bi, x[(size_t)a * nB + b], a);
+    for (int a = ty; a < nA; a += R) better(best, bi, x[(size_t)a * nB + b], a);
   sv[ty][tx] = best;
   si[ty][tx] = bi;
   __syncthreads();
   best = sv[0][tx];
   bi = si[0][tx];
 #pragma unroll
-  for (int r = 1; r < 8; ++r) better(best, bi, sv[r][tx], si[r][tx]);
+  for (int r = 1; r < R; ++r) better(best, bi, sv[r][tx], si[r][tx]);
   __syncthreads();
   float s = 0.f;
   if (b < nB && do_softmax)
-    for (int a = ty; a < nA; a += 8) s += expf(x[(size_t)a * nB + b] - best);
+    for (int a = ty; a < nA; a += R) s += expf(x[(size_t)a * nB + b] - best);
   sv[ty][tx] = s;
   __syncthreads();
   if (ty == 0 && b < nB) {
     float tot = 0.f;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) tot += sv[r][tx];
+    for (int r = 0; r < R; ++r) tot += sv[r][tx];
     const float score = do_softmax ? __fdiv_rn(1.f, tot) : best;
     emit_match(m, sc, b, bi, b, score, wA, wB, nB, code, ks, upsample, shift);
   }
@@ -695,7 +704,7 @@ int launch_proposals(const float* corr, const uint8_t* code, int hA, int wA, int
                      int center, int do_softmax, long long* matches, float* scores, cudaStream_t st) {
   const int nA = hA * wA, nB = hB * wB;
   const int shift = center ? upsample / 2 : 0;
-  proposals_dir1_kernel<<<cdiv(nB, 32), 256, 0, st>>>(corr, nA, nB, wA, wB, code, ksize, upsample, shift, do_softmax,
+  proposals_dir1_kernel<<<cdiv(nB, 32), 1024, 0, st>>>(corr, nA, nB, wA, wB, code, ksize, upsample, shift, do_softmax,
                                                       matches, scores);
   P2P_LAUNCH_OK();
   proposals_dir2_kernel<<<cdiv(nA, 8), 256, 0, st>>>(corr, nA, nB, wA, wB, code, ksize, upsample, shift, do_softmax,
