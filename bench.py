@@ -305,6 +305,7 @@ def run_ours(args):
     with torch.no_grad():
         # ---- hot path, features resident in HBM -------------------------------------------------
         hot_loop(0, Wm, False)
+        sharder.gather_results(results)                  # warm-up of the collective (NCCL sets up channels lazily)
         net.set_option('profile', 1)
         net._handle.profile_read()
         l0 = net._handle.launch_count()
