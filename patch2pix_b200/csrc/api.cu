@@ -60,6 +60,7 @@ struct p2p_handle_s {
   int num_sms = 148;
   int opt_mid_passes = 3, opt_fine_passes = 1, opt_corr_passes = 3, opt_seg_len = 3, opt_gemm_impl = 0, opt_num_sms = 0;
   int opt_mid_band = 30;  // thousandths of a pixel; 0 = pure 3-pass mid stage
+  int opt_fuse_gather = 1;  // 1-pass conv1 builds its A tiles in producer warps (no patch tensor in HBM)
   const int* last_band_count = nullptr;  // device counter of the last risk-band subset
   bool nc_set = false;
   float *nc_w1p = nullptr, *nc_b1p = nullptr, *nc_w2p = nullptr;
@@ -393,6 +394,7 @@ static int* option_slot(p2p_handle_t h, const char* key) {
   if (!strcmp(key, "num_sms")) return &h->opt_num_sms;
   if (!strcmp(key, "profile")) return &h->opt_profile;
   if (!strcmp(key, "mid_band")) return &h->opt_mid_band;
+  if (!strcmp(key, "fuse_gather")) return &h->opt_fuse_gather;
   return nullptr;
 }
 
@@ -641,7 +643,7 @@ int p2p_refine_prepare(p2p_handle_t h, const float* const* feats1, const float* 
   size_t need = 1 << 16;
   for (int s = 0; s < 2; ++s) {
     const size_t px = (size_t)Hs[s] * Ws[s];
-    need += (px / 4 * 64 + px / 16 * 64 + px / 64 * 128) * 4 + (px + px / 4 + px / 16 + px / 64) * 4 + 16384;
+    need += (px / 4 * 64 + px / 16 * 64 + px / 64 * 128) * 6 + (px + px / 4 + px / 16 + px / 64) * 4 + 32768;
   }
   int rc = h->feat.reserve(need);
   if (rc) return rc;
@@ -656,7 +658,8 @@ int p2p_refine_prepare(p2p_handle_t h, const float* const* feats1, const float* 
     for (int l = 0; l < 3; ++l) {
       const int ds = 2 << l;
       pf.nhwc[l] = (float*)h->feat.take((size_t)(Hs[s] / ds) * (Ws[s] / ds) * chans[l] * 4);
-      P2P_REQUIRE(pf.nhwc[l] != nullptr, "scratch carve failed");
+      pf.nhwc16[l] = (__half*)h->feat.take((size_t)(Hs[s] / ds) * (Ws[s] / ds) * chans[l] * 2);
+      P2P_REQUIRE(pf.nhwc[l] != nullptr && pf.nhwc16[l] != nullptr, "scratch carve failed");
     }
     ProfScope ps(h, P2P_PROF_PREP, st);
     if ((rc = launch_feature_prep(s == 0 ? feats1 : feats2, Hs[s], Ws[s], pf, st))) return rc;
@@ -681,7 +684,8 @@ int run_regressor(p2p_handle_s* h, Regressor& R, int which, int passes, const Re
   const bool lo = passes == 3;
   const int kb = rowmap != nullptr ? P2P_PROF_GATHER_BAND : (which == 0 ? P2P_PROF_GATHER_MID : P2P_PROF_GATHER_FINE);
   int rc;
-  {
+  const bool fused = passes == 1 && rowmap == nullptr && h->opt_fuse_gather && h->opt_gemm_impl == 0;
+  if (!fused) {
     ProfScope ps(h, kb, st);
     if ((rc = launch_patch_gather(h->pf[0], h->pf[1], matches_in, is_float, n, B.p_hi, lo ? B.p_lo : nullptr, B.r_hi,
                                   lo ? B.r_lo : nullptr, rowmap, d_count, st)))
@@ -732,8 +736,19 @@ int run_regressor(p2p_handle_s* h, Regressor& R, int which, int passes, const Re
       p.epi.y_hi = B.y_hi;
       p.epi.y_lo = lo ? B.y_lo : nullptr;
       p.epi.n_patches = n;
+      if (fused) {
+        for (int s2 = 0; s2 < 2; ++s2) {
+          p.fg.img[s2] = h->pf[s2].img;
+          for (int l = 0; l < 3; ++l) p.fg.nhwc16[s2][l] = h->pf[s2].nhwc16[l];
+          for (int l = 0; l < 4; ++l) p.fg.nsq[s2][l] = h->pf[s2].nsq[l];
+          p.fg.H[s2] = h->pf[s2].H;
+          p.fg.W[s2] = h->pf[s2].W;
+        }
+        p.fg.matches = matches_in;
+        p.fg.is_float = is_float;
+      }
       ProfScope ps(h, kb + 1, st);
-      if ((rc = launch_umma_gemm(p, EPI_CONV1, passes, sms(h), st))) return rc;
+      if ((rc = launch_umma_gemm(p, EPI_CONV1, passes, sms(h), st, fused))) return rc;
     }
     {  // conv2
       const uint64_t ad[5] = {512, 8, 8, 1, npad};

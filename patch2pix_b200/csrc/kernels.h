@@ -36,6 +36,7 @@ constexpr int kConv2Steps = 72;   // 9 taps x 8 chunks          (K = 4608)
 struct PairFeatures {             // per image: channels-last copies + squared-norm maps
   const float* img;               // [3][H][W]   (level 0 stays NCHW)
   float* nhwc[3];                 // levels 1..3: [h][w][C], C = 64, 64, 128
+  __half* nhwc16[3];              // same, fp16, each pixel divided by its own level norm sqrt(nsq[l+1])
   float* nsq[4];                  // levels 0..3: [h][w]
   int H, W;
 };

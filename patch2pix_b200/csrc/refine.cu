@@ -18,9 +18,11 @@ namespace p2p {
 // feature prep
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) nchw_to_nhwc_nsq_kernel(const float* __restrict__ in, int C, int npx,
-                                                              float* __restrict__ out, float* __restrict__ nsq) {
+                                                              float* __restrict__ out, float* __restrict__ nsq,
+                                                              __half* __restrict__ out16) {
   extern __shared__ float tile[];  // [C][33]
   __shared__ float part[8][32];
+  __shared__ float rinv[32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int px0 = blockIdx.x * 32;
   const int px = px0 + lane;
@@ -37,10 +39,16 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_nsq_kernel(const float* __re
 #pragma unroll
     for (int w = 0; w < 8; ++w) t += part[w][lane];
     nsq[px] = t;
+    rinv[lane] = rsqrtf(t + 1e-30f);
   }
+  __syncthreads();
   for (int i = threadIdx.x; i < 32 * C; i += 256) {
     const int p = i / C, c = i - p * C;
-    if (px0 + p < npx) out[(size_t)(px0 + p) * C + c] = tile[c * 33 + p];
+    if (px0 + p < npx) {
+      const float v = tile[c * 33 + p];
+      out[(size_t)(px0 + p) * C + c] = v;
+      out16[(size_t)(px0 + p) * C + c] = __float2half_rn(v * rinv[p]);   // |.| <= 1: no fp16 range issues
+    }
   }
 }
 
@@ -68,7 +76,7 @@ int launch_feature_prep(const float* const feats[4], int H, int W, PairFeatures&
     const int npx = (H / ds) * (W / ds);
     const int C = chans[l];
     nchw_to_nhwc_nsq_kernel<<<cdiv(npx, 32), 256, sizeof(float) * C * 33, st>>>(feats[l + 1], C, npx, out.nhwc[l],
-                                                                               out.nsq[l + 1]);
+                                                                               out.nsq[l + 1], out.nhwc16[l]);
     P2P_LAUNCH_OK();
   }
   return 0;

@@ -226,8 +226,18 @@ __device__ __forceinline__ void epilogue_piece(const UmmaEpilogue& e, int n_patc
 constexpr int kATile = 128 * 128;   // 128 rows x 64 fp16
 constexpr int kBTile = 256 * 128;   // 256 rows x 64 fp16
 
-template <int PASSES, bool SEGMENTED, int EPI>
-__global__ void __launch_bounds__(384, 1) umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p) {
+__device__ __forceinline__ int fg_clamp(int v, int ds, int full) {   // ((x+dx)//ds).clamp(0, full//ds-1)
+  if (v < 0) return 0;
+  const int q = v / ds, m = full / ds - 1;
+  return q < m ? q : m;
+}
+
+// FUSED (conv1, 1-pass): warps 12..15 are A-operand producers that gather, normalise and convert the
+// patch windows straight into the swizzled shared-memory tile (select_local_patch_feats + patch
+// L2Normalize, networks/utils.py:4-36, networks/patch2pix.py:173-178); TMA then only streams the weights.
+template <int PASSES, bool SEGMENTED, int EPI, bool FUSED>
+__global__ void __launch_bounds__(FUSED ? 512 : 384, 1) umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p) {
+  static_assert(!FUSED || (PASSES == 1 && !SEGMENTED && EPI == EPI_CONV1), "fused gather: conv1, 1-pass only");
   constexpr int STAGES = (PASSES == 3) ? 2 : 4;
   constexpr int NOP = (PASSES == 3) ? 2 : 1;
   constexpr int STAGE_BYTES = NOP * (kATile + kBTile);
@@ -240,6 +250,9 @@ __global__ void __launch_bounds__(384, 1) umma_gemm_kernel(const __grid_constant
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_smem;
+  constexpr int FG = FUSED ? 16 : 1;
+  __shared__ float fg_dinv[2][2][FG][FG];               // act_scale / patch norm per (patch, image, window pixel)
+  __shared__ int fg_org[2][4];                          // window origins (x1,y1,x2,y2) - 8
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int m_tiles = p.m_tiles;
@@ -263,7 +276,7 @@ __global__ void __launch_bounds__(384, 1) umma_gemm_kernel(const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], FUSED ? 129 : 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -292,6 +305,11 @@ __global__ void __launch_bounds__(384, 1) umma_gemm_kernel(const __grid_constant
           mbar_wait(&empty_bar[s], ph ^ 1u);
           const KStep k = p.steps[ks];  // param space (constant bank)
           uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+          if (FUSED) {
+            mbar_expect_tx(&full_bar[s], kBTile);
+            tma_load_2d(&p.b_hi, &full_bar[s], st + kATile, k.bk, n_tile * 256);
+            continue;
+          }
           mbar_expect_tx(&full_bar[s], STAGE_BYTES);
           const int a4 = m_tile * p.a_units_per_tile;
           if (k.kind == 0) {
@@ -355,7 +373,114 @@ __global__ void __launch_bounds__(384, 1) umma_gemm_kernel(const __grid_constant
       }
     }
   }
-  } else {
+  } else if (FUSED && warp >= 12) {
+    // ===================== fused A-operand producers (128 threads) =====================
+    const int ptid = threadIdx.x - 384;
+    const int l8 = ptid & 7, r16 = ptid >> 3;         // 8 lanes per row (8 channels each), 16 rows per pass
+    const FusedGather& g = p.fg;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles;
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // nobody still reads the previous tile's tables
+      if (ptid < 8) {
+        const int pp = ptid >> 2, j = ptid & 3;
+        const int n = m_tile * 2 + pp;
+        int v = 0;
+        if (n < n_units) {
+          if (g.is_float)
+            v = (int)reinterpret_cast<const float*>(g.matches)[(size_t)n * 4 + j];   // .long(): truncation
+          else
+            v = (int)reinterpret_cast<const long long*>(g.matches)[(size_t)n * 4 + j];
+        }
+        fg_org[pp][j] = v - 8;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = ptid; i < 1024; i += 128) {
+        const int pp = i >> 9, si = (i >> 8) & 1, wy = (i >> 4) & 15, wx = i & 15;
+        const int X = fg_org[pp][2 * si] + wx, Y = fg_org[pp][2 * si + 1] + wy;
+        float t = 0.f;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          const int ds = 1 << l;
+          const int xi = fg_clamp(X, ds, g.W[si]), yi = fg_clamp(Y, ds, g.H[si]);
+          t += __ldg(g.nsq[si][l] + (size_t)yi * (g.W[si] / ds) + xi);
+        }
+        fg_dinv[pp][si][wy][wx] = (m_tile * 2 + pp < n_units) ? __fdiv_rn(kActScale, sqrtf(t + 1e-6f)) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int ks = 0; ks < nsteps; ++ks, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        const KStep k = p.steps[ks];
+        uint8_t* at = smem + (size_t)s * STAGE_BYTES;
+        uint4 vals[8];
+        if (k.kind == 0) {
+          const int ty = (k.plane & 2) ? 1 : (k.y < 0 ? 0 : 2), tx = (k.plane & 1) ? 1 : (k.x < 0 ? 0 : 2);
+          const int chunk = k.c0 >> 6, si = chunk >> 2, jj = chunk & 3;
+          const int lvl = jj == 0 ? 0 : (jj == 1 ? 1 : 2);
+          const int ds = 2 << lvl, C = lvl == 2 ? 128 : 64;
+          const int coff = (jj == 3 ? 64 : 0) + l8 * 8;
+          const __half* fmap = g.nhwc16[si][lvl];
+          const float* nsq = g.nsq[si][lvl + 1];
+          const int wl = g.W[si] / ds;
+          float sc[8];
+#pragma unroll
+          for (int ps = 0; ps < 8; ++ps) {               // all 8 loads in flight before the first use
+            const int row = ps * 16 + r16;
+            const int pp = row >> 6, wy = 2 * ((row >> 3) & 7) - 1 + ty, wx = 2 * (row & 7) - 1 + tx;
+            vals[ps] = make_uint4(0, 0, 0, 0);
+            sc[ps] = 0.f;
+            if (wy >= 0 && wx >= 0) {
+              const int xi = fg_clamp(fg_org[pp][2 * si] + wx, ds, g.W[si]);
+              const int yi = fg_clamp(fg_org[pp][2 * si + 1] + wy, ds, g.H[si]);
+              const size_t px = (size_t)yi * wl + xi;
+              vals[ps] = __ldg(reinterpret_cast<const uint4*>(fmap + px * C + coff));
+              sc[ps] = fg_dinv[pp][si][wy][wx] * sqrtf(__ldg(nsq + px) + 1e-30f);   // undo the per-level scale
+            }
+          }
+#pragma unroll
+          for (int ps = 0; ps < 8; ++ps) {
+            const int row = ps * 16 + r16;
+            __half2* h2 = reinterpret_cast<__half2*>(&vals[ps]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 f = __half22float2(h2[q]);
+              h2[q] = __floats2half2_rn(f.x * sc[ps], f.y * sc[ps]);
+            }
+            *reinterpret_cast<uint4*>(at + row * 128 + ((l8 ^ (row & 7)) << 4)) = vals[ps];
+          }
+        } else {
+          // rgb im2col chunk: k = tap*6 + img*3 + ch (54 used)
+#pragma unroll 1
+          for (int ps = 0; ps < 8; ++ps) {
+            const int row = ps * 16 + r16;
+            const int pp = row >> 6, oy = (row >> 3) & 7, ox = row & 7;
+            __align__(16) __half hv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int kk = l8 * 8 + i;
+              float v = 0.f;
+              if (kk < 54) {
+                const int tap = kk / 6, r = kk - tap * 6;
+                const int si = r / 3, ch = r - si * 3;
+                const int wx = 2 * ox - 1 + tap % 3, wy = 2 * oy - 1 + tap / 3;
+                if (wx >= 0 && wy >= 0) {
+                  const int xi = fg_clamp(fg_org[pp][2 * si] + wx, 1, g.W[si]);
+                  const int yi = fg_clamp(fg_org[pp][2 * si + 1] + wy, 1, g.H[si]);
+                  v = __ldg(g.img[si] + ((size_t)ch * g.H[si] + yi) * g.W[si] + xi) * fg_dinv[pp][si][wy][wx];
+                }
+              }
+              hv[i] = __float2half_rn(v);
+            }
+            *reinterpret_cast<uint4*>(at + row * 128 + ((l8 ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4*>(hv);
+          }
+        }
+        fence_proxy_async();            // generic-proxy stores -> visible to the tensor core (async proxy)
+        mbar_arrive(&full_bar[s]);
+      }
+    }
+  } else if (warp >= 4 && warp < 12) {
     // ===================== epilogue =====================
     if (SEGMENTED) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int q = warp & 3, hf = (warp - 4) >> 2;
@@ -459,14 +584,14 @@ int make_tmap_fp16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   return 0;
 }
 
-template <int PASSES, bool SEGMENTED, int EPI>
+template <int PASSES, bool SEGMENTED, int EPI, bool FUSED = false>
 static int launch_one(const UmmaGemmParams& p, int grid, cudaStream_t st) {
   constexpr int STAGES = (PASSES == 3) ? 2 : 4;
   constexpr int NOP = (PASSES == 3) ? 2 : 1;
   const int smem = STAGES * NOP * (kATile + kBTile) + 1024;
-  auto kern = umma_gemm_kernel<PASSES, SEGMENTED, EPI>;
+  auto kern = umma_gemm_kernel<PASSES, SEGMENTED, EPI, FUSED>;
   P2P_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<grid, 384, smem, st>>>(p);
+  kern<<<grid, FUSED ? 512 : 384, smem, st>>>(p);
   P2P_LAUNCH_OK();
   return 0;
 }
@@ -477,12 +602,16 @@ static int launch_epi(const UmmaGemmParams& p, int passes, bool seg, int grid, c
   return seg ? launch_one<1, true, EPI>(p, grid, st) : launch_one<1, false, EPI>(p, grid, st);
 }
 
-int launch_umma_gemm(const UmmaGemmParams& p, int epi, int passes, int num_sms, cudaStream_t st) {
+int launch_umma_gemm(const UmmaGemmParams& p, int epi, int passes, int num_sms, cudaStream_t st, bool fused) {
   P2P_REQUIRE(passes == 1 || passes == 3, "umma gemm: passes must be 1 or 3");
   P2P_REQUIRE(p.nsteps > 0 && p.m_tiles > 0 && p.n_tiles > 0, "umma gemm: empty problem");
   const bool seg = p.seg_len > 0 && p.seg_len < p.nsteps;
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms ? total : num_sms;
+  if (fused) {
+    P2P_REQUIRE(epi == EPI_CONV1 && passes == 1 && !seg, "fused gather is available for 1-pass conv1 only");
+    return launch_one<1, false, EPI_CONV1, true>(p, grid, st);
+  }
   switch (epi) {
     case EPI_PLAIN: return launch_epi<EPI_PLAIN>(p, passes, seg, grid, st);
     case EPI_CONV1: return launch_epi<EPI_CONV1>(p, passes, seg, grid, st);

@@ -27,6 +27,17 @@ struct UmmaEpilogue {
   int n_patches;
 };
 
+// conv1 with the patch gather fused into producer warps (1-pass launches): the A tile of every k-step
+// is built in shared memory straight from the channels-last fp16 pyramid copies.
+struct FusedGather {
+  const float* img[2];            // [3][H][W]
+  const __half* nhwc16[2][3];     // level-normalised fp16 pyramid copies
+  const float* nsq[2][4];         // per-level squared norms
+  int H[2], W[2];
+  const void* matches;            // [n][4] int64 or fp32
+  int is_float;
+};
+
 struct UmmaGemmParams {
   CUtensorMap a_main_hi, a_main_lo, a_rgb_hi, a_rgb_lo, b_hi, b_lo;
   KStep steps[kMaxKSteps];
@@ -37,10 +48,11 @@ struct UmmaGemmParams {
   int seg_len;           // k-steps accumulated in TMEM before a drain (0 / >= nsteps: whole K)
   const int* d_units;    // optional device count of A units (patches): m_tiles = ceil(*d_units / a_units_per_tile)
   UmmaEpilogue epi;
+  FusedGather fg;
 };
 
 int make_tmap_fp16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box);
-int launch_umma_gemm(const UmmaGemmParams& p, int epi, int passes, int num_sms, cudaStream_t st);
+int launch_umma_gemm(const UmmaGemmParams& p, int epi, int passes, int num_sms, cudaStream_t st, bool fused = false);
 
 }  // namespace p2p

@@ -462,3 +462,31 @@ def test_config3_1024x768_ptmax1000_memory_path(nets, seeded_sd):
                'max_conf_err': (finep[0].cpu()[idx] - o_fp[0]).abs()[~strad].max().item()}
         _report('config3_1024x768', rep)
         assert rep['max_err_px_nonstraddle'] < 0.5 and rep['max_conf_err'] < 1e-3 and rep['straddle_rows'] <= 1, rep
+
+
+def test_fused_gather_matches_materialised_gather(nets, seeded_sd):
+    """1-pass conv1 with the gather fused into producer warps vs the TMA path over the materialised
+    patch tensor: same math up to one extra fp16 rounding of the (level-normalised) features."""
+    net = nets[1]
+    H, W = 128, 160
+    m = _random_matches(333, H, W, 11, False)
+    f1, f2, _, _ = _feats(net, 9, H, W)
+    out = {}
+    try:
+        for fuse in (1, 0):
+            net.set_option('fuse_gather', fuse)
+            net.set_option('mid_band', 0)
+            net.set_option('mid_passes', 1)
+            with torch.no_grad():
+                mid, midp = net.forward_fine_match(f1, f2, [m.cuda()], 16, 'center', net.regress_mid)
+                fine, finep = net.forward_fine_match(f1, f2, mid, 16, 'center', net.regress_fine)
+            torch.cuda.synchronize()
+            out[fuse] = (mid[0].cpu(), midp[0].cpu(), fine[0].cpu(), finep[0].cpu())
+    finally:
+        net.set_option('fuse_gather', 1)
+        net.set_option('mid_band', 30)
+        net.set_option('mid_passes', 3)
+    d_mid = (out[1][0] - out[0][0]).abs().max().item()
+    d_p = (out[1][1] - out[0][1]).abs().max().item()
+    _report('fused_vs_materialised', {'mid_diff_px': d_mid, 'conf_diff': d_p})
+    assert d_mid < 0.03 and d_p < 5e-4, (d_mid, d_p)
