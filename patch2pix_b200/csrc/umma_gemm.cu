@@ -276,12 +276,12 @@ __global__ void __launch_bounds__(FUSED ? 512 : 384, 1) umma_gemm_kernel(const _
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], FUSED ? 129 : 1);
+      mbar_init(&full_bar[i], FUSED ? 257 : 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);
+      mbar_init(&tempty_bar[i], FUSED ? 4 : 8);
     }
     fence_barrier_init();
   }
@@ -373,15 +373,17 @@ __global__ void __launch_bounds__(FUSED ? 512 : 384, 1) umma_gemm_kernel(const _
       }
     }
   }
-  } else if (FUSED && warp >= 12) {
-    // ===================== fused A-operand producers (128 threads) =====================
-    const int ptid = threadIdx.x - 384;
-    const int l8 = ptid & 7, r16 = ptid >> 3;         // 8 lanes per row (8 channels each), 16 rows per pass
+  } else if (FUSED && warp >= 8) {
+    // ===================== fused A-operand producers (8 warps, 256 threads) =====================
+    // 8 lanes per tile row (8 channels = 16 B each), 32 rows per pass, 4 passes per k-step.  Warps
+    // drift across pipeline stages independently, which hides the L2 latency of the gathers.
+    const int ptid = threadIdx.x - 256;
+    const int l8 = ptid & 7, r32 = ptid >> 3;
     const FusedGather& g = p.fg;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_tiles;
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // nobody still reads the previous tile's tables
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // nobody still reads the previous tile's tables
       if (ptid < 8) {
         const int pp = ptid >> 2, j = ptid & 3;
         const int n = m_tile * 2 + pp;
@@ -394,8 +396,8 @@ __global__ void __launch_bounds__(FUSED ? 512 : 384, 1) umma_gemm_kernel(const _
         }
         fg_org[pp][j] = v - 8;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = ptid; i < 1024; i += 128) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = ptid; i < 1024; i += 256) {
         const int pp = i >> 9, si = (i >> 8) & 1, wy = (i >> 4) & 15, wx = i & 15;
         const int X = fg_org[pp][2 * si] + wx, Y = fg_org[pp][2 * si + 1] + wy;
         float t = 0.f;
@@ -407,54 +409,55 @@ __global__ void __launch_bounds__(FUSED ? 512 : 384, 1) umma_gemm_kernel(const _
         }
         fg_dinv[pp][si][wy][wx] = (m_tile * 2 + pp < n_units) ? __fdiv_rn(kActScale, sqrtf(t + 1e-6f)) : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       for (int ks = 0; ks < nsteps; ++ks, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
         const KStep k = p.steps[ks];
         uint8_t* at = smem + (size_t)s * STAGE_BYTES;
-        uint4 vals[8];
         if (k.kind == 0) {
           const int ty = (k.plane & 2) ? 1 : (k.y < 0 ? 0 : 2), tx = (k.plane & 1) ? 1 : (k.x < 0 ? 0 : 2);
           const int chunk = k.c0 >> 6, si = chunk >> 2, jj = chunk & 3;
           const int lvl = jj == 0 ? 0 : (jj == 1 ? 1 : 2);
-          const int ds = 2 << lvl, C = lvl == 2 ? 128 : 64;
+          const int sh = lvl + 1, C = lvl == 2 ? 128 : 64;
           const int coff = (jj == 3 ? 64 : 0) + l8 * 8;
           const __half* fmap = g.nhwc16[si][lvl];
           const float* nsq = g.nsq[si][lvl + 1];
-          const int wl = g.W[si] / ds;
-          float sc[8];
+          const int wl = g.W[si] >> sh, hl = g.H[si] >> sh;
+          const int ox0 = fg_org[0][2 * si], oy0 = fg_org[0][2 * si + 1];
+          const int ox1 = fg_org[1][2 * si], oy1 = fg_org[1][2 * si + 1];
+          uint4 vals[4];
+          float nq[4], dv[4];
 #pragma unroll
-          for (int ps = 0; ps < 8; ++ps) {               // all 8 loads in flight before the first use
-            const int row = ps * 16 + r16;
+          for (int ps = 0; ps < 4; ++ps) {               // phase 1: every load in flight before any use
+            const int row = ps * 32 + r32;
             const int pp = row >> 6, wy = 2 * ((row >> 3) & 7) - 1 + ty, wx = 2 * (row & 7) - 1 + tx;
-            vals[ps] = make_uint4(0, 0, 0, 0);
-            sc[ps] = 0.f;
-            if (wy >= 0 && wx >= 0) {
-              const int xi = fg_clamp(fg_org[pp][2 * si] + wx, ds, g.W[si]);
-              const int yi = fg_clamp(fg_org[pp][2 * si + 1] + wy, ds, g.H[si]);
-              const size_t px = (size_t)yi * wl + xi;
-              vals[ps] = __ldg(reinterpret_cast<const uint4*>(fmap + px * C + coff));
-              sc[ps] = fg_dinv[pp][si][wy][wx] * sqrtf(__ldg(nsq + px) + 1e-30f);   // undo the per-level scale
-            }
+            const int X = (pp ? ox1 : ox0) + wx, Y = (pp ? oy1 : oy0) + wy;
+            const int xi = X < 0 ? 0 : min(X >> sh, wl - 1), yi = Y < 0 ? 0 : min(Y >> sh, hl - 1);
+            const int px = yi * wl + xi;
+            vals[ps] = __ldg(reinterpret_cast<const uint4*>(fmap + (size_t)px * C + coff));
+            nq[ps] = __ldg(nsq + px);
+            dv[ps] = (wy >= 0 && wx >= 0) ? fg_dinv[pp][si][wy & 15][wx & 15] : 0.f;   // -1 = conv zero padding
           }
+          mbar_wait(&empty_bar[s], ph ^ 1u);
 #pragma unroll
-          for (int ps = 0; ps < 8; ++ps) {
-            const int row = ps * 16 + r16;
+          for (int ps = 0; ps < 4; ++ps) {               // phase 2: scale, convert, swizzled store
+            const int row = ps * 32 + r32;
+            const float sc = dv[ps] * sqrtf(nq[ps] + 1e-30f);   // undo the per-level normalisation
             __half2* h2 = reinterpret_cast<__half2*>(&vals[ps]);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float2 f = __half22float2(h2[q]);
-              h2[q] = __floats2half2_rn(f.x * sc[ps], f.y * sc[ps]);
+              h2[q] = __floats2half2_rn(f.x * sc, f.y * sc);
             }
             *reinterpret_cast<uint4*>(at + row * 128 + ((l8 ^ (row & 7)) << 4)) = vals[ps];
           }
         } else {
           // rgb im2col chunk: k = tap*6 + img*3 + ch (54 used)
+          mbar_wait(&empty_bar[s], ph ^ 1u);
 #pragma unroll 1
-          for (int ps = 0; ps < 8; ++ps) {
-            const int row = ps * 16 + r16;
+          for (int ps = 0; ps < 4; ++ps) {
+            const int row = ps * 32 + r32;
             const int pp = row >> 6, oy = (row >> 3) & 7, ox = row & 7;
             __align__(16) __half hv[8];
 #pragma unroll
@@ -480,8 +483,8 @@ __global__ void __launch_bounds__(FUSED ? 512 : 384, 1) umma_gemm_kernel(const _
         mbar_arrive(&full_bar[s]);
       }
     }
-  } else if (warp >= 4 && warp < 12) {
-    // ===================== epilogue =====================
+  } else if (warp >= 4 && warp < (FUSED ? 8 : 12)) {
+    // ===================== epilogue (8 warps; 4 warps covering both column halves when FUSED) =====================
     if (SEGMENTED) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int q = warp & 3, hf = (warp - 4) >> 2;
     const int row = q * 32 + lane;
@@ -517,12 +520,17 @@ __global__ void __launch_bounds__(FUSED ? 512 : 384, 1) umma_gemm_kernel(const _
         const uint32_t sph = (uint32_t)(seg >> 1) & 1u;
         mbar_wait(&tfull_bar[slot], sph);
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 256 + hf * 128);
+        constexpr int NH = FUSED ? 2 : 1;              // column halves handled by this warp
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          float v[32];
-          tmem_ld32(taddr + c * 32, v);
-          epilogue_piece<EPI>(p.epi, n_units, m_tile, row, colbase + c * 32, v);
+        for (int hh = 0; hh < NH; ++hh) {
+          const int hcol = FUSED ? hh : hf;
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 256 + hcol * 128);
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            float v[32];
+            tmem_ld32(taddr + c * 32, v);
+            epilogue_piece<EPI>(p.epi, n_units, m_tile, row, n_tile * 256 + hcol * 128 + c * 32, v);
+          }
         }
         tc_fence_before();
         __syncwarp();
