@@ -483,7 +483,7 @@ def test_fused_gather_matches_materialised_gather(nets, seeded_sd):
             torch.cuda.synchronize()
             out[fuse] = (mid[0].cpu(), midp[0].cpu(), fine[0].cpu(), finep[0].cpu())
     finally:
-        net.set_option('fuse_gather', 1)
+        net.set_option('fuse_gather', 0)
         net.set_option('mid_band', 30)
         net.set_option('mid_passes', 3)
     d_mid = (out[1][0] - out[0][0]).abs().max().item()
