@@ -47,6 +47,7 @@ def parse():
     ap.add_argument('--corr-passes', type=int, default=None)
     ap.add_argument('--seg-len', type=int, default=None)
     ap.add_argument('--mid-band', type=int, default=None)
+    ap.add_argument('--fuse-gather', type=int, default=None)
     ap.add_argument('--backbone-fp32', action='store_true', help='keep cuDNN TF32 off in the e2e backbone')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-sample-patches', type=int, default=200)
@@ -217,10 +218,10 @@ def run_ours(args):
     cfg.weights_dict = make_seeded_state_dict(0)
     net = Patch2PixB200(cfg)
     for key, v in (('mid_passes', args.mid_passes), ('fine_passes', args.fine_passes), ('corr_passes', args.corr_passes),
-                   ('seg_len', args.seg_len), ('mid_band', args.mid_band)):
+                   ('seg_len', args.seg_len), ('mid_band', args.mid_band), ('fuse_gather', args.fuse_gather)):
         if v is not None:
             net.set_option(key, v)
-    opts = {k: net._handle.get_option(k) for k in ('mid_passes', 'fine_passes', 'corr_passes', 'seg_len', 'mid_band')}
+    opts = {k: net._handle.get_option(k) for k in ('mid_passes', 'fine_passes', 'corr_passes', 'seg_len', 'mid_band', 'fuse_gather')}
 
     # pair indices: rank 0 decides, NCCL broadcasts (the "scatter pair indices" step)
     total_steps = K + Wm

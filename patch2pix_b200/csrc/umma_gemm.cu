@@ -548,6 +548,243 @@ __global__ void __launch_bounds__(FUSED ? 512 : 384, 1) umma_gemm_kernel(const _
 }
 
 // ------------------------------------------------------------------------------------------------
+// conv1 (1-pass) with the patch gather fused in, second generation: one CTA owns a 128 x 512 tile
+// (all output channels of 2 patches), so every gathered A tile is built once and feeds 8 MMAs
+// (N = 2 x 256); per-tile lookup tables (pixel offset and scale per image / level / window pixel)
+// in shared memory reduce the per-row producer work to two LDS, one LDG and the fp16 re-scaling.
+// 512 threads: warp 0 TMA (weights), 1 MMA, 2 TMEM alloc, 3 idle, 4..7 epilogue, 8..15 A producers.
+// smem: 2 stages x (16 KB A + 64 KB B) + 24 KB tables.
+// ------------------------------------------------------------------------------------------------
+constexpr int kF2Stages = 2;
+constexpr int kF2StageBytes = kATile + 2 * kBTile;
+
+__global__ void __launch_bounds__(512, 1) umma_conv1_fused_kernel(const __grid_constant__ UmmaGemmParams p) {
+  constexpr uint32_t IDESC = make_idesc_f16(128, 256);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  int* tab_px = reinterpret_cast<int*>(smem + kF2Stages * kF2StageBytes);        // [2 patches][2 img][3 lvl][256]
+  float* tab_sc = reinterpret_cast<float*>(tab_px + 3072);                       // same shape
+  __shared__ __align__(8) uint64_t full_bar[kF2Stages];
+  __shared__ __align__(8) uint64_t empty_bar[kF2Stages];
+  __shared__ __align__(8) uint64_t tfull_bar[2];     // per accumulator half
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float fg_dinv[2][2][16][16];
+  __shared__ int fg_org[2][4];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_units = p.epi.n_patches;
+  const int total_tiles = p.m_tiles;
+  const int nsteps = p.nsteps;
+
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&p.b_hi);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kF2Stages; ++i) {
+      mbar_init(&full_bar[i], 257);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int ks = 0; ks < nsteps; ++ks, ++it) {
+          const int s = it % kF2Stages;
+          const uint32_t ph = (uint32_t)(it / kF2Stages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          const KStep k = p.steps[ks];
+          uint8_t* st = smem + (size_t)s * kF2StageBytes;
+          mbar_expect_tx(&full_bar[s], 2 * kBTile);
+          tma_load_2d(&p.b_hi, &full_bar[s], st + kATile, k.bk, 0);
+          tma_load_2d(&p.b_hi, &full_bar[s], st + kATile + kBTile, k.bk, 256);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+        const uint32_t tph = (uint32_t)t & 1u;
+        for (int ks = 0; ks < nsteps; ++ks, ++it) {
+          const int s = it % kF2Stages;
+          const uint32_t ph = (uint32_t)(it / kF2Stages) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * kF2StageBytes);
+          const uint64_t a = make_sw128_desc(sa);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (ks == 0) {
+              mbar_wait(&tempty_bar[h], tph ^ 1u);     // the epilogue has drained this half of the previous tile
+              tc_fence_after();
+            }
+            const uint64_t b = make_sw128_desc(sa + kATile + h * kBTile);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16(tmem_base + (uint32_t)h * 256u, a + 2 * kk, b + 2 * kk, IDESC, (ks > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+          if (ks + 1 == nsteps) {
+            umma_commit(&tfull_bar[0]);
+            umma_commit(&tfull_bar[1]);
+          }
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== A producers =====================
+    const int ptid = threadIdx.x - 256;
+    const int l8 = ptid & 7, r32 = ptid >> 3;
+    const FusedGather& g = p.fg;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (ptid < 8) {
+        const int pp = ptid >> 2, j = ptid & 3;
+        const int n = tile * 2 + pp;
+        int v = 0;
+        if (n < n_units) {
+          if (g.is_float)
+            v = (int)reinterpret_cast<const float*>(g.matches)[(size_t)n * 4 + j];
+          else
+            v = (int)reinterpret_cast<const long long*>(g.matches)[(size_t)n * 4 + j];
+        }
+        fg_org[pp][j] = v - 8;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = ptid; i < 1024; i += 256) {
+        const int pp = i >> 9, si = (i >> 8) & 1, wy = (i >> 4) & 15, wx = i & 15;
+        const int X = fg_org[pp][2 * si] + wx, Y = fg_org[pp][2 * si + 1] + wy;
+        float t = 0.f;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          const int xi = X < 0 ? 0 : min(X >> l, (g.W[si] >> l) - 1), yi = Y < 0 ? 0 : min(Y >> l, (g.H[si] >> l) - 1);
+          t += __ldg(g.nsq[si][l] + (size_t)yi * (g.W[si] >> l) + xi);
+        }
+        fg_dinv[pp][si][wy][wx] = (tile * 2 + pp < n_units) ? __fdiv_rn(kActScale, sqrtf(t + 1e-6f)) : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = ptid; i < 3072; i += 256) {           // [pp][si][lvl][wy][wx]
+        const int wx = i & 15, wy = (i >> 4) & 15, r = i >> 8;
+        const int lvl = r % 3, si = (r / 3) & 1, pp = r / 6;
+        const int sh = lvl + 1;
+        const int X = fg_org[pp][2 * si] + wx, Y = fg_org[pp][2 * si + 1] + wy;
+        const int wl = g.W[si] >> sh, hl = g.H[si] >> sh;
+        const int xi = X < 0 ? 0 : min(X >> sh, wl - 1), yi = Y < 0 ? 0 : min(Y >> sh, hl - 1);
+        const int px = yi * wl + xi;
+        tab_px[i] = px;
+        tab_sc[i] = fg_dinv[pp][si][wy][wx] * sqrtf(__ldg(g.nsq[si][lvl + 1] + px) + 1e-30f);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int ks = 0; ks < nsteps; ++ks, ++it) {
+        const int s = it % kF2Stages;
+        const uint32_t ph = (uint32_t)(it / kF2Stages) & 1u;
+        const KStep k = p.steps[ks];
+        uint8_t* at = smem + (size_t)s * kF2StageBytes;
+        if (k.kind == 0) {
+          const int ty = (k.plane & 2) ? 1 : (k.y < 0 ? 0 : 2), tx = (k.plane & 1) ? 1 : (k.x < 0 ? 0 : 2);
+          const int chunk = k.c0 >> 6, si = chunk >> 2, jj = chunk & 3;
+          const int lvl = jj == 0 ? 0 : (jj == 1 ? 1 : 2);
+          const int C = lvl == 2 ? 128 : 64;
+          const int coff = (jj == 3 ? 64 : 0) + l8 * 8;
+          const __half* fmap = g.nhwc16[si][lvl] + coff;
+          uint4 vals[4];
+          float sc[4];
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) {
+            const int row = ps * 32 + r32;
+            const int pp = row >> 6, wy = 2 * ((row >> 3) & 7) - 1 + ty, wx = 2 * (row & 7) - 1 + tx;
+            const int ti = ((pp * 2 + si) * 3 + lvl) * 256 + ((wy & 15) << 4) + (wx & 15);
+            const int px = tab_px[ti];
+            sc[ps] = (wy >= 0 && wx >= 0) ? tab_sc[ti] : 0.f;      // -1 = conv zero padding
+            vals[ps] = __ldg(reinterpret_cast<const uint4*>(fmap + (size_t)px * C));
+          }
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) {
+            const int row = ps * 32 + r32;
+            __half2* h2 = reinterpret_cast<__half2*>(&vals[ps]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 f = __half22float2(h2[q]);
+              h2[q] = __floats2half2_rn(f.x * sc[ps], f.y * sc[ps]);
+            }
+            *reinterpret_cast<uint4*>(at + row * 128 + ((l8 ^ (row & 7)) << 4)) = vals[ps];
+          }
+        } else {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+#pragma unroll 1
+          for (int ps = 0; ps < 4; ++ps) {
+            const int row = ps * 32 + r32;
+            const int pp = row >> 6, oy = (row >> 3) & 7, ox = row & 7;
+            __align__(16) __half hv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int kk = l8 * 8 + i;
+              float v = 0.f;
+              if (kk < 54) {
+                const int tap = kk / 6, r = kk - tap * 6;
+                const int si = r / 3, ch = r - si * 3;
+                const int wx = 2 * ox - 1 + tap % 3, wy = 2 * oy - 1 + tap / 3;
+                if (wx >= 0 && wy >= 0) {
+                  const int xi = fg_clamp(fg_org[pp][2 * si] + wx, 1, g.W[si]);
+                  const int yi = fg_clamp(fg_org[pp][2 * si + 1] + wy, 1, g.H[si]);
+                  v = __ldg(g.img[si] + ((size_t)ch * g.H[si] + yi) * g.W[si] + xi) * fg_dinv[pp][si][wy][wx];
+                }
+              }
+              hv[i] = __float2half_rn(v);
+            }
+            *reinterpret_cast<uint4*>(at + row * 128 + ((l8 ^ (row & 7)) << 4)) = *reinterpret_cast<const uint4*>(hv);
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(&full_bar[s]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: 4 warps, one TMEM lane quadrant each, 512 columns =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int t = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+      const uint32_t tph = (uint32_t)t & 1u;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait(&tfull_bar[h], tph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 256);
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          float v[32];
+          tmem_ld32(taddr + c * 32, v);
+          epilogue_piece<EPI_CONV1>(p.epi, n_units, tile, row, h * 256 + c * 32, v);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[h]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -618,7 +855,17 @@ int launch_umma_gemm(const UmmaGemmParams& p, int epi, int passes, int num_sms, 
   const int grid = total < num_sms ? total : num_sms;
   if (fused) {
     P2P_REQUIRE(epi == EPI_CONV1 && passes == 1 && !seg, "fused gather is available for 1-pass conv1 only");
-    return launch_one<1, false, EPI_CONV1, true>(p, grid, st);
+    if (p.fg.is_float >= 2) {     // generation 1 (128 x 256 tiles, no tables), kept for comparison: fuse_gather = 2
+      UmmaGemmParams q = p;
+      q.fg.is_float -= 2;
+      return launch_one<1, false, EPI_CONV1, true>(q, grid, st);
+    }
+    const int smem = kF2Stages * kF2StageBytes + 3072 * 8 + 1024;
+    P2P_CUDA_OK(cudaFuncSetAttribute(umma_conv1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int g2 = p.m_tiles < num_sms ? p.m_tiles : num_sms;
+    umma_conv1_fused_kernel<<<g2, 512, smem, st>>>(p);
+    P2P_LAUNCH_OK();
+    return 0;
   }
   switch (epi) {
     case EPI_PLAIN: return launch_epi<EPI_PLAIN>(p, passes, seg, grid, st);

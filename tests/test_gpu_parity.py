@@ -473,7 +473,7 @@ def test_fused_gather_matches_materialised_gather(nets, seeded_sd):
     f1, f2, _, _ = _feats(net, 9, H, W)
     out = {}
     try:
-        for fuse in (1, 0):
+        for fuse in (1, 2, 0):
             net.set_option('fuse_gather', fuse)
             net.set_option('mid_band', 0)
             net.set_option('mid_passes', 1)
@@ -486,7 +486,12 @@ def test_fused_gather_matches_materialised_gather(nets, seeded_sd):
         net.set_option('fuse_gather', 0)
         net.set_option('mid_band', 30)
         net.set_option('mid_passes', 3)
-    d_mid = (out[1][0] - out[0][0]).abs().max().item()
-    d_p = (out[1][1] - out[0][1]).abs().max().item()
-    _report('fused_vs_materialised', {'mid_diff_px': d_mid, 'conf_diff': d_p})
-    assert d_mid < 0.03 and d_p < 5e-4, (d_mid, d_p)
+    rep = {}
+    for fuse in (1, 2):
+        d_mid = (out[fuse][0] - out[0][0]).abs().max().item()
+        d_fine = (out[fuse][2] - out[0][2]).abs().max().item()
+        d_p = (out[fuse][3] - out[0][3]).abs().max().item()
+        rep[f'gen{fuse}'] = {'mid_diff_px': d_mid, 'fine_diff_px': d_fine, 'conf_diff': d_p}
+        assert d_mid < 0.03 and d_p < 5e-4, (fuse, d_mid, d_p)
+    assert torch.equal(out[1][0], out[2][0]), 'both fused generations implement the same arithmetic'
+    _report('fused_vs_materialised', rep)
