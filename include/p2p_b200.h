@@ -74,12 +74,12 @@ P2P_API int p2p_set_regressor_weights(p2p_handle_t h, int which, const p2p_regre
  * "corr_passes" (0 = CUDA-core fp32 correlation, 1/3 = tensor-core), "seg_len" (k-steps per
  * TMEM accumulation segment, 0 = whole K), "gemm_impl" (0 = tcgen05, 1 = CUDA-core checker),
  * "num_sms" (persistent grid size, 0 = all), "profile" (1 = record per-kernel CUDA events),
- * "mid_band" (thousandths of a pixel, default 30 = 3x the largest 1-pass/3-pass difference measured over 77k
+ * "mid_band" (thousandths of a pixel, default 35 = 3x the largest 1-pass/3-pass difference measured over 77k
  * coordinates, profiles/r01_band_stats.json; with mid_passes = 3 every row is first computed 1-pass and
  * only rows with a coordinate within the band of an integer -- where trunc(mid) could differ from the
- * reference -- are re-computed 3-pass; 0 = 3-pass for every row), "fuse_gather" (default 0; 1: 1-pass conv1 launches
- * gather their A tiles in producer warps instead of reading a materialised patch tensor -- parity-tested, but
- * still producer-bound and slower than gather + TMA). */
+ * reference -- are re-computed 3-pass; 0 = 3-pass for every row), "fuse_gather" (default 1: 1-pass conv1 launches
+ * gather their A tiles in producer warps instead of reading a materialised patch tensor; 2 = first-generation
+ * fused kernel, 0 = separate gather kernel + TMA). */
 P2P_API int p2p_set_option(p2p_handle_t h, const char* key, int value);
 P2P_API int p2p_get_option(p2p_handle_t h, const char* key, int* value);
 /* Number of kernel launches enqueued by this handle since creation (bench.py's gpu_launches). */

@@ -59,9 +59,9 @@ struct p2p_handle_s {
   int device = 0;
   int num_sms = 148;
   int opt_mid_passes = 3, opt_fine_passes = 1, opt_corr_passes = 3, opt_seg_len = 3, opt_gemm_impl = 0, opt_num_sms = 0;
-  int opt_mid_band = 30;  // thousandths of a pixel; 0 = pure 3-pass mid stage
-  int opt_fuse_gather = 0;  // 1: 1-pass conv1 builds its A tiles in producer warps (no patch tensor in HBM).
-                            // Correct but producer-bound for now (1.58 ms vs 0.75 + 0.25 ms), hence off by default.
+  int opt_mid_band = 35;  // thousandths of a pixel; 0 = pure 3-pass mid stage
+  int opt_fuse_gather = 1;  // 1: 1-pass conv1 gathers its A tiles in producer warps (128x512 tiles, lookup tables; no patch
+                            // tensor in HBM); 2: first-generation fused kernel (128x256 tiles, producer-bound); 0: gather + TMA
   const int* last_band_count = nullptr;  // device counter of the last risk-band subset
   bool nc_set = false;
   float *nc_w1p = nullptr, *nc_b1p = nullptr, *nc_w2p = nullptr;

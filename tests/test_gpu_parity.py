@@ -225,7 +225,7 @@ def _refine_case(net, sd, pair_idx, H, W, matches, impl, mid_passes, fine_passes
         net.set_option('gemm_impl', 0)
         net.set_option('mid_passes', 3)
         net.set_option('fine_passes', 1)
-        net.set_option('mid_band', 30)
+        net.set_option('mid_band', 35)
     r = {
         'mid_err': (mid[0].cpu() - o_mid[0]).abs().max().item(),
         'mid_p_err': (midp[0].cpu() - o_midp[0]).abs().max().item(),
@@ -250,7 +250,7 @@ def _random_matches(n, H, W, seed, integer):
     return m.long() if integer else m
 
 
-@pytest.mark.parametrize('impl,mid_passes,fine_passes,band', [(1, 3, 3, 0), (0, 3, 3, 0), (0, 3, 1, 0), (0, 1, 1, 0), (0, 3, 1, 30)],
+@pytest.mark.parametrize('impl,mid_passes,fine_passes,band', [(1, 3, 3, 0), (0, 3, 3, 0), (0, 3, 1, 0), (0, 1, 1, 0), (0, 3, 1, 35)],
                          ids=['simt33', 'tc33', 'tc31', 'tc11', 'band31'])
 @pytest.mark.parametrize('integer', [True, False])
 def test_refine_vs_oracle(nets, seeded_sd, impl, mid_passes, fine_passes, band, integer):
@@ -275,7 +275,7 @@ def test_refine_ragged_sizes(nets, seeded_sd, n):
     H, W = 96, 128
     r = _refine_case(net, seeded_sd, 4, H, W, _random_matches(n, H, W, n, True), 0, 3, 1)
     assert r['mid_err'] < 2e-4 and r['fine_same_err'] < 0.05 and r['fine_same_p_err'] < 1e-3, r
-    r = _refine_case(net, seeded_sd, 4, H, W, _random_matches(n, H, W, n, True), 0, 3, 1, 30)
+    r = _refine_case(net, seeded_sd, 4, H, W, _random_matches(n, H, W, n, True), 0, 3, 1, 35)
     assert r['mid_err'] < 0.05 and r['straddle_rows'] == 0 and r['fine_same_err'] < 0.05, r
 
 
@@ -483,15 +483,18 @@ def test_fused_gather_matches_materialised_gather(nets, seeded_sd):
             torch.cuda.synchronize()
             out[fuse] = (mid[0].cpu(), midp[0].cpu(), fine[0].cpu(), finep[0].cpu())
     finally:
-        net.set_option('fuse_gather', 0)
-        net.set_option('mid_band', 30)
+        net.set_option('fuse_gather', 1)
+        net.set_option('mid_band', 35)
         net.set_option('mid_passes', 3)
     rep = {}
     for fuse in (1, 2):
         d_mid = (out[fuse][0] - out[0][0]).abs().max().item()
-        d_fine = (out[fuse][2] - out[0][2]).abs().max().item()
-        d_p = (out[fuse][3] - out[0][3]).abs().max().item()
-        rep[f'gen{fuse}'] = {'mid_diff_px': d_mid, 'fine_diff_px': d_fine, 'conf_diff': d_p}
-        assert d_mid < 0.03 and d_p < 5e-4, (fuse, d_mid, d_p)
+        d_p = (out[fuse][1] - out[0][1]).abs().max().item()
+        same = (out[fuse][0].long() == out[0][0].long()).all(1)          # fine windows identical
+        d_fine = (out[fuse][2] - out[0][2]).abs().max(1)[0][same].max().item()
+        d_fp = (out[fuse][3] - out[0][3]).abs()[same].max().item()
+        rep[f'gen{fuse}'] = {'mid_diff_px': d_mid, 'mid_conf_diff': d_p, 'fine_diff_px_same_window': d_fine,
+                             'fine_conf_diff_same_window': d_fp, 'rows_with_other_window': int((~same).sum())}
+        assert d_mid < 0.03 and d_p < 5e-4 and d_fine < 0.05 and d_fp < 1e-3, (fuse, rep)
     assert torch.equal(out[1][0], out[2][0]), 'both fused generations implement the same arithmetic'
     _report('fused_vs_materialised', rep)
