@@ -370,10 +370,14 @@ __global__ void __launch_bounds__(1024) flag_risky_kernel(const void* __restrict
           m = reinterpret_cast<const float*>(matches_in)[(size_t)r * 4 + j];
         else
           m = (float)reinterpret_cast<const long long*>(matches_in)[(size_t)r * 4 + j];
-        const float v = m + (16.f * tanhf(fmaxf(o, 0.f)) - 8.f);   // un-clamped coordinate
+        const float th = tanhf(fmaxf(o, 0.f));
+        const float v = m + (16.f * th - 8.f);           // un-clamped coordinate
         const float hi = (j == 0) ? W1 : (j == 1) ? H1 : (j == 2) ? W2 : H2;
         if (v <= -tau || v >= hi + tau) continue;        // clamped to the same bound on both sides
-        if (fabsf(v - rintf(v)) < tau) risky = 1;
+        // a 1-pass error do of the raw output moves the coordinate by 16 * sech^2(o) * do: the band
+        // (tau at o = 0) shrinks with the tanh slope, plus a floor for fp32 rounding of the coordinate
+        const float band = fminf(tau, tau * (1.f - th * th) + 3e-4f);
+        if (fabsf(v - rintf(v)) < band) risky = 1;
       }
     }
     const unsigned int ball = __ballot_sync(0xffffffffu, risky);

@@ -17,7 +17,7 @@ torch.backends.cudnn.allow_tf32 = False
 cfg = model_config(torch.device('cuda:0'), 8)
 cfg.weights_dict = make_seeded_state_dict(0)
 net = Patch2PixB200(cfg)
-diffs = []
+diffs, dos = [], []
 with torch.no_grad():
     for p in range(6):
         im1, im2 = synthetic_pair(p, 480, 640)
@@ -29,11 +29,19 @@ with torch.no_grad():
         fine, fp, mid3, mp, cm = net.finish_match(t, 0.0, 400, return_all=True)
         net.set_option('mid_passes', 1)
         mid1, _ = net.forward_fine_match(f1, f2, cm, 16, 'center', net.regress_mid)
-        diffs.append((mid1[0] - mid3[0]).abs().flatten().cpu())
+        d = (mid1[0] - mid3[0]).abs().cpu()
+        diffs.append(d.flatten())
+        # implied error of the raw network output o: d = 16 * sech^2(o) * |do| for un-clamped, un-saturated coordinates
+        t = ((mid3[0].cpu() - cm[0].cpu().float()) + 8.0) / 16.0          # tanh(relu(o))
+        lim = torch.tensor([640.0, 480.0, 640.0, 480.0])
+        ok = (t > 1e-3) & (t < 0.95) & (mid3[0].cpu() > 0.01) & (mid3[0].cpu() < lim - 0.01)
+        dos.append((d / (16.0 * (1.0 - t * t)))[ok].flatten())
         net.set_option('mid_passes', 3)
 d = torch.cat(diffs).double()
 q = torch.quantile(d, torch.tensor([0.5, 0.99, 0.9999], dtype=torch.float64)).tolist()
-rep = {'coords': int(d.numel()), 'max': d.max().item(), 'median': q[0], 'p99': q[1], 'p99.99': q[2],
+do = torch.cat(dos).double()
+rep = {'implied_do_max': do.max().item(), 'implied_do_p99.99': torch.quantile(do[:: max(1, do.numel() // 1000000)], 0.9999).item(),
+       'implied_do_coords': int(do.numel()), 'coords': int(d.numel()), 'max': d.max().item(), 'median': q[0], 'p99': q[1], 'p99.99': q[2],
        'frac_above_0.02': (d > 0.02).double().mean().item(), 'frac_above_0.04': (d > 0.04).double().mean().item()}
 print(json.dumps(rep, indent=1))
 os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
