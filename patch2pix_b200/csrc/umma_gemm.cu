@@ -687,31 +687,30 @@ __global__ void __launch_bounds__(512, 1) umma_conv1_fused_kernel(const __grid_c
         tab_sc[i] = fg_dinv[pp][si][wy][wx] * sqrtf(__ldg(g.nsq[si][lvl + 1] + px) + 1e-30f);
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      // software pipeline: the gathers of k-step i+1 are in flight while k-step i is converted and stored
-      auto issue = [&](int ks, uint4 (&vals)[4], float (&sc)[4]) {
+      for (int ks = 0; ks < nsteps; ++ks, ++it) {
+        const int s = it % kF2Stages;
+        const uint32_t ph = (uint32_t)(it / kF2Stages) & 1u;
         const KStep k = p.steps[ks];
-        if (k.kind != 0) return;
-        const int ty = (k.plane & 2) ? 1 : (k.y < 0 ? 0 : 2), tx = (k.plane & 1) ? 1 : (k.x < 0 ? 0 : 2);
-        const int chunk = k.c0 >> 6, si = chunk >> 2, jj = chunk & 3;
-        const int lvl = jj == 0 ? 0 : (jj == 1 ? 1 : 2);
-        const int C = lvl == 2 ? 128 : 64;
-        const __half* fmap = g.nhwc16[si][lvl] + (jj == 3 ? 64 : 0) + l8 * 8;
-#pragma unroll
-        for (int ps = 0; ps < 4; ++ps) {
-          const int row = ps * 32 + r32;
-          const int pp = row >> 6, wy = 2 * ((row >> 3) & 7) - 1 + ty, wx = 2 * (row & 7) - 1 + tx;
-          const int ti = ((pp * 2 + si) * 3 + lvl) * 256 + ((wy & 15) << 4) + (wx & 15);
-          sc[ps] = (wy >= 0 && wx >= 0) ? tab_sc[ti] : 0.f;      // -1 = conv zero padding
-          vals[ps] = __ldg(reinterpret_cast<const uint4*>(fmap + (size_t)tab_px[ti] * C));
-        }
-      };
-      auto finish = [&](int ks, uint4 (&vals)[4], float (&sc)[4]) {
-        const int itk = it + ks;
-        const int s = itk % kF2Stages;
-        const uint32_t ph = (uint32_t)(itk / kF2Stages) & 1u;
         uint8_t* at = smem + (size_t)s * kF2StageBytes;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        if (p.steps[ks].kind == 0) {
+        if (k.kind == 0) {
+          const int ty = (k.plane & 2) ? 1 : (k.y < 0 ? 0 : 2), tx = (k.plane & 1) ? 1 : (k.x < 0 ? 0 : 2);
+          const int chunk = k.c0 >> 6, si = chunk >> 2, jj = chunk & 3;
+          const int lvl = jj == 0 ? 0 : (jj == 1 ? 1 : 2);
+          const int C = lvl == 2 ? 128 : 64;
+          const int coff = (jj == 3 ? 64 : 0) + l8 * 8;
+          const __half* fmap = g.nhwc16[si][lvl] + coff;
+          uint4 vals[4];
+          float sc[4];
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) {
+            const int row = ps * 32 + r32;
+            const int pp = row >> 6, wy = 2 * ((row >> 3) & 7) - 1 + ty, wx = 2 * (row & 7) - 1 + tx;
+            const int ti = ((pp * 2 + si) * 3 + lvl) * 256 + ((wy & 15) << 4) + (wx & 15);
+            const int px = tab_px[ti];
+            sc[ps] = (wy >= 0 && wx >= 0) ? tab_sc[ti] : 0.f;      // -1 = conv zero padding
+            vals[ps] = __ldg(reinterpret_cast<const uint4*>(fmap + (size_t)px * C));
+          }
+          mbar_wait(&empty_bar[s], ph ^ 1u);
 #pragma unroll
           for (int ps = 0; ps < 4; ++ps) {
             const int row = ps * 32 + r32;
@@ -724,7 +723,7 @@ __global__ void __launch_bounds__(512, 1) umma_conv1_fused_kernel(const __grid_c
             *reinterpret_cast<uint4*>(at + row * 128 + ((l8 ^ (row & 7)) << 4)) = vals[ps];
           }
         } else {
-          // rgb im2col chunk: k = tap*6 + img*3 + ch (54 used)
+          mbar_wait(&empty_bar[s], ph ^ 1u);
 #pragma unroll 1
           for (int ps = 0; ps < 4; ++ps) {
             const int row = ps * 32 + r32;
@@ -751,19 +750,7 @@ __global__ void __launch_bounds__(512, 1) umma_conv1_fused_kernel(const __grid_c
         }
         fence_proxy_async();
         mbar_arrive(&full_bar[s]);
-      };
-      uint4 va[4], vb[4];
-      float sa[4], sb[4];
-      issue(0, va, sa);
-      for (int ks = 0; ks < nsteps; ks += 2) {
-        if (ks + 1 < nsteps) issue(ks + 1, vb, sb);
-        finish(ks, va, sa);
-        if (ks + 1 < nsteps) {
-          if (ks + 2 < nsteps) issue(ks + 2, va, sa);
-          finish(ks + 1, vb, sb);
-        }
       }
-      it += nsteps;
     }
   } else if (warp >= 4) {
     // ===================== epilogue: 4 warps, one TMEM lane quadrant each, 512 columns =====================
