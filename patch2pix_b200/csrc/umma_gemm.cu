@@ -553,17 +553,16 @@ __global__ void __launch_bounds__(FUSED ? 512 : 384, 1) umma_gemm_kernel(const _
 // (N = 2 x 256); per-tile lookup tables (pixel offset and scale per image / level / window pixel)
 // in shared memory reduce the per-row producer work to two LDS, one LDG and the fp16 re-scaling.
 // 512 threads: warp 0 TMA (weights), 1 MMA, 2 TMEM alloc, 3 idle, 4..7 epilogue, 8..15 A producers.
-// smem: A ring 3 x 16 KB (producers), B ring 4 x 32 KB half tiles (TMA; A and B rings are decoupled so
-// that three weight loads are in flight while one is consumed), 24 KB tables.
+// smem: A ring 3 x 16 KB (producers), B ring 8 x 16 KB quarter tiles (TMA; fine-grained so that the TMA
+// latency is covered by 7 items in flight), 24 KB tables.
 // ------------------------------------------------------------------------------------------------
 constexpr int kF2AStages = 3;                 // A ring: 3 x 16 KB (128 rows x 64 ch)
-constexpr int kF2BItems = 4;                  // B ring: 4 x 32 KB (256 output channels x 64 k): 2 k-steps of weights
-constexpr int kF2BItem = kBTile;              // bytes (N = 128 items were measured slower: 16 MMAs per k-step
-                                              // re-read the A tile and saturate the shared-memory read port)
+constexpr int kF2BItems = 8;                  // B ring: 8 x 16 KB (128 output channels x 64 k): 2 k-steps of weights
+constexpr int kF2BItem = 128 * 128;           // bytes
 constexpr int kF2TileBytes = kF2AStages * kATile + kF2BItems * kF2BItem;
 
 __global__ void __launch_bounds__(512, 1) umma_conv1_fused_kernel(const __grid_constant__ UmmaGemmParams p) {
-  constexpr uint32_t IDESC = make_idesc_f16(128, 256);
+  constexpr uint32_t IDESC = make_idesc_f16(128, 128);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_ring = smem;
@@ -585,7 +584,7 @@ __global__ void __launch_bounds__(512, 1) umma_conv1_fused_kernel(const __grid_c
   const int total_tiles = p.m_tiles;
   const int nsteps = p.nsteps;
 
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&p.b_hi);
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&p.b_lo);
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kF2AStages; ++i) {
       mbar_init(&fullA[i], 256);
@@ -614,12 +613,12 @@ __global__ void __launch_bounds__(512, 1) umma_conv1_fused_kernel(const __grid_c
         for (int ks = 0; ks < nsteps; ++ks) {
           const KStep k = p.steps[ks];
 #pragma unroll 1
-          for (int q = 0; q < 2; ++q, ++itb) {
+          for (int q = 0; q < 4; ++q, ++itb) {
             const int sb = itb % kF2BItems;
             const uint32_t ph = (uint32_t)(itb / kF2BItems) & 1u;
             mbar_wait(&emptyB[sb], ph ^ 1u);
             mbar_expect_tx(&fullB[sb], kF2BItem);
-            tma_load_2d(&p.b_hi, &fullB[sb], b_ring + (size_t)sb * kF2BItem, k.bk, q * 256);
+            tma_load_2d(&p.b_lo, &fullB[sb], b_ring + (size_t)sb * kF2BItem, k.bk, q * 128);   // b_lo: 128-row boxes
           }
         }
       }
@@ -636,9 +635,9 @@ __global__ void __launch_bounds__(512, 1) umma_conv1_fused_kernel(const __grid_c
           tc_fence_after();
           const uint64_t a = make_sw128_desc(smem_u32(a_ring + (size_t)sA * kATile));
 #pragma unroll 1
-          for (int q = 0; q < 2; ++q, ++itb) {
-            if (ks == 0) {
-              mbar_wait(&tempty_bar[q], tph ^ 1u);        // the epilogue has drained this half of the previous tile
+          for (int q = 0; q < 4; ++q, ++itb) {
+            if (ks == 0 && (q & 1) == 0) {
+              mbar_wait(&tempty_bar[q >> 1], tph ^ 1u);   // the epilogue has drained this half of the previous tile
               tc_fence_after();
             }
             const int sb = itb % kF2BItems;
@@ -648,7 +647,7 @@ __global__ void __launch_bounds__(512, 1) umma_conv1_fused_kernel(const __grid_c
             const uint64_t b = make_sw128_desc(smem_u32(b_ring + (size_t)sb * kF2BItem));
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              umma_f16(tmem_base + (uint32_t)q * 256u, a + 2 * kk, b + 2 * kk, IDESC, (ks > 0 || kk > 0) ? 1u : 0u);
+              umma_f16(tmem_base + (uint32_t)q * 128u, a + 2 * kk, b + 2 * kk, IDESC, (ks > 0 || kk > 0) ? 1u : 0u);
             umma_commit(&emptyB[sb]);
           }
           umma_commit(&emptyA[sA]);
