@@ -738,8 +738,6 @@ int run_regressor(p2p_handle_s* h, Regressor& R, int which, int passes, const Re
       p.epi.y_lo = lo ? B.y_lo : nullptr;
       p.epi.n_patches = n;
       if (fused) {
-        const uint32_t qbox[2] = {64, 128};   // the fused kernel streams the weights in 128-row quarter tiles
-        if ((rc = make_tmap_fp16(&p.b_lo, R.w1_hi, 2, bd, bs, qbox))) return rc;
         for (int s2 = 0; s2 < 2; ++s2) {
           p.fg.img[s2] = h->pf[s2].img;
           for (int l = 0; l < 3; ++l) p.fg.nhwc16[s2][l] = h->pf[s2].nhwc16[l];

@@ -553,26 +553,19 @@ __global__ void __launch_bounds__(FUSED ? 512 : 384, 1) umma_gemm_kernel(const _
 // (N = 2 x 256); per-tile lookup tables (pixel offset and scale per image / level / window pixel)
 // in shared memory reduce the per-row producer work to two LDS, one LDG and the fp16 re-scaling.
 // 512 threads: warp 0 TMA (weights), 1 MMA, 2 TMEM alloc, 3 idle, 4..7 epilogue, 8..15 A producers.
-// smem: A ring 3 x 16 KB (producers), B ring 8 x 16 KB quarter tiles (TMA; fine-grained so that the TMA
-// latency is covered by 7 items in flight), 24 KB tables.
+// smem: 2 stages x (16 KB A + 64 KB B) + 24 KB tables.
 // ------------------------------------------------------------------------------------------------
-constexpr int kF2AStages = 3;                 // A ring: 3 x 16 KB (128 rows x 64 ch)
-constexpr int kF2BItems = 8;                  // B ring: 8 x 16 KB (128 output channels x 64 k): 2 k-steps of weights
-constexpr int kF2BItem = 128 * 128;           // bytes
-constexpr int kF2TileBytes = kF2AStages * kATile + kF2BItems * kF2BItem;
+constexpr int kF2Stages = 2;
+constexpr int kF2StageBytes = kATile + 2 * kBTile;
 
 __global__ void __launch_bounds__(512, 1) umma_conv1_fused_kernel(const __grid_constant__ UmmaGemmParams p) {
-  constexpr uint32_t IDESC = make_idesc_f16(128, 128);
+  constexpr uint32_t IDESC = make_idesc_f16(128, 256);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* a_ring = smem;
-  uint8_t* b_ring = smem + kF2AStages * kATile;
-  int* tab_px = reinterpret_cast<int*>(smem + kF2TileBytes);                     // [2 patches][2 img][3 lvl][256]
+  int* tab_px = reinterpret_cast<int*>(smem + kF2Stages * kF2StageBytes);        // [2 patches][2 img][3 lvl][256]
   float* tab_sc = reinterpret_cast<float*>(tab_px + 3072);                       // same shape
-  __shared__ __align__(8) uint64_t fullA[kF2AStages];
-  __shared__ __align__(8) uint64_t emptyA[kF2AStages];
-  __shared__ __align__(8) uint64_t fullB[kF2BItems];
-  __shared__ __align__(8) uint64_t emptyB[kF2BItems];
+  __shared__ __align__(8) uint64_t full_bar[kF2Stages];
+  __shared__ __align__(8) uint64_t empty_bar[kF2Stages];
   __shared__ __align__(8) uint64_t tfull_bar[2];     // per accumulator half
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_smem;
@@ -584,15 +577,11 @@ __global__ void __launch_bounds__(512, 1) umma_conv1_fused_kernel(const __grid_c
   const int total_tiles = p.m_tiles;
   const int nsteps = p.nsteps;
 
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&p.b_lo);
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&p.b_hi);
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kF2AStages; ++i) {
-      mbar_init(&fullA[i], 256);
-      mbar_init(&emptyA[i], 1);
-    }
-    for (int i = 0; i < kF2BItems; ++i) {
-      mbar_init(&fullB[i], 1);
-      mbar_init(&emptyB[i], 1);
+    for (int i = 0; i < kF2Stages; ++i) {
+      mbar_init(&full_bar[i], 257);
+      mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -608,49 +597,44 @@ __global__ void __launch_bounds__(512, 1) umma_conv1_fused_kernel(const __grid_c
 
   if (warp == 0) {
     if (lane == 0) {
-      int itb = 0;
+      int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        for (int ks = 0; ks < nsteps; ++ks) {
+        for (int ks = 0; ks < nsteps; ++ks, ++it) {
+          const int s = it % kF2Stages;
+          const uint32_t ph = (uint32_t)(it / kF2Stages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
           const KStep k = p.steps[ks];
-#pragma unroll 1
-          for (int q = 0; q < 4; ++q, ++itb) {
-            const int sb = itb % kF2BItems;
-            const uint32_t ph = (uint32_t)(itb / kF2BItems) & 1u;
-            mbar_wait(&emptyB[sb], ph ^ 1u);
-            mbar_expect_tx(&fullB[sb], kF2BItem);
-            tma_load_2d(&p.b_lo, &fullB[sb], b_ring + (size_t)sb * kF2BItem, k.bk, q * 128);   // b_lo: 128-row boxes
-          }
+          uint8_t* st = smem + (size_t)s * kF2StageBytes;
+          mbar_expect_tx(&full_bar[s], 2 * kBTile);
+          tma_load_2d(&p.b_hi, &full_bar[s], st + kATile, k.bk, 0);
+          tma_load_2d(&p.b_hi, &full_bar[s], st + kATile + kBTile, k.bk, 256);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      int ita = 0, itb = 0, t = 0;
+      int it = 0, t = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
         const uint32_t tph = (uint32_t)t & 1u;
-        for (int ks = 0; ks < nsteps; ++ks, ++ita) {
-          const int sA = ita % kF2AStages;
-          const uint32_t phA = (uint32_t)(ita / kF2AStages) & 1u;
-          mbar_wait(&fullA[sA], phA);
+        for (int ks = 0; ks < nsteps; ++ks, ++it) {
+          const int s = it % kF2Stages;
+          const uint32_t ph = (uint32_t)(it / kF2Stages) & 1u;
+          mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint64_t a = make_sw128_desc(smem_u32(a_ring + (size_t)sA * kATile));
-#pragma unroll 1
-          for (int q = 0; q < 4; ++q, ++itb) {
-            if (ks == 0 && (q & 1) == 0) {
-              mbar_wait(&tempty_bar[q >> 1], tph ^ 1u);   // the epilogue has drained this half of the previous tile
+          const uint32_t sa = smem_u32(smem + (size_t)s * kF2StageBytes);
+          const uint64_t a = make_sw128_desc(sa);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (ks == 0) {
+              mbar_wait(&tempty_bar[h], tph ^ 1u);     // the epilogue has drained this half of the previous tile
               tc_fence_after();
             }
-            const int sb = itb % kF2BItems;
-            const uint32_t phB = (uint32_t)(itb / kF2BItems) & 1u;
-            mbar_wait(&fullB[sb], phB);
-            tc_fence_after();
-            const uint64_t b = make_sw128_desc(smem_u32(b_ring + (size_t)sb * kF2BItem));
+            const uint64_t b = make_sw128_desc(sa + kATile + h * kBTile);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
-              umma_f16(tmem_base + (uint32_t)q * 128u, a + 2 * kk, b + 2 * kk, IDESC, (ks > 0 || kk > 0) ? 1u : 0u);
-            umma_commit(&emptyB[sb]);
+              umma_f16(tmem_base + (uint32_t)h * 256u, a + 2 * kk, b + 2 * kk, IDESC, (ks > 0 || kk > 0) ? 1u : 0u);
           }
-          umma_commit(&emptyA[sA]);
+          umma_commit(&empty_bar[s]);
           if (ks + 1 == nsteps) {
             umma_commit(&tfull_bar[0]);
             umma_commit(&tfull_bar[1]);
@@ -704,12 +688,10 @@ __global__ void __launch_bounds__(512, 1) umma_conv1_fused_kernel(const __grid_c
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       for (int ks = 0; ks < nsteps; ++ks, ++it) {
-        const int s = it % kF2AStages;
-        const uint32_t ph = (uint32_t)(it / kF2AStages) & 1u;
+        const int s = it % kF2Stages;
+        const uint32_t ph = (uint32_t)(it / kF2Stages) & 1u;
         const KStep k = p.steps[ks];
-        uint8_t* at = a_ring + (size_t)s * kATile;
-        uint64_t* empty_bar = emptyA;
-        uint64_t* full_bar = fullA;
+        uint8_t* at = smem + (size_t)s * kF2StageBytes;
         if (k.kind == 0) {
           const int ty = (k.plane & 2) ? 1 : (k.y < 0 ? 0 : 2), tx = (k.plane & 1) ? 1 : (k.x < 0 ? 0 : 2);
           const int chunk = k.c0 >> 6, si = chunk >> 2, jj = chunk & 3;
@@ -878,7 +860,7 @@ int launch_umma_gemm(const UmmaGemmParams& p, int epi, int passes, int num_sms, 
       q.fg.is_float -= 2;
       return launch_one<1, false, EPI_CONV1, true>(q, grid, st);
     }
-    const int smem = kF2TileBytes + 3072 * 8 + 1024;
+    const int smem = kF2Stages * kF2StageBytes + 3072 * 8 + 1024;
     P2P_CUDA_OK(cudaFuncSetAttribute(umma_conv1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int g2 = p.m_tiles < num_sms ? p.m_tiles : num_sms;
     umma_conv1_fused_kernel<<<g2, 512, smem, st>>>(p);
