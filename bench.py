@@ -62,6 +62,16 @@ def model_config(device, panc):
                      weights_dict=None, change_stride=True, regressor_config=rc)
 
 
+def load_traffic():
+    """DRAM bytes (read + write) per launch from the committed `ncu --set full` capture of the round
+    (profiles/r01_traffic.json: kernel kind -> bytes), or {}."""
+    p = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
+
+
 def load_peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -358,8 +368,12 @@ def run_ours(args):
         if dom:
             ach = kern[dom]['algorithmic_tflops']
             gemm_ms = sum(kern[k]['ms_per_launch'] * kern[k]['launches'] for k in gemm_names)
-            roofline = {'kernel': f'umma_gemm_kernel ({dom})', 'bound': 'tensor', 'achieved': ach, 'peak': peaks['tflops'],
-                        'unit': 'TFLOP/s', 'frac': ach / peaks['tflops'], 'traffic': None,
+            kname = 'umma_conv1_fused_kernel' if (dom.startswith('conv1') and not dom.endswith('band') and opts['fuse_gather'] == 1) \
+                else 'umma_gemm_kernel'
+            traffic = load_traffic().get(dom if kname == 'umma_gemm_kernel' else 'conv1_fused')
+            roofline = {'kernel': f'{kname} ({dom})', 'bound': 'tensor', 'achieved': ach, 'peak': peaks['tflops'],
+                        'unit': 'TFLOP/s', 'frac': ach / peaks['tflops'], 'traffic': traffic,
+                        'traffic_unit': 'bytes of DRAM read+write per launch (ncu --set full, profiles/)',
                         'peak_source': peaks['src'] + ' bf16 sustained (fp16 runs at the same tensor rate)',
                         'tensor_passes': kern[dom]['tensor_passes'],
                         'issued_frac': kern[dom]['issued_tflops'] / peaks['tflops'],
