@@ -310,16 +310,6 @@ int launch_mutual_matching(const float* x, int nA, int nB, float* rowmax, unsign
 // produces 32 channels (16 per net) and layer 2 reduces each group of 16 to one map.
 // hidden layout: [A cell][32][hB][wB] fp32 (HBM round trip: 2*32*V*4 B, << the FMA time).
 // ------------------------------------------------------------------------------------------------
-// NC weights live in constant memory: every weight read in the two kernels is warp-uniform, so it goes
-// through the uniform datapath / constant cache instead of the shared-memory port that the activation
-// tiles need (with smem-resident weights both layers were bound by shared-memory bandwidth, not by FMAs).
-struct NcConst {
-  float w1[81 * 32];
-  float w2[81 * 32];
-  float b1[32];
-};
-__constant__ NcConst c_nc;
-
 // layer 1: grid (ceil(hB/8), nA), block (ceil(wB/2), 8); thread = 2 adjacent B cells x 32 channels.
 template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) nc_layer1_kernel(const float* __restrict__ x, int hA, int wA, int hB, int wB,
@@ -327,12 +317,14 @@ __global__ void __launch_bounds__(MAXT, MINB) nc_layer1_kernel(const float* __re
                                                        float* __restrict__ hidden) {
   extern __shared__ __align__(16) float smem[];
   const int PW = wB + 4;                 // halo row pitch (>= wB+2, covers the 2-wide thread tile)
-  float* xs = smem;                      // [9][10][PW]
+  float* w1s = smem;                     // [81][32]
+  float* xs = smem + 81 * 32;            // [9][10][PW]
   const int nthreads = blockDim.x * blockDim.y;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const int a = blockIdx.y, ia = a / wA, ja = a - ia * wA;
   const int k0 = blockIdx.x * 8;
   const int nB = hB * wB;
+  for (int i = tid; i < 81 * 32; i += nthreads) w1s[i] = w1p[i];
   for (int i = tid; i < 9 * 10 * PW; i += nthreads) {
     const int ab = i / (10 * PW);
     const int rem = i - ab * 10 * PW;
@@ -349,7 +341,7 @@ __global__ void __launch_bounds__(MAXT, MINB) nc_layer1_kernel(const float* __re
   const int l0 = 2 * tl, k = k0 + tk;
   float acc0[32], acc1[32];
 #pragma unroll
-  for (int c = 0; c < 32; ++c) acc0[c] = acc1[c] = c_nc.b1[c];
+  for (int c = 0; c < 32; ++c) acc0[c] = acc1[c] = b1p[c];
   for (int ab = 0; ab < 9; ++ab) {
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -359,12 +351,18 @@ __global__ void __launch_bounds__(MAXT, MINB) nc_layer1_kernel(const float* __re
       for (int e = 0; e < 3; ++e) {
         const float u0 = e == 0 ? v0 : (e == 1 ? v1 : v2);
         const float u1 = e == 0 ? v1 : (e == 1 ? v2 : v3);
-        const float* wv = c_nc.w1 + (ab * 9 + d * 3 + e) * 32;      // warp-uniform -> constant bank
+        const float4* wv = reinterpret_cast<const float4*>(w1s + (ab * 9 + d * 3 + e) * 32);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float wq = wv[c];
-          acc0[c] = fmaf(u0, wq, acc0[c]);
-          acc1[c] = fmaf(u1, wq, acc1[c]);
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 wq = wv[c4];
+          acc0[c4 * 4 + 0] = fmaf(u0, wq.x, acc0[c4 * 4 + 0]);
+          acc0[c4 * 4 + 1] = fmaf(u0, wq.y, acc0[c4 * 4 + 1]);
+          acc0[c4 * 4 + 2] = fmaf(u0, wq.z, acc0[c4 * 4 + 2]);
+          acc0[c4 * 4 + 3] = fmaf(u0, wq.w, acc0[c4 * 4 + 3]);
+          acc1[c4 * 4 + 0] = fmaf(u1, wq.x, acc1[c4 * 4 + 0]);
+          acc1[c4 * 4 + 1] = fmaf(u1, wq.y, acc1[c4 * 4 + 1]);
+          acc1[c4 * 4 + 2] = fmaf(u1, wq.z, acc1[c4 * 4 + 2]);
+          acc1[c4 * 4 + 3] = fmaf(u1, wq.w, acc1[c4 * 4 + 3]);
         }
       }
     }
@@ -418,7 +416,8 @@ __global__ void __launch_bounds__(384) nc_layer2_kernel(const float* __restrict_
   const int PW = nc2_pitch(wB);                       // [3 unused | left halo | interior | right halo ...]
   const int PH = hB + 2 + 1;                          // covers 2*tk+3
   const int plane = PH * PW;
-  float* tile = smem;                                 // [2 buffers][4 planes][PH][PW]
+  float* w2s = smem;                                  // [81][32]
+  float* tile = smem + 81 * 32;                       // [2 buffers][4 planes][PH][PW]
   __shared__ int s_nb[18];
   __shared__ int s_nnb;
   const int nthreads = blockDim.x * blockDim.y;
@@ -426,6 +425,7 @@ __global__ void __launch_bounds__(384) nc_layer2_kernel(const float* __restrict_
   const int nJ = (wA + JB - 1) / JB;
   const int ia = blockIdx.x / nJ, j0 = (blockIdx.x - ia * nJ) * JB;
   const int nB = hB * wB;
+  for (int i = tid; i < 81 * 32; i += nthreads) w2s[i] = w2p[i];
   for (int i = tid; i < 8 * plane + 16; i += nthreads) tile[i] = 0.f;   // halo stays zero for the whole kernel
   if (tid == 0) {
     int n = 0;
@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(384) nc_layer2_kernel(const float* __restrict_
       for (int jj = 0; jj < 4; ++jj) {
         const int b = dj - jj;                       // A-column tap of output jj for this neighbour
         if (jj < JB && b >= 0 && b <= 2) {           // block-uniform
-          const float* wrow = c_nc.w2 + (di * 3 + b) * 9 * 32 + c0 + cc;   // warp-uniform -> constant bank
+          const float* wrow = w2s + (di * 3 + b) * 9 * 32 + c0 + cc;
 #pragma unroll
           for (int d = 0; d < 3; ++d)
 #pragma unroll
@@ -552,14 +552,11 @@ __global__ void __launch_bounds__(384) nc_layer2_kernel(const float* __restrict_
 int launch_neigh_consensus(const float* x, int hA, int wA, int hB, int wB, const float* w1p, const float* b1p,
                            const float* w2p, float b2, float* hidden, float* out, cudaStream_t st) {
   const int nA = hA * wA;
-  // w1p | w2p | b1p are one contiguous device allocation (api.cu); stream-ordered 20 KB device-to-device copy
-  P2P_REQUIRE(w2p == w1p + 81 * 32 && b1p == w2p + 81 * 32, "NC weights must be packed contiguously");
-  P2P_CUDA_OK(cudaMemcpyToSymbolAsync(c_nc, w1p, sizeof(NcConst), 0, cudaMemcpyDeviceToDevice, st));
   {
     dim3 block(cdiv(wB, 2), 8);
     P2P_REQUIRE(block.x * block.y <= 512, "NC layer 1: pooled width too large (wB <= 128)");
     dim3 grid(cdiv(hB, 8), nA);
-    const size_t smem = sizeof(float) * (9 * 10 * (wB + 4));
+    const size_t smem = sizeof(float) * (81 * 32 + 9 * 10 * (wB + 4));
     if (block.x * block.y <= 160) {   // small B grids: cap registers so that 4 blocks share an SM
       auto k = nc_layer1_kernel<160, 4>;
       P2P_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -579,7 +576,7 @@ int launch_neigh_consensus(const float* x, int hA, int wA, int hB, int wB, const
     P2P_REQUIRE(cdiv(hB * wB, (int)(block.x * block.y)) <= kNc2MaxCopies, "NC layer 2: copy slots exhausted");
     P2P_REQUIRE(wB % 4 != 0 || cdiv(hB * wB / 4, (int)(block.x * block.y)) <= 3, "NC layer 2: vector copy slots exhausted");
     const int PW = nc2_pitch(wB), PH = hB + 3;
-    const size_t smem = sizeof(float) * (8 * PH * PW + 16);
+    const size_t smem = sizeof(float) * (81 * 32 + 8 * PH * PW + 16);
     P2P_REQUIRE(smem <= 200 * 1024, "NC layer 2: pooled B grid does not fit shared memory");
     // A cells per block: the choice with the least wave-quantisation waste on this device
     int JB = 2, nsm = 148;
