@@ -490,9 +490,22 @@ class Patch2PixB200(nn.Module):
         g = getattr(self, '_bb_graphs', None)
         if g is not None and tuple(im1.shape) == g['shape'] and im1.shape[0] == 1:
             inst = g['inst'][slot % len(g['inst'])]
-            inst['inp'][0:1].copy_(im1, non_blocking=True)
-            inst['inp'][1:2].copy_(im2, non_blocking=True)
+            main = torch.cuda.current_stream(self.device)
+            if im1.is_cuda:
+                inst['inp'][0:1].copy_(im1, non_blocking=True)
+                inst['inp'][1:2].copy_(im2, non_blocking=True)
+            else:
+                # host images: H2D on a side stream so that the copy overlaps the kernels still queued on the
+                # main stream; the instance's input buffer is free once its previous replay has finished
+                cs = g['copy_stream']
+                cs.wait_event(inst['consumed'])
+                with torch.cuda.stream(cs):
+                    inst['inp'][0:1].copy_(im1, non_blocking=True)
+                    inst['inp'][1:2].copy_(im2, non_blocking=True)
+                    ready = cs.record_event()
+                main.wait_event(ready)
             inst['graph'].replay()
+            inst['consumed'] = main.record_event()
             feats = inst['out']
         else:
             feats = self.extract.forward_all(torch.cat([im1, im2], 0), [], early_feat=True)
@@ -516,7 +529,10 @@ class Patch2PixB200(nn.Module):
                         out = self.extract.forward_all(inp, [], early_feat=True)
                     insts.append({'inp': inp, 'graph': graph, 'out': out})
             torch.cuda.current_stream().wait_stream(side)
-        self._bb_graphs = {'shape': shape, 'inst': insts}
+            for inst in insts:
+                inst['consumed'] = torch.cuda.current_stream().record_event()
+            copy_stream = torch.cuda.Stream()
+        self._bb_graphs = {'shape': shape, 'inst': insts, 'copy_stream': copy_stream}
 
     def predict_train_sequence(self, im1, im2, ksize=2, ptmax=400, return_all=False):
         """train_patch2pix.py:97-118 under eval()/no_grad: forward -> cal_coarse_matches ->
