@@ -746,7 +746,8 @@ int run_regressor(p2p_handle_s* h, Regressor& R, int which, int passes, const Re
           p.fg.W[s2] = h->pf[s2].W;
         }
         p.fg.matches = matches_in;
-        p.fg.is_float = is_float + (h->opt_fuse_gather == 2 ? 2 : 0);
+        p.fg.is_float = is_float;
+        p.fg.generation = h->opt_fuse_gather == 2 ? 1 : 2;
       }
       ProfScope ps(h, kb + 1, st);
       if ((rc = launch_umma_gemm(p, EPI_CONV1, passes, sms(h), st, fused))) return rc;

@@ -855,11 +855,8 @@ int launch_umma_gemm(const UmmaGemmParams& p, int epi, int passes, int num_sms, 
   const int grid = total < num_sms ? total : num_sms;
   if (fused) {
     P2P_REQUIRE(epi == EPI_CONV1 && passes == 1 && !seg, "fused gather is available for 1-pass conv1 only");
-    if (p.fg.is_float >= 2) {     // generation 1 (128 x 256 tiles, no tables), kept for comparison: fuse_gather = 2
-      UmmaGemmParams q = p;
-      q.fg.is_float -= 2;
-      return launch_one<1, false, EPI_CONV1, true>(q, grid, st);
-    }
+    if (p.fg.generation == 1)     // first version (128 x 256 tiles, no tables), kept for comparison: fuse_gather = 2
+      return launch_one<1, false, EPI_CONV1, true>(p, grid, st);
     const int smem = kF2Stages * kF2StageBytes + 3072 * 8 + 1024;
     P2P_CUDA_OK(cudaFuncSetAttribute(umma_conv1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int g2 = p.m_tiles < num_sms ? p.m_tiles : num_sms;

@@ -36,6 +36,7 @@ struct FusedGather {
   int H[2], W[2];
   const void* matches;            // [n][4] int64 or fp32
   int is_float;
+  int generation;                 // 2: 128x512 tiles + lookup tables (default); 1: first version (128x256 tiles)
 };
 
 struct UmmaGemmParams {
