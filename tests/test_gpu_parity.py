@@ -498,3 +498,26 @@ def test_fused_gather_matches_materialised_gather(nets, seeded_sd):
         assert d_mid < 0.03 and d_p < 5e-4 and d_fine < 0.05 and d_fp < 1e-3, (fuse, rep)
     assert torch.equal(out[1][0], out[2][0]), 'both fused generations implement the same arithmetic'
     _report('fused_vs_materialised', rep)
+
+
+def test_estimate_matches_helper(seeded_sd):
+    """The matcher glue of utils/eval/model_helper.py:64-109 (io_thres filter, rescaling) on top of the CUDA path."""
+    from oracle import p2p_oracle as O
+    from patch2pix_b200.eval_helper import estimate_matches, load_model
+    from patch2pix_b200.synth import synthetic_pair
+    net = load_model(seeded_sd)
+    im1, im2 = synthetic_pair(6, 240, 320)
+    m, s, c = estimate_matches(net, im1, im2, scale1=(2.0, 1.5), scale2=(1.25, 1.0), io_thres=0.45)
+    with torch.no_grad():
+        f1 = net.extract.forward_all(im1.cuda(), [], True)
+        f2 = net.extract.forward_all(im2.cuda(), [], True)
+        fine, fp, cm = O.hot_path_from_feats([t.cpu() for t in f1], [t.cpu() for t in f2], seeded_sd, 2, 0.0, True)
+    fine, fp, cm = fine[0].reshape(-1, 4).numpy(), fp[0].reshape(-1).numpy(), cm[0].numpy()
+    pos = np.where(fp > 0.45)[0]
+    if len(pos) > 0:
+        fine, fp, cm = fine[pos], fp[pos], cm[pos]
+    up = np.array([[2.0, 1.5, 1.25, 1.0]])
+    assert m.shape == fine.shape and np.abs(m - up * fine).max() < 0.5 * 2.0
+    assert np.abs(s - fp).max() < 1e-3 and np.array_equal(c, up * cm)
+    mc, sc, _ = estimate_matches(net, im1, im2, eval_type='coarse', mutual=False)
+    assert mc.shape[1] == 4 and mc.shape[0] == sc.shape[0] > 0
