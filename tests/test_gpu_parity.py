@@ -507,13 +507,16 @@ def test_estimate_matches_helper(seeded_sd):
     from patch2pix_b200.synth import synthetic_pair
     net = load_model(seeded_sd)
     im1, im2 = synthetic_pair(6, 240, 320)
-    m, s, c = estimate_matches(net, im1, im2, scale1=(2.0, 1.5), scale2=(1.25, 1.0), io_thres=0.45)
     with torch.no_grad():
-        f1 = net.extract.forward_all(im1.cuda(), [], True)
-        f2 = net.extract.forward_all(im2.cuda(), [], True)
+        f1, f2 = net.extract_pair(im1.cuda(), im2.cuda())         # the same (batched) backbone call predict_fine makes
         fine, fp, cm = O.hot_path_from_feats([t.cpu() for t in f1], [t.cpu() for t in f2], seeded_sd, 2, 0.0, True)
     fine, fp, cm = fine[0].reshape(-1, 4).numpy(), fp[0].reshape(-1).numpy(), cm[0].numpy()
-    pos = np.where(fp > 0.45)[0]
+    srt = np.sort(fp)
+    gaps = srt[1:] - srt[:-1]
+    g = int(np.argmax(gaps))
+    thr = float(0.5 * (srt[g] + srt[g + 1]))          # threshold in the widest score gap: robust to 1e-4 differences
+    m, s, c = estimate_matches(net, im1, im2, scale1=(2.0, 1.5), scale2=(1.25, 1.0), io_thres=thr)
+    pos = np.where(fp > thr)[0]
     if len(pos) > 0:
         fine, fp, cm = fine[pos], fp[pos], cm[pos]
     up = np.array([[2.0, 1.5, 1.25, 1.0]])
