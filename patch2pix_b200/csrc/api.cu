@@ -45,6 +45,9 @@ struct Regressor {
   float *scale1 = nullptr, *bias1 = nullptr, *scale2 = nullptr, *bias2 = nullptr;
   float y_scale = 1.f;
   FcWeights fc = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // tensor-core FC path: K-major fp16 hi/lo weights [out][in] with per-row pow2 scale, 1/(act*w scale), bias
+  __half *f1_hi = nullptr, *f1_lo = nullptr, *f2_hi = nullptr, *f2_lo = nullptr;
+  float *fa1 = nullptr, *fa2 = nullptr;
   KStep steps1[kConv1Steps];
   KStep steps2[kConv2Steps];
   KStep *d_steps1 = nullptr, *d_steps2 = nullptr;
@@ -60,6 +63,7 @@ struct p2p_handle_s {
   int num_sms = 148;
   int opt_mid_passes = 3, opt_fine_passes = 1, opt_corr_passes = 3, opt_seg_len = 3, opt_gemm_impl = 0, opt_num_sms = 0;
   int opt_mid_band = 35;  // thousandths of a pixel; 0 = pure 3-pass mid stage
+  int opt_fc_impl = 1;      // 1: the two big Linear layers on the tensor cores (3-pass); 0: CUDA-core FC kernel
   int opt_fuse_gather = 1;  // 1: 1-pass conv1 gathers its A tiles in producer warps (128x512 tiles, lookup tables; no patch
                             // tensor in HBM); 2: first-generation fused kernel (128x256 tiles, producer-bound); 0: gather + TMA
   const int* last_band_count = nullptr;  // device counter of the last risk-band subset
@@ -222,8 +226,27 @@ int pack_regressor(p2p_handle_s* h, Regressor& R, const p2p_regressor_weights_t&
     for (int k = 0; k < 256; ++k) f3t[k * 5 + o] = w.fc6_weight[o * 256 + k];
     f3b[o] = w.fc6_bias[o];
   }
+  // tensor-core FC operands
+  std::vector<__half> f1h((size_t)512 * 512), f1l((size_t)512 * 512), f2h((size_t)256 * 512), f2l((size_t)256 * 512);
+  std::vector<float> fa1(512), fa2(256);
+  for (int o = 0; o < 512; ++o) {
+    float m = 0.f;
+    for (int k = 0; k < 512; ++k) m = fmaxf(m, fabsf(w.fc0_weight[(size_t)o * 512 + k] * gf1[o]));
+    const float sw = pow2_floor_scale(m, 1024.f);
+    fa1[o] = 1.f / (kFcActScale * sw);
+    for (int k = 0; k < 512; ++k)
+      split_half(w.fc0_weight[(size_t)o * 512 + k] * gf1[o] * sw, f1h[(size_t)o * 512 + k], f1l[(size_t)o * 512 + k]);
+  }
+  for (int o = 0; o < 256; ++o) {
+    float m = 0.f;
+    for (int k = 0; k < 512; ++k) m = fmaxf(m, fabsf(w.fc3_weight[(size_t)o * 512 + k] * gf2[o]));
+    const float sw = pow2_floor_scale(m, 1024.f);
+    fa2[o] = 1.f / (kFcActScale * sw);
+    for (int k = 0; k < 512; ++k)
+      split_half(w.fc3_weight[(size_t)o * 512 + k] * gf2[o] * sw, f2h[(size_t)o * 512 + k], f2l[(size_t)o * 512 + k]);
+  }
   // device blob
-  const size_t total = 4 * align_up((size_t)512 * K1 * 2, 256) + 8 * 4096 + align_up(f1t.size() * 4, 256) +
+  const size_t total = 2 * 1024 * 1024 + 65536 + 4 * align_up((size_t)512 * K1 * 2, 256) + 8 * 4096 + align_up(f1t.size() * 4, 256) +
                        align_up(f2t.size() * 4, 256) + 8 * 8192 + 65536;
   if (R.blob == nullptr) {
     if (cudaMalloc(&R.blob, total) != cudaSuccess) {
@@ -249,6 +272,12 @@ int pack_regressor(p2p_handle_s* h, Regressor& R, const p2p_regressor_weights_t&
   R.fc.b3 = carve<float>(p, 5);
   R.d_steps1 = carve<KStep>(p, kConv1Steps);
   R.d_steps2 = carve<KStep>(p, kConv2Steps);
+  R.f1_hi = carve<__half>(p, f1h.size());
+  R.f1_lo = carve<__half>(p, f1l.size());
+  R.f2_hi = carve<__half>(p, f2h.size());
+  R.f2_lo = carve<__half>(p, f2l.size());
+  R.fa1 = carve<float>(p, 512);
+  R.fa2 = carve<float>(p, 256);
 #define UP(dst, src, bytes) P2P_CUDA_OK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice))
   UP(R.w1_hi, w1h.data(), w1h.size() * 2);
   UP(R.w1_lo, w1l.data(), w1l.size() * 2);
@@ -266,6 +295,12 @@ int pack_regressor(p2p_handle_s* h, Regressor& R, const p2p_regressor_weights_t&
   UP(R.fc.b3, f3b.data(), 20);
   UP(R.d_steps1, R.steps1, sizeof(R.steps1));
   UP(R.d_steps2, R.steps2, sizeof(R.steps2));
+  UP(R.f1_hi, f1h.data(), f1h.size() * 2);
+  UP(R.f1_lo, f1l.data(), f1l.size() * 2);
+  UP(R.f2_hi, f2h.data(), f2h.size() * 2);
+  UP(R.f2_lo, f2l.data(), f2l.size() * 2);
+  UP(R.fa1, fa1.data(), 2048);
+  UP(R.fa2, fa2.data(), 1024);
 #undef UP
   R.set = true;
   (void)h;
@@ -396,6 +431,7 @@ static int* option_slot(p2p_handle_t h, const char* key) {
   if (!strcmp(key, "profile")) return &h->opt_profile;
   if (!strcmp(key, "mid_band")) return &h->opt_mid_band;
   if (!strcmp(key, "fuse_gather")) return &h->opt_fuse_gather;
+  if (!strcmp(key, "fc_impl")) return &h->opt_fc_impl;
   return nullptr;
 }
 
@@ -673,6 +709,7 @@ namespace {
 
 struct RefineBuffers {
   __half *p_hi, *p_lo, *r_hi, *r_lo, *y_hi, *y_lo;
+  __half *q_hi, *q_lo, *h1_hi, *h1_lo, *h2_hi, *h2_lo;   // tensor-core FC operands, rows padded to 128
   float *pooled, *raw;
   int *rowmap, *d_count;
   int npad;
@@ -774,8 +811,48 @@ int run_regressor(p2p_handle_s* h, Regressor& R, int which, int passes, const Re
     }
   }
   ProfScope ps(h, kb + 3, st);
-  return launch_fc_parse(B.pooled, R.fc, matches_in, is_float, n, h->pf[0].W, h->pf[0].H, h->pf[1].W, h->pf[1].H,
-                         matches_out, probs_out, raw_out, rowmap, d_count, st);
+  if (h->opt_fc_impl == 0 || h->opt_gemm_impl == 1)
+    return launch_fc_parse(B.pooled, R.fc, matches_in, is_float, n, h->pf[0].W, h->pf[0].H, h->pf[1].W, h->pf[1].H,
+                           matches_out, probs_out, raw_out, rowmap, d_count, st);
+  // tensor-core FC: split -> Linear(512,512)+BN+ReLU -> Linear(512,256)+BN+ReLU (3-pass, segmented) -> Linear(256,5)+parse
+  if ((rc = launch_pooled_split(B.pooled, n, B.q_hi, B.q_lo, d_count, st))) return rc;
+  const uint64_t m128 = align_up(n, 128);
+  const uint32_t abx[5] = {64, 1, 1, 1, 128};
+  const uint32_t bbx[2] = {64, 256};
+  for (int layer = 0; layer < 2; ++layer) {
+    UmmaGemmParams p;
+    memset(&p, 0, sizeof(p));
+    const int nout = layer == 0 ? 512 : 256;
+    const uint64_t ad[5] = {512, 1, 1, 1, m128};
+    const uint64_t as[4] = {1024, 1024, 1024, 1024};
+    const uint64_t bd[2] = {512, (uint64_t)nout};
+    const uint64_t bs[1] = {1024};
+    const __half* a_hi = layer == 0 ? B.q_hi : B.h1_hi;
+    const __half* a_lo = layer == 0 ? B.q_lo : B.h1_lo;
+    if ((rc = make_tmap_fp16(&p.a_main_hi, a_hi, 5, ad, as, abx))) return rc;
+    if ((rc = make_tmap_fp16(&p.a_main_lo, a_lo, 5, ad, as, abx))) return rc;
+    if ((rc = make_tmap_fp16(&p.b_hi, layer == 0 ? R.f1_hi : R.f2_hi, 2, bd, bs, bbx))) return rc;
+    if ((rc = make_tmap_fp16(&p.b_lo, layer == 0 ? R.f1_lo : R.f2_lo, 2, bd, bs, bbx))) return rc;
+    p.a_rgb_hi = p.a_main_hi;
+    p.a_rgb_lo = p.a_main_lo;
+    p.nsteps = 8;
+    for (int s2 = 0; s2 < 8; ++s2) p.steps[s2] = KStep{(short)(s2 * 64), 0, 0, 0, 0, 0, s2 * 64};
+    p.m_tiles = (int)(m128 / 128);
+    p.n_tiles = nout / 256;
+    p.a_units_per_tile = 128;
+    p.seg_len = 2;
+    p.d_units = d_count;
+    p.epi.scale = layer == 0 ? R.fa1 : R.fa2;
+    p.epi.bias = layer == 0 ? R.fc.b1 : R.fc.b2;
+    p.epi.y_scale = kFcActScale;
+    p.epi.y_hi = layer == 0 ? B.h1_hi : B.h2_hi;
+    p.epi.y_lo = layer == 0 ? B.h1_lo : B.h2_lo;
+    p.epi.ldc = nout;
+    p.epi.n_patches = n;
+    if ((rc = launch_umma_gemm(p, EPI_FC, 3, sms(h), st))) return rc;
+  }
+  return launch_fc3_parse(B.h2_hi, B.h2_lo, R.fc.w3t, R.fc.b3, matches_in, is_float, n, h->pf[0].W, h->pf[0].H,
+                          h->pf[1].W, h->pf[1].H, matches_out, probs_out, raw_out, rowmap, d_count, st);
 }
 
 }  // namespace
@@ -798,7 +875,9 @@ int p2p_refine(p2p_handle_t h, int which, const void* matches_in, int is_float, 
   const int npad = (int)align_up(n, 2);
   const size_t pbytes = (size_t)npad * kPatchPos * kMainCh * 2, rbytes = (size_t)npad * 4096 * 2,
                ybytes = (size_t)npad * 64 * 512 * 2, qbytes = (size_t)npad * 512 * 4;
-  int rc = h->refine.reserve(2 * (pbytes + rbytes + ybytes) + qbytes + (size_t)n * 24 + (1 << 16));
+  const size_t n128 = align_up(n, 128);
+  int rc = h->refine.reserve(2 * (pbytes + rbytes + ybytes) + qbytes + (size_t)n * 24 + n128 * (512 + 512 + 256) * 4 +
+                             (1 << 16));
   if (rc) return rc;
   Arena& A = h->refine;
   RefineBuffers B;
@@ -810,9 +889,16 @@ int p2p_refine(p2p_handle_t h, int which, const void* matches_in, int is_float, 
   B.y_hi = (__half*)A.take(ybytes);
   B.y_lo = (__half*)A.take(ybytes);
   B.pooled = (float*)A.take(qbytes);
+  B.q_hi = (__half*)A.take(n128 * 512 * 2);
+  B.q_lo = (__half*)A.take(n128 * 512 * 2);
+  B.h1_hi = (__half*)A.take(n128 * 512 * 2);
+  B.h1_lo = (__half*)A.take(n128 * 512 * 2);
+  B.h2_hi = (__half*)A.take(n128 * 256 * 2);
+  B.h2_lo = (__half*)A.take(n128 * 256 * 2);
   B.raw = (float*)A.take((size_t)n * 5 * 4);
   B.rowmap = (int*)A.take((size_t)n * 4 + 16);
-  P2P_REQUIRE(B.p_hi && B.p_lo && B.r_hi && B.r_lo && B.y_hi && B.y_lo && B.pooled && B.raw && B.rowmap,
+  P2P_REQUIRE(B.p_hi && B.p_lo && B.r_hi && B.r_lo && B.y_hi && B.y_lo && B.pooled && B.raw && B.rowmap && B.q_hi &&
+                  B.q_lo && B.h1_hi && B.h1_lo && B.h2_hi && B.h2_lo,
               "scratch carve failed");
   B.d_count = B.rowmap + n;
   if (which == 0) h->last_band_count = band ? B.d_count : nullptr;

@@ -58,6 +58,13 @@ int launch_fc_parse(const float* pooled, const FcWeights& fc, const void* matche
                     int H1, int W2, int H2, float* matches_out, float* probs_out, float* raw_out, const int* rowmap,
                     const int* d_count, cudaStream_t st);
 
+// Tensor-core FC path helpers: pooled fp32 -> fp16 hi/lo A operand; final Linear(256,5) + parse_regressor_out.
+constexpr float kFcActScale = 16.f;
+int launch_pooled_split(const float* pooled, int n, __half* hi, __half* lo, const int* d_count, cudaStream_t st);
+int launch_fc3_parse(const __half* h2_hi, const __half* h2_lo, const float* w3t, const float* b3, const void* matches_in,
+                     int is_float, int N, int W1, int H1, int W2, int H2, float* matches_out, float* probs_out,
+                     float* raw_out, const int* rowmap, const int* d_count, cudaStream_t st);
+
 // One k-step of an implicit GEMM: where the [128 rows x 64 ch] A box starts and which K offset of
 // the K-major weight matrix it multiplies.
 struct KStep {

@@ -187,6 +187,25 @@ __device__ __forceinline__ void epilogue_piece(const UmmaEpilogue& e, int n_patc
       if (lane == i) mine = m;
     }
     if (n < n_patches) atomicMax(reinterpret_cast<unsigned int*>(e.pooled) + (size_t)n * 512 + col0 + lane, mine);
+  } else if (EPI == EPI_FC) {
+    // Linear + folded BatchNorm1d + ReLU; output re-split to fp16 hi/lo as the next layer's A operand
+    const int r = m_tile * 128 + row;
+    if (r < n_patches) {
+      __align__(16) __half h[32];
+      __align__(16) __half l[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float y = fmaxf(fmaf(v[i], __ldg(e.scale + col0 + i), __ldg(e.bias + col0 + i)), 0.f) * e.y_scale;
+        h[i] = __float2half_rn(y);
+        l[i] = __float2half_rn(y - __half2float(h[i]));
+      }
+      const size_t o = (size_t)r * e.ldc + col0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        reinterpret_cast<uint4*>(e.y_hi + o)[q] = reinterpret_cast<const uint4*>(h)[q];
+        reinterpret_cast<uint4*>(e.y_lo + o)[q] = reinterpret_cast<const uint4*>(l)[q];
+      }
+    }
   } else if (EPI == EPI_CORR) {
     // rows/cols are in pooling-window order: 4 rows x 4 cols = one 4D window
     const int lane = threadIdx.x & 31;
@@ -869,6 +888,7 @@ int launch_umma_gemm(const UmmaGemmParams& p, int epi, int passes, int num_sms, 
     case EPI_CONV1: return launch_epi<EPI_CONV1>(p, passes, seg, grid, st);
     case EPI_CONV2: return launch_epi<EPI_CONV2>(p, passes, seg, grid, st);
     case EPI_CORR: return launch_epi<EPI_CORR>(p, passes, seg, grid, st);
+    case EPI_FC: return launch_epi<EPI_FC>(p, passes, seg, grid, st);
   }
   set_last_error("umma gemm: unknown epilogue");
   return -1;

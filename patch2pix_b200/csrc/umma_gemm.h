@@ -6,7 +6,7 @@
 
 namespace p2p {
 
-enum { EPI_PLAIN = 0, EPI_CONV1 = 1, EPI_CONV2 = 2, EPI_CORR = 3 };
+enum { EPI_PLAIN = 0, EPI_CONV1 = 1, EPI_CONV2 = 2, EPI_CORR = 3, EPI_FC = 4 };
 constexpr int kMaxKSteps = 96;
 
 struct UmmaEpilogue {

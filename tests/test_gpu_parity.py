@@ -524,3 +524,27 @@ def test_estimate_matches_helper(seeded_sd):
     assert np.abs(s - fp).max() < 1e-3 and np.array_equal(c, up * cm)
     mc, sc, _ = estimate_matches(net, im1, im2, eval_type='coarse', mutual=False)
     assert mc.shape[1] == 4 and mc.shape[0] == sc.shape[0] > 0
+
+
+def test_fc_tensor_core_vs_cuda_core(nets):
+    """FeatRegressNet.fc on the tensor cores (3-pass, segmented) vs the fp32 CUDA-core FC kernel."""
+    net = nets[1]
+    H, W = 128, 160
+    m = _random_matches(300, H, W, 5, True)
+    f1, f2, _, _ = _feats(net, 9, H, W)
+    out = {}
+    try:
+        net.set_option('mid_band', 0)
+        for impl in (1, 0):
+            net.set_option('fc_impl', impl)
+            with torch.no_grad():
+                mid, midp = net.forward_fine_match(f1, f2, [m.cuda()], 16, 'center', net.regress_mid)
+            torch.cuda.synchronize()
+            out[impl] = (mid[0].cpu(), midp[0].cpu())
+    finally:
+        net.set_option('fc_impl', 1)
+        net.set_option('mid_band', 35)
+    d = (out[1][0] - out[0][0]).abs().max().item()
+    dp = (out[1][1] - out[0][1]).abs().max().item()
+    _report('fc_tc_vs_simt', {'mid_diff_px': d, 'conf_diff': dp})
+    assert d < 1e-4 and dp < 1e-5, (d, dp)
