@@ -408,15 +408,13 @@ __host__ __device__ inline int nc2_pitch(int wB) {
 // One block owns JB (<= 4) consecutive A cells of one A row: the 3 x (JB+2) neighbouring A cells'
 // hidden planes are staged once and every staged plane feeds up to 3 of the JB outputs from the
 // same registers (about 2x the FMAs per shared-memory load of a one-cell block).
-// RPT = B rows per thread (2: fewer, fatter threads; 1: twice the warps per block, which hides the
-// shared-memory load latency this kernel is bound by).
-template <bool VEC, int RPT>
-__global__ void __launch_bounds__(RPT == 1 ? 768 : 384) nc_layer2_kernel(const float* __restrict__ hidden, int hA, int wA, int hB,
+template <bool VEC>
+__global__ void __launch_bounds__(384) nc_layer2_kernel(const float* __restrict__ hidden, int hA, int wA, int hB,
                                                        int wB, int JB, const float* __restrict__ w2p, float b2,
                                                        float* __restrict__ out) {
   extern __shared__ __align__(16) float smem[];
   const int PW = nc2_pitch(wB);                       // [3 unused | left halo | interior | right halo ...]
-  const int PH = hB + 2 + 1;                          // covers RPT*tk+RPT+1
+  const int PH = hB + 2 + 1;                          // covers 2*tk+3
   const int plane = PH * PW;
   float* w2s = smem;                                  // [81][32]
   float* tile = smem + 81 * 32;                       // [2 buffers][4 planes][PH][PW]
@@ -482,12 +480,11 @@ __global__ void __launch_bounds__(RPT == 1 ? 768 : 384) nc_layer2_kernel(const f
     cp_async_commit();
   };
   const int tl = threadIdx.x, tk = threadIdx.y;
-  constexpr int NC = RPT * 4;                         // cells per thread
-  float total[4][NC], acc[4][NC];
+  float total[4][8], acc[4][8];
 #pragma unroll
   for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-    for (int i = 0; i < NC; ++i) { total[jj][i] = 0.f; acc[jj][i] = b2; }
+    for (int i = 0; i < 8; ++i) { total[jj][i] = 0.f; acc[jj][i] = b2; }
   issue(0);
   for (int item = 0; item < nitems; ++item) {
     if (item + 1 < nitems) {
@@ -504,10 +501,10 @@ __global__ void __launch_bounds__(RPT == 1 ? 768 : 384) nc_layer2_kernel(const f
     const float* buf = tile + (item & 1) * 4 * plane;
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {
-      float r[RPT + 2][6];
+      float r[4][6];
 #pragma unroll
-      for (int rr = 0; rr < RPT + 2; ++rr) {
-        const float* p = buf + cc * plane + (RPT * tk + rr) * PW + 4 * tl + kNc2Left - 1;   // B column 4*tl-1
+      for (int rr = 0; rr < 4; ++rr) {
+        const float* p = buf + cc * plane + (2 * tk + rr) * PW + 4 * tl + kNc2Left - 1;   // B column 4*tl-1
         const float4 q = *reinterpret_cast<const float4*>(p + 1);
         r[rr][0] = p[0]; r[rr][1] = q.x; r[rr][2] = q.y; r[rr][3] = q.z; r[rr][4] = q.w; r[rr][5] = p[5];
       }
@@ -522,7 +519,7 @@ __global__ void __launch_bounds__(RPT == 1 ? 768 : 384) nc_layer2_kernel(const f
             for (int e = 0; e < 3; ++e) {
               const float wv = wrow[(d * 3 + e) * 32];
 #pragma unroll
-              for (int kk = 0; kk < RPT; ++kk)
+              for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
                 for (int ll = 0; ll < 4; ++ll)
                   acc[jj][kk * 4 + ll] = fmaf(r[kk + d][ll + e], wv, acc[jj][kk * 4 + ll]);
@@ -534,7 +531,7 @@ __global__ void __launch_bounds__(RPT == 1 ? 768 : 384) nc_layer2_kernel(const f
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-        for (int i = 0; i < NC; ++i) { total[jj][i] += fmaxf(acc[jj][i], 0.f); acc[jj][i] = b2; }
+        for (int i = 0; i < 8; ++i) { total[jj][i] += fmaxf(acc[jj][i], 0.f); acc[jj][i] = b2; }
     }
     __syncthreads();             // everyone is done with this buffer before it is refilled
   }
@@ -543,10 +540,10 @@ __global__ void __launch_bounds__(RPT == 1 ? 768 : 384) nc_layer2_kernel(const f
     if (jj >= JB || j0 + jj >= wA) continue;
     const size_t a = (size_t)ia * wA + j0 + jj;
 #pragma unroll
-    for (int kk = 0; kk < RPT; ++kk)
+    for (int kk = 0; kk < 2; ++kk)
 #pragma unroll
       for (int ll = 0; ll < 4; ++ll) {
-        const int k = RPT * tk + kk, l = 4 * tl + ll;
+        const int k = 2 * tk + kk, l = 4 * tl + ll;
         if (k < hB && l < wB) out[a * nB + k * wB + l] = total[jj][kk * 4 + ll];
       }
   }
@@ -574,10 +571,8 @@ int launch_neigh_consensus(const float* x, int hA, int wA, int hB, int wB, const
     P2P_LAUNCH_OK();
   }
   {
-    // one B row per thread while the block stays <= 768 threads (twice the warps to hide LDS latency), else two
-    const int rpt = cdiv(wB, 4) * hB <= 768 ? 1 : 2;
-    dim3 block(cdiv(wB, 4), cdiv(hB, rpt));
-    P2P_REQUIRE(block.x * block.y <= (rpt == 1 ? 768u : 384u), "NC layer 2: pooled B grid too large (hB*wB <= 3072)");
+    dim3 block(cdiv(wB, 4), cdiv(hB, 2));
+    P2P_REQUIRE(block.x * block.y <= 384, "NC layer 2: pooled B grid too large (hB*wB <= 3072)");
     P2P_REQUIRE(cdiv(hB * wB, (int)(block.x * block.y)) <= kNc2MaxCopies, "NC layer 2: copy slots exhausted");
     P2P_REQUIRE(wB % 4 != 0 || cdiv(hB * wB / 4, (int)(block.x * block.y)) <= 3, "NC layer 2: vector copy slots exhausted");
     const int PW = nc2_pitch(wB), PH = hB + 3;
@@ -598,18 +593,15 @@ int launch_neigh_consensus(const float* x, int hA, int wA, int hB, int wB, const
       }
     }
     const int grid = hA * cdiv(wA, JB);
-    auto launch = [&](auto kern) -> int {
-      P2P_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      P2P_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      kern<<<grid, block, smem, st>>>(hidden, hA, wA, hB, wB, JB, w2p, b2, out);
-      return 0;
-    };
-    int rc;
-    if (wB % 4 == 0)
-      rc = rpt == 1 ? launch(nc_layer2_kernel<true, 1>) : launch(nc_layer2_kernel<true, 2>);
-    else
-      rc = rpt == 1 ? launch(nc_layer2_kernel<false, 1>) : launch(nc_layer2_kernel<false, 2>);
-    if (rc) return rc;
+    if (wB % 4 == 0) {
+      P2P_CUDA_OK(cudaFuncSetAttribute(nc_layer2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      P2P_CUDA_OK(cudaFuncSetAttribute(nc_layer2_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      nc_layer2_kernel<true><<<grid, block, smem, st>>>(hidden, hA, wA, hB, wB, JB, w2p, b2, out);
+    } else {
+      P2P_CUDA_OK(cudaFuncSetAttribute(nc_layer2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      P2P_CUDA_OK(cudaFuncSetAttribute(nc_layer2_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      nc_layer2_kernel<false><<<grid, block, smem, st>>>(hidden, hA, wA, hB, wB, JB, w2p, b2, out);
+    }
     P2P_LAUNCH_OK();
   }
   return 0;
