@@ -49,7 +49,6 @@ def parse():
     ap.add_argument('--mid-band', type=int, default=None)
     ap.add_argument('--fuse-gather', type=int, default=None)
     ap.add_argument('--backbone-fp32', action='store_true', help='keep cuDNN TF32 off in the e2e backbone')
-    ap.add_argument('--backbone-nchw', action='store_true', help='do not switch the e2e backbone to channels_last')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-sample-patches', type=int, default=200)
     return ap.parse_args()
@@ -337,7 +336,7 @@ def run_ours(args):
         # backbone in PyTorch's default cuDNN mode (TF32 convolutions allowed, as the reference would run)
         torch.backends.cudnn.allow_tf32 = not args.backbone_fp32
         torch.backends.cudnn.benchmark = True
-        net.enable_backbone_graphs(H, W, instances=2, channels_last=not args.backbone_nchw)
+        net.enable_backbone_graphs(H, W, instances=2)
         host_outs = [torch.empty(n_patches, 5).pin_memory() for _ in range(2)]
         e2e_loop(0, max(min(Wm, 3), 1), host_outs)
 
@@ -410,7 +409,7 @@ def run_ours(args):
                        'options': opts},
             'e2e': {'value': pairs / (ms_e2e / 1e3), 'unit': 'pairs/s', 'ms_per_step': ms_e2e / K,
                     'h2d_bytes_per_step': 2 * 3 * H * W * 4, 'd2h_bytes_per_step': n_patches * 5 * 4,
-                    'path': 'pinned host images -> H2D -> cuDNN ResNet34 pyramid, both images as one batch, ' + ('NCHW' if args.backbone_nchw else 'channels_last') + ', CUDA graph (' + ('fp32' if args.backbone_fp32 else 'TF32 convs, PyTorch default') + ') -> hot path -> D2H matches+scores'},
+                    'path': 'pinned host images -> H2D -> cuDNN ResNet34 pyramid, both images as one batch, CUDA graph (' + ('fp32' if args.backbone_fp32 else 'TF32 convs, PyTorch default') + ') -> hot path -> D2H matches+scores'},
             'gpu_launches': launches, 'roofline': roofline, 'kernels': kern, 'clocks': clocks, 'cpu_baseline': cpu,
         }
         print(json.dumps(line), flush=True)

@@ -512,26 +512,21 @@ class Patch2PixB200(nn.Module):
         b = im1.shape[0]
         return [f[:b] for f in feats], [f[b:] for f in feats]
 
-    def enable_backbone_graphs(self, height, width, instances=2, channels_last=True):
-        """Capture the (launch-bound) backbone for a fixed image size into CUDA graphs.  With
-        `channels_last` cuDNN runs its NHWC tensor-core kernels; the pyramid is converted back to the
-        contiguous NCHW tensors the hot path (and the reference API) expects inside the graph."""
+    def enable_backbone_graphs(self, height, width, instances=2):
+        """Capture the (launch-bound) backbone for a fixed image size into CUDA graphs."""
         shape = (1, 3, height, width)
         insts = []
-        fmt = torch.channels_last if channels_last else torch.contiguous_format
         with torch.no_grad(), torch.cuda.device(self.device):
-            if channels_last:
-                self.extract.to(memory_format=torch.channels_last)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(instances):
-                    inp = torch.zeros(2, 3, height, width, device=self.device).contiguous(memory_format=fmt)
+                    inp = torch.zeros(2, 3, height, width, device=self.device)
                     for _ in range(3):
                         self.extract.forward_all(inp, [], early_feat=True)
                     graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(graph, stream=side):
-                        out = [f.contiguous() for f in self.extract.forward_all(inp, [], early_feat=True)]
+                        out = self.extract.forward_all(inp, [], early_feat=True)
                     insts.append({'inp': inp, 'graph': graph, 'out': out})
             torch.cuda.current_stream().wait_stream(side)
             for inst in insts:
