@@ -396,87 +396,6 @@ __device__ __forceinline__ void cp_async16(float* dst_smem, const float* src) {
                : "memory");
 }
 
-// layer 1, second version: FMA-bound instead of shared-memory-bound.  128 threads = 4 warps, one
-// 8-channel group per warp (so the weight reads of a warp are two broadcast LDS.128 per tap instead of
-// eight); a lane owns 8 consecutive B cells of one B row: 64 accumulators, 10 activations per row and tap
-// row (2 x LDS.128 + LDS.64).  grid (ceil(hB/R), nA) with R = 32 / ceil(wB/8) B rows per block.
-__global__ void __launch_bounds__(128, 4) nc_layer1_v2_kernel(const float* __restrict__ x, int hA, int wA, int hB, int wB,
-                                                            int R, int TL, const float* __restrict__ w1p,
-                                                            const float* __restrict__ b1p, float* __restrict__ hidden) {
-  extern __shared__ __align__(16) float smem[];
-  const int PW = 8 * TL + 4;             // halo row pitch: multiple of 4, covers column 8*TL+1
-  float* w1s = smem;                     // [81][32]
-  float* xs = smem + 81 * 32;            // [9][R+2][PW]
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int a = blockIdx.y, ia = a / wA, ja = a - ia * wA;
-  const int k0 = blockIdx.x * R;
-  const int nB = hB * wB;
-  for (int i = tid; i < 81 * 32; i += 128) w1s[i] = w1p[i];
-  for (int row = wid; row < 9 * (R + 2); row += 4) {          // one warp per halo row: no per-element div/mod
-    const int ab = row / (R + 2), kk = row - ab * (R + 2);
-    const int si = ia + ab / 3 - 1, sj = ja + ab % 3 - 1, sk = k0 + kk - 1;
-    const bool rv = si >= 0 && si < hA && sj >= 0 && sj < wA && sk >= 0 && sk < hB;
-    const float* src = x + (size_t)(si * wA + sj) * nB + sk * wB;
-    for (int ll = lane; ll < PW; ll += 32) {
-      const int sl = ll - 1;
-      xs[row * PW + ll] = (rv && sl >= 0 && sl < wB) ? __ldg(src + sl) : 0.f;
-    }
-  }
-  __syncthreads();
-  const int tk = lane / TL, tl = lane - tk * TL;
-  const bool active = tk < R;
-  const int c0 = wid * 8;
-  float acc[8][8];                       // [cell][channel]
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const float b = b1p[c0 + c];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i][c] = b;
-  }
-  if (active) {
-    for (int ab = 0; ab < 9; ++ab) {
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const float* row = xs + (ab * (R + 2) + tk + d) * PW + 8 * tl;
-        const float4 q0 = *reinterpret_cast<const float4*>(row);
-        const float4 q1 = *reinterpret_cast<const float4*>(row + 4);
-        const float2 q2 = *reinterpret_cast<const float2*>(row + 8);
-        const float v[10] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
-#pragma unroll
-        for (int e = 0; e < 3; ++e) {
-          const float4 wa = *reinterpret_cast<const float4*>(w1s + (ab * 9 + d * 3 + e) * 32 + c0);
-          const float4 wb = *reinterpret_cast<const float4*>(w1s + (ab * 9 + d * 3 + e) * 32 + c0 + 4);
-          const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int c = 0; c < 8; ++c) acc[i][c] = fmaf(v[i + e], wv[c], acc[i][c]);
-        }
-      }
-    }
-    const int k = k0 + tk;
-    if (k < hB) {
-      const int l0 = 8 * tl;
-      float* hp = hidden + ((size_t)a * 32 + c0) * nB + k * wB + l0;
-      const bool vec = (wB % 4 == 0) && (l0 + 8 <= wB);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float* dst = hp + (size_t)c * nB;
-        if (vec) {
-          *reinterpret_cast<float4*>(dst) = make_float4(fmaxf(acc[0][c], 0.f), fmaxf(acc[1][c], 0.f),
-                                                         fmaxf(acc[2][c], 0.f), fmaxf(acc[3][c], 0.f));
-          *reinterpret_cast<float4*>(dst + 4) = make_float4(fmaxf(acc[4][c], 0.f), fmaxf(acc[5][c], 0.f),
-                                                             fmaxf(acc[6][c], 0.f), fmaxf(acc[7][c], 0.f));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (l0 + i < wB) dst[i] = fmaxf(acc[i][c], 0.f);
-        }
-      }
-    }
-  }
-}
-
 // Row pitch of the staged planes: a multiple of 4 floats with 2*pitch = 8 (mod 32), so that the
 // float4 reads of consecutive thread rows (2 plane rows apart) fall into disjoint banks.
 __host__ __device__ inline int nc2_pitch(int wB) {
@@ -638,15 +557,7 @@ int launch_neigh_consensus(const float* x, int hA, int wA, int hB, int wB, const
     P2P_REQUIRE(block.x * block.y <= 512, "NC layer 1: pooled width too large (wB <= 128)");
     dim3 grid(cdiv(hB, 8), nA);
     const size_t smem = sizeof(float) * (81 * 32 + 9 * 10 * (wB + 4));
-    const int TL = cdiv(wB, 8);
-    if (TL <= 16) {                   // second version: one 8-channel group per warp, 8 cells per lane
-      const int R = 32 / TL;
-      dim3 grid2(cdiv(hB, R), nA);
-      const size_t smem2 = sizeof(float) * (81 * 32 + 9 * (R + 2) * (8 * TL + 4));
-      P2P_CUDA_OK(cudaFuncSetAttribute(nc_layer1_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-      P2P_CUDA_OK(cudaFuncSetAttribute(nc_layer1_v2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      nc_layer1_v2_kernel<<<grid2, 128, smem2, st>>>(x, hA, wA, hB, wB, R, TL, w1p, b1p, hidden);
-    } else if (block.x * block.y <= 160) {   // small B grids: cap registers so that 4 blocks share an SM
+    if (block.x * block.y <= 160) {   // small B grids: cap registers so that 4 blocks share an SM
       auto k = nc_layer1_kernel<160, 4>;
       P2P_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       P2P_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
