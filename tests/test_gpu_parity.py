@@ -548,3 +548,29 @@ def test_fc_tensor_core_vs_cuda_core(nets):
     dp = (out[1][1] - out[0][1]).abs().max().item()
     _report('fc_tc_vs_simt', {'mid_diff_px': d, 'conf_diff': dp})
     assert d < 1e-4 and dp < 1e-5, (d, dp)
+
+
+def test_batched_inputs(nets, seeded_sd):
+    """The reference API is batched (b > 1 in forward_coarse_match / cal_coarse_matches, lists in
+    forward_fine_match); the CUDA path loops over batch items and must give per-item identical results."""
+    from oracle import p2p_oracle as O
+    from patch2pix_b200.model import filter_coarse
+    net = nets[1]
+    fa = _feats(net, 3, 96, 128)
+    fb = _feats(net, 4, 96, 128)
+    f1 = [torch.cat([x, y], 0) for x, y in zip(fa[0], fb[0])]
+    f2 = [torch.cat([x, y], 0) for x, y in zip(fa[1], fb[1])]
+    with torch.no_grad():
+        corr4d, delta4d = net.forward_coarse_match(f1[-1], f2[-1], ksize=2)
+        assert corr4d.shape[0] == 2 and delta4d[0].shape[0] == 2
+        cm, sc = net.cal_coarse_matches(corr4d, delta4d, ksize=2, upsample=net.upsample, center=True)
+        fm, fs = filter_coarse(cm, sc, 0.0, True)
+        assert len(fm) == 2
+        mid, midp = net.forward_fine_match(f1, f2, fm, 16, 'center', net.regress_mid)
+        fine, finep = net.forward_fine_match(f1, f2, mid, 16, 'center', net.regress_fine)
+        torch.cuda.synchronize()
+        for i, (c1, c2) in enumerate(((fa[2], fa[3]), (fb[2], fb[3]))):
+            o_fine, o_fp, o_cm = O.hot_path_from_feats(c1, c2, seeded_sd, 2, 0.0, True)
+            assert torch.equal(fm[i].cpu(), o_cm[0])
+            assert (fine[i].cpu().reshape(-1, 4) - o_fine[0].reshape(-1, 4)).abs().max() < 0.5
+            assert (finep[i].cpu().reshape(-1) - o_fp[0].reshape(-1)).abs().max() < 1e-3
