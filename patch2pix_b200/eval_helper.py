@@ -29,6 +29,31 @@ def load_model(state_dict, regressor_config=None, device='cuda:0', method='patch
     return Patch2PixB200(config)
 
 
+def load_checkpoint(ckpt_path, device='cuda:0', method='patch2pix', lprint=print):
+    """utils/eval/model_helper.py:28-62 + utils/common/setup_helper.py:25-30 including the file I/O.
+
+    Released checkpoints are pickled dicts {'backbone', 'feat_idx', 'state_dict', 'regressor_config': Namespace,
+    ['last_epoch']}; torch >= 2.6 refuses the Namespace under `weights_only=True`, so the file is read with
+    `weights_only=False` (SURVEY.md s8c shim 3) onto the CPU -- `pack_weights` does the one upload. An 'nc'
+    checkpoint may be a bare state_dict (:54-57). Only the released architecture is accepted."""
+    ckpt = torch.load(ckpt_path, map_location='cpu', weights_only=False)
+    lprint('\nLoad model method:{} '.format(method))
+    if 'patch2pix' in method:
+        if ckpt.get('backbone', 'ResNet34') != 'ResNet34' or list(ckpt.get('feat_idx', [0, 1, 2, 3])) != [0, 1, 2, 3]:
+            raise RuntimeError('only the released ResNet34 / feat_idx [0,1,2,3] configuration is supported, got '
+                               f"{ckpt.get('backbone')} / {ckpt.get('feat_idx')}")
+        if 'last_epoch' in ckpt:
+            lprint(f"Ckpt:{ckpt_path} epochs:{ckpt['last_epoch'] + 1}")
+        else:
+            lprint(f'Ckpt:{ckpt_path}')
+        return load_model(ckpt['state_dict'], ckpt.get('regressor_config'), device=device, method=method)
+    if 'nc' in method:
+        sd = ckpt['state_dict'] if isinstance(ckpt, dict) and 'state_dict' in ckpt else ckpt
+        lprint('Load pretrained weights: {}'.format(ckpt_path))
+        return load_model(sd, None, device=device, method=method)
+    raise ValueError('Wrong method name.')
+
+
 def estimate_matches(net, im1, im2, scale1=(1.0, 1.0), scale2=(1.0, 1.0), ksize=2, ncn_thres=0.0, mutual=True,
                      io_thres=0.25, eval_type='fine'):
     """utils/eval/model_helper.py:64-109 on image tensors -> (matches, scores, coarse_matches) numpy arrays."""

@@ -127,3 +127,29 @@ def test_bench_reference_arm_line():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line['impl'] == 'reference' and line['value'] > 0 and line['cpu_baseline']['kind'] == 'port'
     assert line['e2e']['h2d_bytes_per_step'] == 0 and line['unit'] == 'pairs/s'
+
+
+def test_load_checkpoint_parses_the_released_file_format(tmp_path, seeded_sd):
+    """utils/eval/model_helper.py:28-62: released checkpoints are pickled dicts holding a Namespace; the loader
+    must read them (weights_only=False), reject other architectures, and -- with no GPU here -- stop at the
+    constructor's 'no CPU fallback' error rather than silently building a CPU model."""
+    from patch2pix_b200.eval_helper import load_checkpoint
+    rc = Namespace(conv_dims=[512, 512], conv_kers=[3, 3], conv_strs=[2, 1], fc_dims=[512, 256], feat_comb='pre',
+                   psize=[16, 16], pshift=8, panc=8, shared=False)
+    good = tmp_path / 'p2p.pth'
+    torch.save({'backbone': 'ResNet34', 'feat_idx': [0, 1, 2, 3], 'state_dict': seeded_sd, 'regressor_config': rc,
+                'last_epoch': 24}, good)
+    lines = []
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        load_checkpoint(str(good), device='cpu', lprint=lines.append)
+    assert any('epochs:25' in ln for ln in lines)
+    bad = tmp_path / 'r50.pth'
+    torch.save({'backbone': 'ResNet50', 'feat_idx': [0, 1, 2, 3], 'state_dict': {}, 'regressor_config': rc}, bad)
+    with pytest.raises(RuntimeError, match='released ResNet34'):
+        load_checkpoint(str(bad), device='cpu', lprint=lines.append)
+    nc = tmp_path / 'nc.pth'
+    torch.save({k: v for k, v in seeded_sd.items() if not k.startswith('regress')}, nc)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        load_checkpoint(str(nc), device='cpu', method='nc', lprint=lines.append)
+    with pytest.raises(ValueError):
+        load_checkpoint(str(nc), device='cpu', method='other', lprint=lines.append)

@@ -574,3 +574,32 @@ def test_batched_inputs(nets, seeded_sd):
             assert torch.equal(fm[i].cpu(), o_cm[0])
             assert (fine[i].cpu().reshape(-1, 4) - o_fine[0].reshape(-1, 4)).abs().max() < 0.5
             assert (finep[i].cpu().reshape(-1) - o_fp[0].reshape(-1)).abs().max() < 1e-3
+
+
+def test_load_checkpoint_file(tmp_path, nets, seeded_sd):
+    """A checkpoint file in the released format (model_helper.py:28-62) gives the same network as the in-memory
+    state_dict: panc is forced to 1 and predict_fine is bit-identical to a directly constructed model."""
+    from argparse import Namespace
+    from patch2pix_b200.eval_helper import load_checkpoint, load_model
+    from patch2pix_b200.synth import synthetic_pair
+    rc = Namespace(conv_dims=[512, 512], conv_kers=[3, 3], conv_strs=[2, 1], fc_dims=[512, 256], feat_comb='pre',
+                   psize=[16, 16], pshift=8, panc=8, shared=False)
+    path = tmp_path / 'p2p.pth'
+    torch.save({'backbone': 'ResNet34', 'feat_idx': [0, 1, 2, 3], 'state_dict': seeded_sd, 'regressor_config': rc}, path)
+    net_f = load_checkpoint(str(path), lprint=lambda s: None)
+    net_m = load_model(seeded_sd)
+    assert net_f.panc == 1
+    im1, im2 = synthetic_pair(2, 96, 128)
+    with torch.no_grad():
+        a = net_f.predict_fine(im1.cuda(), im2.cuda(), ksize=2)
+        b = net_m.predict_fine(im1.cuda(), im2.cuda(), ksize=2)
+    torch.cuda.synchronize()
+    for x, y in zip(a, b):
+        assert torch.equal(x[0], y[0])
+    nc_path = tmp_path / 'nc.pth'
+    torch.save({k: v for k, v in seeded_sd.items() if not k.startswith('regress')}, nc_path)
+    net_nc = load_checkpoint(str(nc_path), method='nc', lprint=lambda s: None)
+    with torch.no_grad():
+        cm, sc = net_nc.predict_coarse(im1.cuda(), im2.cuda(), ksize=2)
+        cm2, sc2 = net_m.predict_coarse(im1.cuda(), im2.cuda(), ksize=2)
+    assert torch.equal(cm[0], cm2[0]) and torch.equal(sc[0], sc2[0])
