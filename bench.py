@@ -48,6 +48,7 @@ def parse():
     ap.add_argument('--seg-len', type=int, default=None)
     ap.add_argument('--mid-band', type=int, default=None)
     ap.add_argument('--fuse-gather', type=int, default=None)
+    ap.add_argument('--gemm-pair', type=int, default=None, help='bitmask of GEMM launches on the CTA-pair kernel')
     ap.add_argument('--backbone-fp32', action='store_true', help='keep cuDNN TF32 off in the e2e backbone')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-sample-patches', type=int, default=200)
@@ -228,10 +229,12 @@ def run_ours(args):
     cfg.weights_dict = make_seeded_state_dict(0)
     net = Patch2PixB200(cfg)
     for key, v in (('mid_passes', args.mid_passes), ('fine_passes', args.fine_passes), ('corr_passes', args.corr_passes),
-                   ('seg_len', args.seg_len), ('mid_band', args.mid_band), ('fuse_gather', args.fuse_gather)):
+                   ('seg_len', args.seg_len), ('mid_band', args.mid_band), ('fuse_gather', args.fuse_gather),
+                   ('gemm_pair', args.gemm_pair)):
         if v is not None:
             net.set_option(key, v)
-    opts = {k: net._handle.get_option(k) for k in ('mid_passes', 'fine_passes', 'corr_passes', 'seg_len', 'mid_band', 'fuse_gather')}
+    opts = {k: net._handle.get_option(k) for k in ('mid_passes', 'fine_passes', 'corr_passes', 'seg_len', 'mid_band', 'fuse_gather',
+                                                    'gemm_pair')}
 
     # pair indices: rank 0 decides, NCCL broadcasts (the "scatter pair indices" step)
     total_steps = K + Wm

@@ -63,6 +63,9 @@ struct p2p_handle_s {
   int num_sms = 148;
   int opt_mid_passes = 3, opt_fine_passes = 1, opt_corr_passes = 3, opt_seg_len = 3, opt_gemm_impl = 0, opt_num_sms = 0;
   int opt_mid_band = 35;  // thousandths of a pixel; 0 = pure 3-pass mid stage
+  int opt_gemm_pair = 35;   // bitmask of launches that use the CTA-pair (cta_group::2) GEMM kernel:
+                            // 1: 1-pass convs, 2: 3-pass convs, 4: FC, 8: correlation, 16: p2p_test_gemm,
+                            // 32: fused-gather conv1
   int opt_fc_impl = 1;      // 1: the two big Linear layers on the tensor cores (3-pass); 0: CUDA-core FC kernel
   int opt_fuse_gather = 1;  // 1: 1-pass conv1 gathers its A tiles in producer warps (128x512 tiles, lookup tables; no patch
                             // tensor in HBM); 2: first-generation fused kernel (128x256 tiles, producer-bound); 0: gather + TMA
@@ -432,6 +435,7 @@ static int* option_slot(p2p_handle_t h, const char* key) {
   if (!strcmp(key, "mid_band")) return &h->opt_mid_band;
   if (!strcmp(key, "fuse_gather")) return &h->opt_fuse_gather;
   if (!strcmp(key, "fc_impl")) return &h->opt_fc_impl;
+  if (!strcmp(key, "gemm_pair")) return &h->opt_gemm_pair;
   return nullptr;
 }
 
@@ -502,7 +506,8 @@ static int corr_umma(p2p_handle_s* h, const __half* a_hi, const __half* a_lo, co
   const uint32_t ab[5] = {64, 1, 1, 1, 128};
   const uint64_t bd[2] = {(uint64_t)C, (uint64_t)n2pad};
   const uint64_t bs[1] = {(uint64_t)C * 2};
-  const uint32_t bb[2] = {64, 256};
+  p.pair = (h->opt_gemm_pair & 8) ? 1 : 0;
+  const uint32_t bb[2] = {64, p.pair ? 128u : 256u};
   int rc;
   if ((rc = make_tmap_fp16(&p.a_main_hi, a_hi, 5, ad, as, ab))) return rc;
   if ((rc = make_tmap_fp16(&p.b_hi, b_hi, 2, bd, bs, bb))) return rc;
@@ -746,7 +751,10 @@ int run_regressor(p2p_handle_s* h, Regressor& R, int which, int passes, const Re
     UmmaGemmParams p;
     memset(&p, 0, sizeof(p));
     const uint32_t abox[5] = {64, 8, 8, 1, 2};
-    const uint32_t bbox[2] = {64, 256};
+    const int pair = fused ? ((h->opt_gemm_pair & 32) && h->opt_fuse_gather == 1 ? 1 : 0)      // 32: fused conv1
+                           : ((h->opt_gemm_pair & (lo ? 2 : 1)) ? 1 : 0);
+    const int pair2 = (h->opt_gemm_pair & (lo ? 2 : 1)) ? 1 : 0;       // conv2 never runs fused
+    uint32_t bbox[2] = {64, pair ? 128u : 256u};
     const uint64_t npad = (uint64_t)B.npad;
     {  // conv1
       const uint64_t ad[5] = {512, 8, 8, 4, npad};
@@ -761,6 +769,7 @@ int run_regressor(p2p_handle_s* h, Regressor& R, int which, int passes, const Re
       if ((rc = make_tmap_fp16(&p.a_main_lo, lo ? B.p_lo : B.p_hi, 5, ad, as, abox))) return rc;
       if ((rc = make_tmap_fp16(&p.a_rgb_lo, lo ? B.r_lo : B.r_hi, 5, rd, rs, abox))) return rc;
       if ((rc = make_tmap_fp16(&p.b_lo, R.w1_lo, 2, bd, bs, bbox))) return rc;
+      p.pair = pair;
       p.nsteps = kConv1Steps;
       memcpy(p.steps, R.steps1, sizeof(R.steps1));
       p.m_tiles = (n + 1) / 2;
@@ -794,6 +803,8 @@ int run_regressor(p2p_handle_s* h, Regressor& R, int which, int passes, const Re
       const uint64_t as[4] = {1024, 8192, 65536, 65536};
       const uint64_t bd[2] = {(uint64_t)kConv2Steps * 64, 512};
       const uint64_t bs[1] = {(uint64_t)kConv2Steps * 64 * 2};
+      p.pair = pair2;
+      bbox[1] = pair2 ? 128u : 256u;
       if ((rc = make_tmap_fp16(&p.a_main_hi, B.y_hi, 5, ad, as, abox))) return rc;
       if ((rc = make_tmap_fp16(&p.a_main_lo, lo ? B.y_lo : B.y_hi, 5, ad, as, abox))) return rc;
       if ((rc = make_tmap_fp16(&p.b_hi, R.w2_hi, 2, bd, bs, bbox))) return rc;
@@ -818,10 +829,11 @@ int run_regressor(p2p_handle_s* h, Regressor& R, int which, int passes, const Re
   if ((rc = launch_pooled_split(B.pooled, n, B.q_hi, B.q_lo, d_count, st))) return rc;
   const uint64_t m128 = align_up(n, 128);
   const uint32_t abx[5] = {64, 1, 1, 1, 128};
-  const uint32_t bbx[2] = {64, 256};
+  const uint32_t bbx[2] = {64, (h->opt_gemm_pair & 4) ? 128u : 256u};
   for (int layer = 0; layer < 2; ++layer) {
     UmmaGemmParams p;
     memset(&p, 0, sizeof(p));
+    p.pair = (h->opt_gemm_pair & 4) ? 1 : 0;
     const int nout = layer == 0 ? 512 : 256;
     const uint64_t ad[5] = {512, 1, 1, 1, m128};
     const uint64_t as[4] = {1024, 1024, 1024, 1024};
@@ -944,7 +956,8 @@ int p2p_test_gemm(p2p_handle_t h, const float* a, const float* b, float* c, int 
   const uint32_t abx[5] = {64, 1, 1, 1, 128};
   const uint64_t bd[2] = {(uint64_t)K, (uint64_t)npad};
   const uint64_t bs[1] = {(uint64_t)K * 2};
-  const uint32_t bbx[2] = {64, 256};
+  p.pair = (h->opt_gemm_pair & 16) ? 1 : 0;
+  const uint32_t bbx[2] = {64, p.pair ? 128u : 256u};
   if ((rc = make_tmap_fp16(&p.a_main_hi, a_hi, 5, ad, as, abx))) return rc;
   if ((rc = make_tmap_fp16(&p.a_main_lo, a_lo, 5, ad, as, abx))) return rc;
   if ((rc = make_tmap_fp16(&p.b_hi, b_hi, 2, bd, bs, bbx))) return rc;

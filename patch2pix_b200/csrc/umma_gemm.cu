@@ -81,6 +81,63 @@ __device__ __forceinline__ void tma_load_5d(const CUtensorMap* m, uint64_t* bar,
       : "memory");
 }
 
+// ---- CTA-pair (cta_group::2) variants: two CTAs of a cluster drive one M=256 MMA; the barrier that
+// collects TMA bytes / epilogue arrivals lives in the leader (cluster rank 0) CTA, addressed by clearing
+// the rank bit of the CTA-local shared address.
+constexpr uint32_t kLeaderMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kLeaderMask) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kLeaderMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                                 int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6, %7}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kLeaderMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -254,13 +311,18 @@ __device__ __forceinline__ int fg_clamp(int v, int ds, int full) {   // ((x+dx)/
 // FUSED (conv1, 1-pass): warps 12..15 are A-operand producers that gather, normalise and convert the
 // patch windows straight into the swizzled shared-memory tile (select_local_patch_feats + patch
 // L2Normalize, networks/utils.py:4-36, networks/patch2pix.py:173-178); TMA then only streams the weights.
-template <int PASSES, bool SEGMENTED, int EPI, bool FUSED>
+// PAIR: two CTAs of a cluster (one TPC) share every tile step through tcgen05.mma.cta_group::2 -- an M=256
+// (2 x 128 rows) x N=256 instruction whose B operand is split between the two CTAs' shared memories, so each
+// SM ingests 16 KB A + 16 KB B per k-step instead of 16 + 32 and the ring holds 6 (3 for 3-pass) stages.
+template <int PASSES, bool SEGMENTED, int EPI, bool FUSED, bool PAIR>
 __global__ void __launch_bounds__(FUSED ? 512 : 384, 1) umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p) {
   static_assert(!FUSED || (PASSES == 1 && !SEGMENTED && EPI == EPI_CONV1), "fused gather: conv1, 1-pass only");
-  constexpr int STAGES = (PASSES == 3) ? 2 : 4;
+  static_assert(!(FUSED && PAIR), "the fused-gather variant is single-CTA");
+  constexpr int BT = PAIR ? kBTile / 2 : kBTile;      // B rows held by this CTA: 128 of the 256 when paired
+  constexpr int STAGES = PAIR ? ((PASSES == 3) ? 3 : 6) : ((PASSES == 3) ? 2 : 4);
   constexpr int NOP = (PASSES == 3) ? 2 : 1;
-  constexpr int STAGE_BYTES = NOP * (kATile + kBTile);
-  constexpr uint32_t IDESC = make_idesc_f16(128, 256);
+  constexpr int STAGE_BYTES = NOP * (kATile + BT);
+  constexpr uint32_t IDESC = make_idesc_f16(PAIR ? 256 : 128, 256);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -280,7 +342,11 @@ __global__ void __launch_bounds__(FUSED ? 512 : 384, 1) umma_gemm_kernel(const _
     n_units = __ldg(p.d_units);
     m_tiles = (n_units + p.a_units_per_tile - 1) / p.a_units_per_tile;
   }
-  const int total_tiles = m_tiles * p.n_tiles;
+  // paired: a "tile" is two consecutive 128-row m-tiles (one per CTA of the cluster) x one 256-column n-tile
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int cta0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int ctas = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int total_tiles = (PAIR ? (m_tiles + 1) / 2 : m_tiles) * p.n_tiles;
   const int nsteps = p.nsteps;
   const int seg_len = SEGMENTED ? p.seg_len : nsteps;
   const int nseg = (nsteps + seg_len - 1) / seg_len;
@@ -300,13 +366,17 @@ __global__ void __launch_bounds__(FUSED ? 512 : 384, 1) umma_gemm_kernel(const _
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], FUSED ? 4 : 8);
+      mbar_init(&tempty_bar[i], FUSED ? 4 : (PAIR ? 16 : 8));   // paired: the epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_pair(&tmem_base_smem, 512);
+    else tmem_alloc(&tmem_base_smem, 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();      // the peer's barriers must exist before any remote arrive / TMA completion
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
@@ -316,8 +386,9 @@ __global__ void __launch_bounds__(FUSED ? 512 : 384, 1) umma_gemm_kernel(const _
     // ===================== TMA producer =====================
     if (lane == 0) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      for (int tile = cta0; tile < total_tiles; tile += ctas) {
+        const int mt = tile / p.n_tiles, n_tile = tile - mt * p.n_tiles;
+        const int m_tile = PAIR ? mt * 2 + rank : mt;     // past the last m-tile (odd count): TMA zero-fills
         for (int ks = 0; ks < nsteps; ++ks, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -329,8 +400,23 @@ __global__ void __launch_bounds__(FUSED ? 512 : 384, 1) umma_gemm_kernel(const _
             tma_load_2d(&p.b_hi, &full_bar[s], st + kATile, k.bk, n_tile * 256);
             continue;
           }
-          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
           const int a4 = m_tile * p.a_units_per_tile;
+          if (PAIR) {
+            // both CTAs' bytes complete on the leader's barrier; its single arrival carries the whole count
+            if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+            const int brow = n_tile * 256 + rank * 128;
+            if (k.kind == 0) {
+              tma_load_5d_pair(&p.a_main_hi, &full_bar[s], st, k.c0, k.x, k.y, k.plane, a4);
+              if (PASSES == 3) tma_load_5d_pair(&p.a_main_lo, &full_bar[s], st + kATile, k.c0, k.x, k.y, k.plane, a4);
+            } else {
+              tma_load_5d_pair(&p.a_rgb_hi, &full_bar[s], st, 0, 0, 0, 0, a4);
+              if (PASSES == 3) tma_load_5d_pair(&p.a_rgb_lo, &full_bar[s], st + kATile, 0, 0, 0, 0, a4);
+            }
+            tma_load_2d_pair(&p.b_hi, &full_bar[s], st + NOP * kATile, k.bk, brow);
+            if (PASSES == 3) tma_load_2d_pair(&p.b_lo, &full_bar[s], st + NOP * kATile + BT, k.bk, brow);
+            continue;
+          }
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
           if (k.kind == 0) {
             tma_load_5d(&p.a_main_hi, &full_bar[s], st, k.c0, k.x, k.y, k.plane, a4);
             if (PASSES == 3) tma_load_5d(&p.a_main_lo, &full_bar[s], st + kATile, k.c0, k.x, k.y, k.plane, a4);
@@ -344,10 +430,10 @@ __global__ void __launch_bounds__(FUSED ? 512 : 384, 1) umma_gemm_kernel(const _
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (paired: the leader CTA issues for both) =====================
+    if (lane == 0 && rank == 0) {
       int it = 0, seg = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = cta0; tile < total_tiles; tile += ctas) {
         uint32_t d_tmem = 0;
         for (int ks = 0; ks < nsteps; ++ks, ++it) {
           const bool seg_start = (ks % seg_len) == 0;
@@ -366,26 +452,32 @@ __global__ void __launch_bounds__(FUSED ? 512 : 384, 1) umma_gemm_kernel(const _
           const uint64_t a_hi = make_sw128_desc(sa);
           const uint64_t b_hi = make_sw128_desc(sa + NOP * kATile);
           uint32_t acc = seg_start ? 0u : 1u;
+          auto mma = [&](uint64_t a, uint64_t b, uint32_t accum) {
+            if (PAIR) umma_f16_pair(d_tmem, a, b, IDESC, accum);
+            else umma_f16(d_tmem, a, b, IDESC, accum);
+          };
           if (PASSES == 3) {
             const uint64_t a_lo = make_sw128_desc(sa + kATile);
-            const uint64_t b_lo = make_sw128_desc(sa + NOP * kATile + kBTile);
+            const uint64_t b_lo = make_sw128_desc(sa + NOP * kATile + BT);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              umma_f16(d_tmem, a_lo + 2 * kk, b_hi + 2 * kk, IDESC, acc);
+              mma(a_lo + 2 * kk, b_hi + 2 * kk, acc);
               acc = 1u;
             }
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) umma_f16(d_tmem, a_hi + 2 * kk, b_lo + 2 * kk, IDESC, 1u);
+            for (int kk = 0; kk < 4; ++kk) mma(a_hi + 2 * kk, b_lo + 2 * kk, 1u);
           }
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            umma_f16(d_tmem, a_hi + 2 * kk, b_hi + 2 * kk, IDESC, acc);
+            mma(a_hi + 2 * kk, b_hi + 2 * kk, acc);
             acc = 1u;
           }
-          umma_commit(&empty_bar[s]);
+          if (PAIR) umma_commit_pair(&empty_bar[s]);
+          else umma_commit(&empty_bar[s]);
           const bool seg_end = ((ks + 1) % seg_len) == 0 || (ks + 1) == nsteps;
           if (seg_end) {
-            umma_commit(&tfull_bar[seg & 1]);
+            if (PAIR) umma_commit_pair(&tfull_bar[seg & 1]);
+            else umma_commit(&tfull_bar[seg & 1]);
             ++seg;
           }
         }
@@ -400,7 +492,7 @@ __global__ void __launch_bounds__(FUSED ? 512 : 384, 1) umma_gemm_kernel(const _
     const int l8 = ptid & 7, r32 = ptid >> 3;
     const FusedGather& g = p.fg;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = cta0; tile < total_tiles; tile += ctas) {
       const int m_tile = tile / p.n_tiles;
       asm volatile("bar.sync 1, 256;" ::: "memory");   // nobody still reads the previous tile's tables
       if (ptid < 8) {
@@ -508,8 +600,13 @@ __global__ void __launch_bounds__(FUSED ? 512 : 384, 1) umma_gemm_kernel(const _
     const int q = warp & 3, hf = (warp - 4) >> 2;
     const int row = q * 32 + lane;
     int seg = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+    auto release_slot = [&](int slot) {
+      if (PAIR) mbar_arrive_leader(&tempty_bar[slot]);
+      else mbar_arrive(&tempty_bar[slot]);
+    };
+    for (int tile = cta0; tile < total_tiles; tile += ctas) {
+      const int mt = tile / p.n_tiles, n_tile = tile - mt * p.n_tiles;
+      const int m_tile = PAIR ? mt * 2 + rank : mt;
       const int colbase = n_tile * 256 + hf * 128;
       if (SEGMENTED) {
         float tot[128];
@@ -530,7 +627,7 @@ __global__ void __launch_bounds__(FUSED ? 512 : 384, 1) umma_gemm_kernel(const _
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[slot]);
+          if (lane == 0) release_slot(slot);
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) epilogue_piece<EPI>(p.epi, n_units, m_tile, row, colbase + c * 32, tot + c * 32);
@@ -553,16 +650,18 @@ __global__ void __launch_bounds__(FUSED ? 512 : 384, 1) umma_gemm_kernel(const _
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[slot]);
+        if (lane == 0) release_slot(slot);
         ++seg;
       }
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();      // neither CTA may free TMEM / exit while the pair's MMAs can still touch it
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -574,11 +673,20 @@ __global__ void __launch_bounds__(FUSED ? 512 : 384, 1) umma_gemm_kernel(const _
 // 512 threads: warp 0 TMA (weights), 1 MMA, 2 TMEM alloc, 3 idle, 4..7 epilogue, 8..15 A producers.
 // smem: 2 stages x (16 KB A + 64 KB B) + 24 KB tables.
 // ------------------------------------------------------------------------------------------------
+// PAIR: a cluster of two CTAs owns 256 rows (4 patches) x 512 columns through cta_group::2 MMAs; each CTA
+// gathers its own 128 A rows and streams only half of the weights (2 x 16 KB per k-step), which makes room
+// for kF2PairStages stages.  Producer warps of both CTAs arrive (once per warp) on the leader's full barrier.
 constexpr int kF2Stages = 2;
+constexpr int kF2PairStages = 3;
 constexpr int kF2StageBytes = kATile + 2 * kBTile;
+constexpr int kF2PairStageBytes = kATile + kBTile;
 
+template <bool PAIR>
 __global__ void __launch_bounds__(512, 1) umma_conv1_fused_kernel(const __grid_constant__ UmmaGemmParams p) {
-  constexpr uint32_t IDESC = make_idesc_f16(128, 256);
+  constexpr uint32_t IDESC = make_idesc_f16(PAIR ? 256 : 128, 256);
+  constexpr int kF2Stages = PAIR ? p2p::kF2PairStages : p2p::kF2Stages;
+  constexpr int kF2StageBytes = PAIR ? p2p::kF2PairStageBytes : p2p::kF2StageBytes;
+  constexpr int BH = PAIR ? kBTile / 2 : kBTile;      // bytes of one 256-column weight half held by this CTA
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   int* tab_px = reinterpret_cast<int*>(smem + kF2Stages * kF2StageBytes);        // [2 patches][2 img][3 lvl][256]
@@ -593,47 +701,60 @@ __global__ void __launch_bounds__(512, 1) umma_conv1_fused_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_units = p.epi.n_patches;
-  const int total_tiles = p.m_tiles;
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int cta0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int ctas = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int total_tiles = PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles;     // cluster tiles when paired
   const int nsteps = p.nsteps;
 
   if (warp == 0 && lane == 0) tma_prefetch_desc(&p.b_hi);
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kF2Stages; ++i) {
-      mbar_init(&full_bar[i], 257);
+      mbar_init(&full_bar[i], PAIR ? 17 : 257);     // TMA expect_tx + producers (per thread; per warp x 2 CTAs)
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], PAIR ? 8 : 4);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_pair(&tmem_base_smem, 512);
+    else tmem_alloc(&tmem_base_smem, 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = cta0; tile < total_tiles; tile += ctas) {
         for (int ks = 0; ks < nsteps; ++ks, ++it) {
           const int s = it % kF2Stages;
           const uint32_t ph = (uint32_t)(it / kF2Stages) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
           const KStep k = p.steps[ks];
           uint8_t* st = smem + (size_t)s * kF2StageBytes;
-          mbar_expect_tx(&full_bar[s], 2 * kBTile);
-          tma_load_2d(&p.b_hi, &full_bar[s], st + kATile, k.bk, 0);
-          tma_load_2d(&p.b_hi, &full_bar[s], st + kATile + kBTile, k.bk, 256);
+          if (PAIR) {
+            if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * kBTile);     // 2 CTAs x 2 halves x 16 KB
+            tma_load_2d_pair(&p.b_hi, &full_bar[s], st + kATile, k.bk, rank * 128);
+            tma_load_2d_pair(&p.b_hi, &full_bar[s], st + kATile + BH, k.bk, 256 + rank * 128);
+          } else {
+            mbar_expect_tx(&full_bar[s], 2 * kBTile);
+            tma_load_2d(&p.b_hi, &full_bar[s], st + kATile, k.bk, 0);
+            tma_load_2d(&p.b_hi, &full_bar[s], st + kATile + kBTile, k.bk, 256);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       int it = 0, t = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+      for (int tile = cta0; tile < total_tiles; tile += ctas, ++t) {
         const uint32_t tph = (uint32_t)t & 1u;
         for (int ks = 0; ks < nsteps; ++ks, ++it) {
           const int s = it % kF2Stages;
@@ -648,15 +769,25 @@ __global__ void __launch_bounds__(512, 1) umma_conv1_fused_kernel(const __grid_c
               mbar_wait(&tempty_bar[h], tph ^ 1u);     // the epilogue has drained this half of the previous tile
               tc_fence_after();
             }
-            const uint64_t b = make_sw128_desc(sa + kATile + h * kBTile);
+            const uint64_t b = make_sw128_desc(sa + kATile + h * BH);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_f16(tmem_base + (uint32_t)h * 256u, a + 2 * kk, b + 2 * kk, IDESC, (ks > 0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < 4; ++kk) {
+              if (PAIR)
+                umma_f16_pair(tmem_base + (uint32_t)h * 256u, a + 2 * kk, b + 2 * kk, IDESC, (ks > 0 || kk > 0) ? 1u : 0u);
+              else
+                umma_f16(tmem_base + (uint32_t)h * 256u, a + 2 * kk, b + 2 * kk, IDESC, (ks > 0 || kk > 0) ? 1u : 0u);
+            }
           }
-          umma_commit(&empty_bar[s]);
+          if (PAIR) umma_commit_pair(&empty_bar[s]);
+          else umma_commit(&empty_bar[s]);
           if (ks + 1 == nsteps) {
-            umma_commit(&tfull_bar[0]);
-            umma_commit(&tfull_bar[1]);
+            if (PAIR) {
+              umma_commit_pair(&tfull_bar[0]);
+              umma_commit_pair(&tfull_bar[1]);
+            } else {
+              umma_commit(&tfull_bar[0]);
+              umma_commit(&tfull_bar[1]);
+            }
           }
         }
       }
@@ -667,7 +798,8 @@ __global__ void __launch_bounds__(512, 1) umma_conv1_fused_kernel(const __grid_c
     const int l8 = ptid & 7, r32 = ptid >> 3;
     const FusedGather& g = p.fg;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int ctile = cta0; ctile < total_tiles; ctile += ctas) {
+      const int tile = PAIR ? ctile * 2 + rank : ctile;       // this CTA's 128-row tile (2 patches); may be past the end
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (ptid < 8) {
         const int pp = ptid >> 2, j = ptid & 3;
@@ -768,7 +900,12 @@ __global__ void __launch_bounds__(512, 1) umma_conv1_fused_kernel(const __grid_c
           }
         }
         fence_proxy_async();
-        mbar_arrive(&full_bar[s]);
+        if (PAIR) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&full_bar[s]);
+        } else {
+          mbar_arrive(&full_bar[s]);
+        }
       }
     }
   } else if (warp >= 4) {
@@ -776,7 +913,8 @@ __global__ void __launch_bounds__(512, 1) umma_conv1_fused_kernel(const __grid_c
     const int q = warp & 3;
     const int row = q * 32 + lane;
     int t = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+    for (int ctile = cta0; ctile < total_tiles; ctile += ctas, ++t) {
+      const int tile = PAIR ? ctile * 2 + rank : ctile;
       const uint32_t tph = (uint32_t)t & 1u;
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
@@ -791,15 +929,20 @@ __global__ void __launch_bounds__(512, 1) umma_conv1_fused_kernel(const __grid_c
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[h]);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_leader(&tempty_bar[h]);
+          else mbar_arrive(&tempty_bar[h]);
+        }
       }
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -848,20 +991,41 @@ int make_tmap_fp16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   return 0;
 }
 
-template <int PASSES, bool SEGMENTED, int EPI, bool FUSED = false>
+template <int PASSES, bool SEGMENTED, int EPI, bool FUSED = false, bool PAIR = false>
 static int launch_one(const UmmaGemmParams& p, int grid, cudaStream_t st) {
-  constexpr int STAGES = (PASSES == 3) ? 2 : 4;
+  constexpr int STAGES = PAIR ? ((PASSES == 3) ? 3 : 6) : ((PASSES == 3) ? 2 : 4);
   constexpr int NOP = (PASSES == 3) ? 2 : 1;
-  const int smem = STAGES * NOP * (kATile + kBTile) + 1024;
-  auto kern = umma_gemm_kernel<PASSES, SEGMENTED, EPI, FUSED>;
+  const int smem = STAGES * NOP * (kATile + (PAIR ? kBTile / 2 : kBTile)) + 1024;
+  auto kern = umma_gemm_kernel<PASSES, SEGMENTED, EPI, FUSED, PAIR>;
   P2P_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<grid, FUSED ? 512 : 384, smem, st>>>(p);
+  if (PAIR) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(384);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    P2P_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
+  } else {
+    kern<<<grid, FUSED ? 512 : 384, smem, st>>>(p);
+  }
   P2P_LAUNCH_OK();
   return 0;
 }
 
 template <int EPI>
 static int launch_epi(const UmmaGemmParams& p, int passes, bool seg, int grid, cudaStream_t st) {
+  if (p.pair) {
+    if (passes == 3)
+      return seg ? launch_one<3, true, EPI, false, true>(p, grid, st) : launch_one<3, false, EPI, false, true>(p, grid, st);
+    return seg ? launch_one<1, true, EPI, false, true>(p, grid, st) : launch_one<1, false, EPI, false, true>(p, grid, st);
+  }
   if (passes == 3) return seg ? launch_one<3, true, EPI>(p, grid, st) : launch_one<3, false, EPI>(p, grid, st);
   return seg ? launch_one<1, true, EPI>(p, grid, st) : launch_one<1, false, EPI>(p, grid, st);
 }
@@ -871,15 +1035,44 @@ int launch_umma_gemm(const UmmaGemmParams& p, int epi, int passes, int num_sms, 
   P2P_REQUIRE(p.nsteps > 0 && p.m_tiles > 0 && p.n_tiles > 0, "umma gemm: empty problem");
   const bool seg = p.seg_len > 0 && p.seg_len < p.nsteps;
   const int total = p.m_tiles * p.n_tiles;
-  const int grid = total < num_sms ? total : num_sms;
+  int grid = total < num_sms ? total : num_sms;
+  if (p.pair) {      // clusters of 2 CTAs; a pair tile = two m-tiles x one n-tile
+    P2P_REQUIRE(!fused || p.fg.generation == 2, "the first-generation fused-gather kernel is single-CTA");
+    const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    const int clusters = pair_tiles < num_sms / 2 ? pair_tiles : num_sms / 2;
+    grid = 2 * clusters;
+  }
   if (fused) {
     P2P_REQUIRE(epi == EPI_CONV1 && passes == 1 && !seg, "fused gather is available for 1-pass conv1 only");
     if (p.fg.generation == 1)     // first version (128 x 256 tiles, no tables), kept for comparison: fuse_gather = 2
       return launch_one<1, false, EPI_CONV1, true>(p, grid, st);
+    if (p.pair) {
+      const int smem = kF2PairStages * kF2PairStageBytes + 3072 * 8 + 1024;
+      auto kern = umma_conv1_fused_kernel<true>;
+      P2P_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      const int ptiles = (p.m_tiles + 1) / 2;
+      const int clusters = ptiles < num_sms / 2 ? ptiles : num_sms / 2;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(2 * clusters));
+      cfg.blockDim = dim3(512);
+      cfg.dynamicSmemBytes = (size_t)smem;
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      P2P_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
+      P2P_LAUNCH_OK();
+      return 0;
+    }
     const int smem = kF2Stages * kF2StageBytes + 3072 * 8 + 1024;
-    P2P_CUDA_OK(cudaFuncSetAttribute(umma_conv1_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    auto kern = umma_conv1_fused_kernel<false>;
+    P2P_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int g2 = p.m_tiles < num_sms ? p.m_tiles : num_sms;
-    umma_conv1_fused_kernel<<<g2, 512, smem, st>>>(p);
+    kern<<<g2, 512, smem, st>>>(p);
     P2P_LAUNCH_OK();
     return 0;
   }

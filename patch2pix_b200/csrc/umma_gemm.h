@@ -47,6 +47,7 @@ struct UmmaGemmParams {
   int n_tiles;           // 256-column tiles
   int a_units_per_tile;  // step of the outermost A coordinate per m-tile (2 patches, or 128 rows)
   int seg_len;           // k-steps accumulated in TMEM before a drain (0 / >= nsteps: whole K)
+  int pair;              // 1: CTA-pair kernel (cta_group::2); the B tensor maps must then use 128-row boxes
   const int* d_units;    // optional device count of A units (patches): m_tiles = ceil(*d_units / a_units_per_tile)
   UmmaEpilogue epi;
   FusedGather fg;

@@ -111,6 +111,32 @@ def test_umma_gemm_positive_accumulation_drift():
     assert abs(res['p3_s1']['rel_bias']) < 2e-6
 
 
+@pytest.mark.parametrize('M,N,K', [(128, 256, 64), (300, 300, 512), (1000, 512, 4608), (3000, 256, 1024)])
+def test_umma_gemm_cta_pair_is_bit_identical(M, N, K):
+    """The CTA-pair kernel (tcgen05.mma.cta_group::2, M=256 over two SMs) issues the same MMA sequence per output
+    element as the single-CTA kernel, so results must be bit-identical -- including odd m-tile counts, where the
+    second CTA of the last pair works on TMA zero fill, and problems smaller than one cluster wave."""
+    from patch2pix_b200 import _lib
+    h = _lib.default_handle('cuda:0')
+    g = torch.Generator().manual_seed(M + N + K)
+    ad = torch.randn(M, K, generator=g).cuda()
+    bd = torch.randn(N, K, generator=g).cuda()
+    try:
+        for passes, seg in ((1, 0), (1, 2), (3, 0), (3, 1), (3, 3)):
+            out = []
+            for pair in (0, 16):
+                h.set_option('gemm_pair', pair)
+                c = torch.full((M, N), float('nan'), device='cuda')
+                _lib.check(h.lib.p2p_test_gemm(h.h, _lib.ptr(ad), _lib.ptr(bd), _lib.ptr(c), M, N, K, passes, seg, 64.0,
+                                               h.stream()))
+                torch.cuda.synchronize()
+                out.append(c.cpu())
+            assert torch.isfinite(out[1]).all(), (passes, seg)
+            assert torch.equal(out[0], out[1]), (passes, seg, (out[0] - out[1]).abs().max().item())
+    finally:
+        h.set_option('gemm_pair', 0)
+
+
 # ------------------------------------------------------------------------------------------------
 # coarse stage
 # ------------------------------------------------------------------------------------------------
