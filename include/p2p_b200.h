@@ -80,9 +80,10 @@ P2P_API int p2p_set_regressor_weights(p2p_handle_t h, int which, const p2p_regre
  * reference -- are re-computed 3-pass; 0 = 3-pass for every row), "fuse_gather" (default 1: 1-pass conv1 launches
  * gather their A tiles in producer warps instead of reading a materialised patch tensor; 2 = first-generation
  * fused kernel, 0 = separate gather kernel + TMA), "fc_impl" (default 1: the 512-512 and 512-256 Linear layers run on
- * the tensor cores, 3-pass; 0: fp32 CUDA-core FC kernel), "gemm_pair" (default 3; bitmask of GEMM launches that run
+ * the tensor cores, 3-pass; 0: fp32 CUDA-core FC kernel), "gemm_pair" (bitmask of GEMM launches that run
  * on the CTA-pair kernel -- tcgen05.mma.cta_group::2, one M=256 tile over the two SMs of a TPC, bit-identical
- * results: 1 = 1-pass convs, 2 = 3-pass convs, 4 = FC, 8 = correlation, 16 = p2p_test_gemm). */
+ * results: 1 = 1-pass convs, 2 = 3-pass convs, 4 = FC, 8 = correlation, 16 = p2p_test_gemm, 32 = fused-gather conv1;
+ * default 35 = all conv launches). */
 P2P_API int p2p_set_option(p2p_handle_t h, const char* key, int value);
 P2P_API int p2p_get_option(p2p_handle_t h, const char* key, int* value);
 /* Number of kernel launches enqueued by this handle since creation (bench.py's gpu_launches). */
