@@ -17,6 +17,8 @@
 // warps 4..11 epilogue (TMEM lane quadrant = warp % 4, column half = (warp-4)/4).
 // Tile = 128 rows x 256 columns, K chunk 64 (one 128-byte swizzle row); two TMEM accumulator
 // slots (2 x 256 columns) so the drain of one segment/tile overlaps the MMAs of the next.
+// PAIR variants (default for the conv launches): clusters of two CTAs issue tcgen05.mma.cta_group::2
+// (M = 256 over the two SMs of a TPC, B split between their shared memories); see the kernel comment.
 #include <cuda.h>
 
 #include "kernels.h"
