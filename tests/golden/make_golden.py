@@ -31,6 +31,8 @@ from networks.ncn.model import MutualMatching                       # noqa: E402
 from networks.utils import filter_coarse                            # noqa: E402
 
 from patch2pix_b200.synth import make_seeded_state_dict, synthetic_pair  # noqa: E402
+sys.path.insert(0, HERE)
+from filter_cases import FILTER_CASES, filter_case_inputs           # noqa: E402
 
 
 def build_ref(sd, panc):
@@ -126,7 +128,23 @@ def case_refine_only(net, name, pair_idx, H, W, n):
     print(name, refined.shape, refined_t.shape)
 
 
+def case_filter_quirks(name='filter_quirks'):
+    """networks/utils.py:38-72 on crafted candidate lists: every branch of filter_coarse."""
+    out = {}
+    for cname, kind, thres, mutual, ptmax, seed in FILTER_CASES:
+        rows, scores = filter_case_inputs(kind)
+        np.random.seed(seed)
+        fm, fs = filter_coarse([rows.clone()], [scores.clone()], thres, mutual, ptmax=ptmax)
+        out[cname + '_matches'] = np_(fm[0])
+        out[cname + '_scores'] = np_(fs[0])
+        print(cname, tuple(fm[0].shape))
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'filter':      # only the (network-free) filter_coarse fixture
+        case_filter_quirks()
+        sys.exit(0)
     torch.manual_seed(0)
     sd = make_seeded_state_dict(0)
     net1 = build_ref(dict(sd), panc=1)
@@ -137,3 +155,4 @@ if __name__ == '__main__':
     case_stages(net1, 'stages_128x96', 5, 128, 96)
     case_train_sequence(net8, 'trainseq_96x128', 3, 96, 128, ptmax=12, np_seed=123)
     case_refine_only(net1, 'refine_128x160', 9, 128, 160, 40)
+    case_filter_quirks()

@@ -99,3 +99,19 @@ def test_shift_to_anchors_and_filter_quirks():
     fm, fs = O.filter_coarse(cm, sc, 0.0, True)
     assert fm[0].tolist() == [[3, 1, 1, 1], [9, 1, 1, 1]]
     assert fs[0].tolist() == pytest.approx([0.2, 0.3])
+
+
+def test_filter_coarse_branches_vs_live_reference():
+    """Every branch of networks/utils.py:38-72 (mutual skip, threshold skip, ptmax fill / cut / degenerate ids, numpy
+    RNG order) on crafted candidate lists: fixtures written by the live reference (`make_golden.py filter`)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('filter_cases', os.path.join(GOLD, 'filter_cases.py'))
+    fc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fc)
+    g = np.load(os.path.join(GOLD, 'filter_quirks.npz'))
+    for cname, kind, thres, mutual, ptmax, seed in fc.FILTER_CASES:
+        rows, scores = fc.filter_case_inputs(kind)
+        np.random.seed(seed)
+        fm, fs = O.filter_coarse([rows.clone()], [scores.clone()], thres, mutual, ptmax=ptmax)
+        assert np.array_equal(fm[0].numpy(), g[cname + '_matches']), cname
+        assert np.array_equal(fs[0].numpy(), g[cname + '_scores']), cname
