@@ -1041,7 +1041,8 @@ int launch_umma_gemm(const UmmaGemmParams& p, int epi, int passes, int num_sms, 
   if (p.pair) {      // clusters of 2 CTAs; a pair tile = two m-tiles x one n-tile
     P2P_REQUIRE(!fused || p.fg.generation == 2, "the first-generation fused-gather kernel is single-CTA");
     const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
-    const int clusters = pair_tiles < num_sms / 2 ? pair_tiles : num_sms / 2;
+    const int max_clusters = num_sms >= 2 ? num_sms / 2 : 1;
+    const int clusters = pair_tiles < max_clusters ? pair_tiles : max_clusters;
     grid = 2 * clusters;
   }
   if (fused) {
@@ -1053,7 +1054,8 @@ int launch_umma_gemm(const UmmaGemmParams& p, int epi, int passes, int num_sms, 
       auto kern = umma_conv1_fused_kernel<true>;
       P2P_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       const int ptiles = (p.m_tiles + 1) / 2;
-      const int clusters = ptiles < num_sms / 2 ? ptiles : num_sms / 2;
+      const int max_clusters = num_sms >= 2 ? num_sms / 2 : 1;
+      const int clusters = ptiles < max_clusters ? ptiles : max_clusters;
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)(2 * clusters));
       cfg.blockDim = dim3(512);
