@@ -35,8 +35,15 @@ def _bn(sd, gen, name, c, var):
     sd[name + '.running_var'] = var * (0.7 + 0.6 * torch.rand(c, generator=gen))
 
 
-def make_seeded_state_dict(seed=0, backbone=True, regressors=True):
-    """Flat fp32 dict with the reference's state_dict names (layer4 / num_batches_tracked omitted)."""
+def make_seeded_state_dict(seed=0, backbone=True, regressors=True, nc_init='uniform'):
+    """Flat fp32 dict with the reference's state_dict names (layer4 / num_batches_tracked omitted).
+
+    nc_init: 'uniform' -- NeighConsensus weights uniform in +-0.1 (an untrained net: its output is
+    unrelated to the correlation, a pair yields 10-20 mutual matches and exact zeros / ties abound);
+    'consensus' -- centre-tap-dominant filters with small random neighbourhood terms, i.e. what a
+    trained neighbourhood-consensus net does: it keeps the correlation structure, so a pair of
+    overlapping views yields ~1000 distinct mutual matches at 640x480 (the benchmark workload).
+    Every other tensor is identical between the two modes."""
     g = torch.Generator().manual_seed(seed)
     sd = {}
     if backbone:
@@ -59,6 +66,15 @@ def make_seeded_state_dict(seed=0, backbone=True, regressors=True):
     sd['ncn.conv.0.bias'] = 0.01 * torch.randn(16, generator=g)
     sd['ncn.conv.2.weight'] = (torch.rand(3, 1, 16, 3, 3, 3, generator=g) * 2 - 1) * 0.1
     sd['ncn.conv.2.bias'] = 0.01 * torch.randn(1, generator=g)
+    if nc_init == 'consensus':
+        gn = torch.Generator().manual_seed(12345 + seed)      # own stream: the tensors below stay as in 'uniform'
+        w0 = (torch.rand(3, 16, 1, 3, 3, 3, generator=gn) * 2 - 1) * 0.03
+        w0[1, :, :, 1, 1, 1] += 0.5 * torch.rand(16, 1, generator=gn) + 0.25
+        w2 = (torch.rand(3, 1, 16, 3, 3, 3, generator=gn) * 2 - 1) * 0.03
+        w2[1, :, :, 1, 1, 1] += 0.5 * torch.rand(1, 16, generator=gn) + 0.25
+        sd['ncn.conv.0.weight'], sd['ncn.conv.2.weight'] = w0, w2
+    elif nc_init != 'uniform':
+        raise ValueError("nc_init must be 'uniform' or 'consensus'")
     if regressors:
         for r in ('regress_mid', 'regress_fine'):
             sd[f'{r}.conv.0.weight'] = _xavier(g, 512, 518, 3, 3)
@@ -86,4 +102,35 @@ def synthetic_pair(pair_idx, height, width):
     base = base + 0.3 * torch.randn(1, 3, height + 32, width + 32, generator=g)
     im1 = base[:, :, 16:16 + height, 16:16 + width].contiguous()
     im2 = base[:, :, 8:8 + height, 24:24 + width].contiguous()
+    return im1, im2
+
+
+def shifted_pair_offset(pair_idx):
+    """(dx, dy) of synthetic_pair_shifted: multiples of 16 px, never (0, 0)."""
+    g = torch.Generator().manual_seed(2000 + int(pair_idx))
+    dx = 16 * int(torch.randint(-3, 4, (1,), generator=g))
+    dy = 16 * int(torch.randint(-2, 3, (1,), generator=g))
+    if dx == 0 and dy == 0:
+        dx = 16
+    return dx, dy
+
+
+def synthetic_pair_shifted(pair_idx, height, width, noise=0.05):
+    """Benchmark workload (round 2): two overlapping views of one texture whose offset is a multiple
+    of 16 px (= one pooled correlation cell at ksize 2), so that coarse cells correspond one to one in
+    the overlap, plus independent noise on the second view (no exact feature equality).  With the
+    'consensus' NC weights this gives ~1000 distinct mutual matches at 640x480 (vs 13-17 for
+    `synthetic_pair`), i.e. filter_coarse(ptmax=400) samples 400 DISTINCT proposals.
+    Returns im1, im2 as [1,3,H,W] fp32 on CPU."""
+    g = torch.Generator().manual_seed(2000 + int(pair_idx))
+    dx = 16 * int(torch.randint(-3, 4, (1,), generator=g))
+    dy = 16 * int(torch.randint(-2, 3, (1,), generator=g))
+    if dx == 0 and dy == 0:
+        dx = 16
+    low = torch.randn(1, 3, height // 8 + 12, width // 8 + 12, generator=g)
+    base = F.interpolate(low, size=(height + 96, width + 96), mode='bicubic', align_corners=False)
+    base = base + 0.3 * torch.randn(1, 3, height + 96, width + 96, generator=g)
+    im1 = base[:, :, 48:48 + height, 48:48 + width].contiguous()
+    im2 = base[:, :, 48 + dy:48 + dy + height, 48 + dx:48 + dx + width].contiguous()
+    im2 = im2 + noise * torch.randn(im2.shape, generator=g)
     return im1, im2

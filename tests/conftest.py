@@ -30,3 +30,10 @@ def pytest_collection_modifyitems(config, items):
 def seeded_sd():
     from patch2pix_b200.synth import make_seeded_state_dict
     return make_seeded_state_dict(0)
+
+
+@pytest.fixture(scope='session')
+def consensus_sd():
+    """Benchmark-workload weights: as seeded_sd but with trained-like (centre-dominant) NC filters."""
+    from patch2pix_b200.synth import make_seeded_state_dict
+    return make_seeded_state_dict(0, nc_init='consensus')

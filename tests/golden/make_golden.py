@@ -30,7 +30,7 @@ from networks.modules import maxpool4d, L2Normalize                 # noqa: E402
 from networks.ncn.model import MutualMatching                       # noqa: E402
 from networks.utils import filter_coarse                            # noqa: E402
 
-from patch2pix_b200.synth import make_seeded_state_dict, synthetic_pair  # noqa: E402
+from patch2pix_b200.synth import make_seeded_state_dict, synthetic_pair, synthetic_pair_shifted  # noqa: E402
 sys.path.insert(0, HERE)
 from filter_cases import FILTER_CASES, filter_case_inputs           # noqa: E402
 
@@ -48,9 +48,9 @@ def np_(t):
     return t.detach().cpu().numpy()
 
 
-def case_stages(net, name, pair_idx, H, W, ksize=2):
+def case_stages(net, name, pair_idx, H, W, ksize=2, gen=synthetic_pair):
     """predict_fine path with every intermediate of the coarse stage."""
-    im1, im2 = synthetic_pair(pair_idx, H, W)
+    im1, im2 = gen(pair_idx, H, W)
     out = {'pair_idx': pair_idx, 'H': H, 'W': W, 'ksize': ksize}
     with torch.no_grad():
         f1s, f2s = [], []
@@ -89,9 +89,9 @@ def case_stages(net, name, pair_idx, H, W, ksize=2):
     print(name, 'mutual', out['mutual_matches'].shape, 'fine', out['fine'].shape)
 
 
-def case_train_sequence(net8, name, pair_idx, H, W, ptmax, np_seed):
+def case_train_sequence(net8, name, pair_idx, H, W, ptmax, np_seed, gen=synthetic_pair):
     """train_patch2pix.py:97-118 forward sequence under eval()/no_grad (ptmax, panc=8)."""
-    im1, im2 = synthetic_pair(pair_idx, H, W)
+    im1, im2 = gen(pair_idx, H, W)
     out = {'pair_idx': pair_idx, 'H': H, 'W': W, 'ptmax': ptmax, 'np_seed': np_seed}
     with torch.no_grad():
         corr4d, delta4d, feats1, feats2 = net8.forward(im1, im2, ksize=2, return_feats=True)
@@ -146,13 +146,21 @@ if __name__ == '__main__':
         case_filter_quirks()
         sys.exit(0)
     torch.manual_seed(0)
-    sd = make_seeded_state_dict(0)
-    net1 = build_ref(dict(sd), panc=1)
-    net8 = build_ref(dict(sd), panc=8)
-    missing = [k for k in net1.state_dict() if k not in sd and 'layer4' not in k and 'num_batches' not in k]
-    assert not missing, missing
-    case_stages(net1, 'stages_96x128', 3, 96, 128)
-    case_stages(net1, 'stages_128x96', 5, 128, 96)
-    case_train_sequence(net8, 'trainseq_96x128', 3, 96, 128, ptmax=12, np_seed=123)
-    case_refine_only(net1, 'refine_128x160', 9, 128, 160, 40)
-    case_filter_quirks()
+    if not (len(sys.argv) > 1 and sys.argv[1] == 'shift'):
+        sd = make_seeded_state_dict(0)
+        net1 = build_ref(dict(sd), panc=1)
+        net8 = build_ref(dict(sd), panc=8)
+        missing = [k for k in net1.state_dict() if k not in sd and 'layer4' not in k and 'num_batches' not in k]
+        assert not missing, missing
+        case_stages(net1, 'stages_96x128', 3, 96, 128)
+        case_stages(net1, 'stages_128x96', 5, 128, 96)
+        case_train_sequence(net8, 'trainseq_96x128', 3, 96, 128, ptmax=12, np_seed=123)
+        case_refine_only(net1, 'refine_128x160', 9, 128, 160, 40)
+        case_filter_quirks()
+    # round 2: the benchmark workload family -- 'consensus' NC weights + 16-px-shifted views (hundreds of distinct
+    # mutual matches instead of a dozen), so that proposal / refine parity is pinned on many distinct windows
+    sdc = make_seeded_state_dict(0, nc_init='consensus')
+    netc1 = build_ref(dict(sdc), panc=1)
+    netc8 = build_ref(dict(sdc), panc=8)
+    case_stages(netc1, 'stages_shift_128x160', 2, 128, 160, gen=synthetic_pair_shifted)
+    case_train_sequence(netc8, 'trainseq_shift_160x240', 7, 160, 240, ptmax=60, np_seed=321, gen=synthetic_pair_shifted)

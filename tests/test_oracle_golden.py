@@ -9,7 +9,7 @@ import pytest
 import torch
 
 from oracle import p2p_oracle as O
-from patch2pix_b200.synth import synthetic_pair
+from patch2pix_b200.synth import synthetic_pair, synthetic_pair_shifted
 
 GOLD = os.path.join(os.path.dirname(__file__), 'golden')
 RTOL, ATOL = 2e-4, 2e-5
@@ -19,10 +19,12 @@ def _close(a, b, rtol=RTOL, atol=ATOL):
     np.testing.assert_allclose(np.asarray(a), np.asarray(b), rtol=rtol, atol=atol)
 
 
-@pytest.mark.parametrize('name', ['stages_96x128', 'stages_128x96'])
-def test_coarse_stages_and_predict_fine(name, seeded_sd):
+@pytest.mark.parametrize('name', ['stages_96x128', 'stages_128x96', 'stages_shift_128x160'])
+def test_coarse_stages_and_predict_fine(name, seeded_sd, consensus_sd):
     g = np.load(os.path.join(GOLD, name + '.npz'))
-    im1, im2 = synthetic_pair(int(g['pair_idx']), int(g['H']), int(g['W']))
+    gen = synthetic_pair_shifted if 'shift' in name else synthetic_pair
+    seeded_sd = consensus_sd if 'shift' in name else seeded_sd
+    im1, im2 = gen(int(g['pair_idx']), int(g['H']), int(g['W']))
     with torch.no_grad():
         f1 = O.backbone_forward_all(im1, seeded_sd)
         f2 = O.backbone_forward_all(im2, seeded_sd)
@@ -53,9 +55,12 @@ def test_coarse_stages_and_predict_fine(name, seeded_sd):
         _close(ps[0], g['predict_coarse_nomutual_scores'])
 
 
-def test_train_forward_sequence(seeded_sd):
-    g = np.load(os.path.join(GOLD, 'trainseq_96x128.npz'))
-    im1, im2 = synthetic_pair(int(g['pair_idx']), int(g['H']), int(g['W']))
+@pytest.mark.parametrize('name', ['trainseq_96x128', 'trainseq_shift_160x240'])
+def test_train_forward_sequence(name, seeded_sd, consensus_sd):
+    g = np.load(os.path.join(GOLD, name + '.npz'))
+    gen = synthetic_pair_shifted if 'shift' in name else synthetic_pair
+    seeded_sd = consensus_sd if 'shift' in name else seeded_sd
+    im1, im2 = gen(int(g['pair_idx']), int(g['H']), int(g['W']))
     with torch.no_grad():
         np.random.seed(int(g['np_seed']))
         fine, fine_p, mid, mid_p, anchors = O.train_forward_sequence(
