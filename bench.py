@@ -31,6 +31,15 @@ sys.path.insert(0, ROOT)
 
 H_DEF, W_DEF, PTMAX_DEF, PANC_DEF = 480, 640, 400, 8
 MAC_CONV1, MAC_CONV2 = 152764416, 150994944        # per patch, dense count
+N_DISTINCT = 8                                      # distinct synthetic pairs cycled per rank
+
+
+def workload_string(W, H, ptmax):
+    """Identical in both arms (the driver compares the strings)."""
+    cfgno = {(640, 480, 400): 2, (480, 320, 200): 1, (1024, 768, 1000): 3}.get((W, H, ptmax))
+    tag = f' (BASELINE configs[{cfgno}])' if cfgno is not None else ''
+    return (f'{W}x{H} pair, ptmax={ptmax} panc={PANC_DEF} -> {ptmax * PANC_DEF} patches/stage{tag}; synthetic '
+            f'16-px-shifted views + consensus NC weights (distinct proposals)')
 
 
 def parse():
@@ -51,6 +60,10 @@ def parse():
     ap.add_argument('--gemm-pair', type=int, default=None, help='bitmask of GEMM launches on the CTA-pair kernel')
     ap.add_argument('--backbone-fp32', action='store_true', help='keep cuDNN TF32 off in the e2e backbone')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--pairs', type=int, default=0,
+                    help='strong-scaling mode (BASELINE configs[4]): this many pairs in total, sharded over the ranks; '
+                         'rank 0 re-computes a sample of the other ranks\' pairs and checks bit-equality')
+    ap.add_argument('--legacy-workload', action='store_true', help="round-1 generator (13-17 mutual matches per pair)")
     ap.add_argument('--cpu-sample-patches', type=int, default=200)
     return ap.parse_args()
 
@@ -65,8 +78,8 @@ def model_config(device, panc):
 
 def load_traffic():
     """DRAM bytes (read + write) per launch from the committed `ncu --set full` capture of the round
-    (profiles/r01_traffic.json: kernel kind -> bytes), or {}."""
-    p = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    (profiles/r02_traffic.json: kernel kind -> bytes), or {}."""
+    p = os.path.join(ROOT, 'profiles', 'r02_traffic.json')
     if os.path.exists(p):
         with open(p) as f:
             return json.load(f)
@@ -74,46 +87,54 @@ def load_traffic():
 
 
 def load_peaks():
+    """Burst peak for a kernel whose timed region is short (clocks near max), sustained for seconds-long regions."""
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return {'hbm_gbs': d['hbm_gbs'], 'tflops': d.get('bf16_tflops_sustained', d['bf16_tflops']), 'src': 'measured'}
-    return {'hbm_gbs': 6650.0, 'tflops': 1400.0, 'src': 'fallback'}
+        return {'hbm_gbs': d['hbm_gbs'], 'tflops_burst': d['bf16_tflops'],
+                'tflops_sustained': d.get('bf16_tflops_sustained', d['bf16_tflops']), 'src': 'measured'}
+    return {'hbm_gbs': 6650.0, 'tflops_burst': 1590.0, 'tflops_sustained': 1400.0, 'src': 'fallback'}
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
-
-    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """Samples SM clock / power / throttle reasons through NVML every 5 ms while the timed region runs
+    (the region can be ~0.1 s long: nvidia-smi's process start-up alone would miss it)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
+        self.index, self.rows, self._halt, self.err = index, [], threading.Event(), None
+        self.sm_max = None
 
     def run(self):
-        while not self._halt.is_set():
-            try:
-                out = subprocess.run(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(',')]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
-            except Exception:
-                pass
-            self._halt.wait(0.2)
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[self.index]) if vis and vis.split(',')[self.index].isdigit() else self.index
+            h = N.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            reasons = getattr(N, 'nvmlDeviceGetCurrentClocksEventReasons', None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._halt.is_set():
+                self.rows.append((float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), N.nvmlDeviceGetPowerUsage(h) / 1e3,
+                                  int(reasons(h))))
+                self._halt.wait(0.005)
+        except Exception as e:   # NVML missing: report it, never fake a sample
+            self.err = repr(e)
 
     def finish(self):
         self._halt.set()
         self.join(timeout=6)
         if not self.rows:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
-        sm = [float(r[0]) for r in self.rows if r[0].replace('.', '').isdigit()]
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith('active') for r in self.rows)]
-        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': float(self.rows[0][1]),
-                'power_w_max': max(float(r[2]) for r in self.rows), 'samples': len(self.rows), 'reasons': reasons}
+            return {'sm_mhz': None, 'sm_max_mhz': self.sm_max, 'reasons': ['unavailable: ' + str(self.err)]}
+        bits = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20, 'sw_power_cap': 0x4,
+                'hw_power_brake_slowdown': 0x80}
+        allbits = 0
+        for r in self.rows:
+            allbits |= r[2]
+        return {'sm_mhz': statistics.median(r[0] for r in self.rows), 'sm_min_mhz': min(r[0] for r in self.rows),
+                'sm_max_mhz': self.sm_max, 'power_w_max': max(r[1] for r in self.rows), 'samples': len(self.rows),
+                'interval_ms': 5, 'source': 'nvml', 'reasons': [n for n, b in bits.items() if allbits & b]}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -168,18 +189,27 @@ def cpu_step(O, sd, im1, im2, ptmax, panc, n_sample, nc_slices=None):
             'n_sample': n_sub, 'n_full': n_full, 'nc_slices': 'all' if sl is None else f'{len(sl)}/{hA}'}
 
 
+def make_workload(args):
+    """(state_dict, pair generator): the benchmark workload family unless --legacy-workload."""
+    from patch2pix_b200.synth import make_seeded_state_dict, synthetic_pair, synthetic_pair_shifted
+    if args.legacy_workload:
+        return make_seeded_state_dict(0), synthetic_pair
+    return make_seeded_state_dict(0, nc_init='consensus'), synthetic_pair_shifted
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     from oracle import p2p_oracle as O
-    from patch2pix_b200.synth import make_seeded_state_dict, synthetic_pair
     threads = cpu_threads()
     torch.set_num_threads(threads)
-    sd = make_seeded_state_dict(0)
+    sd, gen = make_workload(args)
     H, W = args.height, args.width
-    pairs = [synthetic_pair(p, H, W) for p in range(2)]
-    # size the per-step sample so that the whole run stays within ~3 minutes
+    pairs = [gen(p, H, W) for p in range(2)]
+    # bounded sample per step (tier rule: the whole --steps/--warmup run must end within a few minutes): the NC 4D
+    # conv runs on a subset of its output slices and the refine stages on a subset of the patches; both are scaled
+    # to the full pair and the line says so ("extrapolated", with the sampled fractions)
     budget = 150.0 / max(args.steps + min(args.warmup, 1), 1)
     nc_slices, n_sample = (None, args.cpu_sample_patches) if budget > 12 else ((8, 96) if budget > 4 else (3, 32))
     for i in range(min(args.warmup, 1)):
@@ -187,13 +217,18 @@ def run_reference(args):
     rs = [cpu_step(O, sd, *pairs[i % 2], args.ptmax, PANC_DEF, n_sample, nc_slices) for i in range(args.steps)]
     hot = sum(r['hot_path_s'] for r in rs) / len(rs)
     e2e = sum(r['e2e_s'] for r in rs) / len(rs)
+    wall = sum(r['wall_s'] for r in rs) / len(rs)
+    hA = H // 16
+    nc_frac = 1.0 if rs[0]['nc_slices'] == 'all' else int(rs[0]['nc_slices'].split('/')[0]) / hA
     sample = (f'per step, one {W}x{H} pair: full backbone + correlation/max-pool/mutual/proposals, NC 4D conv on '
               f'{rs[0]["nc_slices"]} output slices, mid+fine refine on {rs[0]["n_sample"]} of {rs[0]["n_full"]} patches; '
-              f'sampled parts scaled to the full pair (mean wall {sum(r["wall_s"] for r in rs) / len(rs):.2f} s/step)')
+              f'sampled parts scaled to the full pair (measured wall {wall:.2f} s/step, extrapolated {e2e:.2f} s/pair)')
     line = {'impl': 'reference', 'metric': 'image-pairs/sec', 'value': 1.0 / e2e, 'unit': 'pairs/s', 'n_gpus': 0,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': e2e * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': f'{W}x{H} pair, ptmax={args.ptmax} panc={PANC_DEF} (BASELINE configs[2])',
+            'extrapolated': True, 'measured_wall_ms_per_step': wall * 1e3,
+            'sampled_fractions': {'nc_output_slices': nc_frac, 'refine_patches': rs[0]['n_sample'] / rs[0]['n_full']},
+            'config': {'workload': workload_string(W, H, args.ptmax),
                        'sequence': 'train_patch2pix.py:97-118 under eval/no_grad', 'includes_backbone': True},
             'cpu_baseline': {'value': 1.0 / e2e, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port', 'sample': sample,
                              'host_cores': os.cpu_count(), 'hot_path_only_pairs_per_s': 1.0 / hot},
@@ -209,7 +244,6 @@ def run_ours(args):
     import torch.distributed as dist
     from patch2pix_b200.model import Patch2PixB200
     from patch2pix_b200.sharding import PairSharder
-    from patch2pix_b200.synth import make_seeded_state_dict, synthetic_pair
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -225,8 +259,12 @@ def run_ours(args):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     H, W, K, Wm = args.height, args.width, args.steps, args.warmup
+    strong = args.pairs > 0
+    if strong:
+        K = (args.pairs + world - 1) // world            # steps per rank; ranks past the end of the list idle
+    sd, gen = make_workload(args)
     cfg = model_config(dev, PANC_DEF)
-    cfg.weights_dict = make_seeded_state_dict(0)
+    cfg.weights_dict = sd
     net = Patch2PixB200(cfg)
     for key, v in (('mid_passes', args.mid_passes), ('fine_passes', args.fine_passes), ('corr_passes', args.corr_passes),
                    ('seg_len', args.seg_len), ('mid_band', args.mid_band), ('fuse_gather', args.fuse_gather),
@@ -236,52 +274,63 @@ def run_ours(args):
     opts = {k: net._handle.get_option(k) for k in ('mid_passes', 'fine_passes', 'corr_passes', 'seg_len', 'mid_band', 'fuse_gather',
                                                     'gemm_pair')}
 
-    # pair indices: rank 0 decides, NCCL broadcasts (the "scatter pair indices" step)
+    # pair indices: rank 0 decides, NCCL broadcasts (the "scatter pair indices" step); global pair p -> rank p % world
     total_steps = K + Wm
-    all_pairs = sharder.scatter_pair_indices(torch.arange(total_steps * world, dtype=torch.int64))
-    n_distinct = 4                                      # distinct synthetic pairs cycled per rank
-    imgs = [synthetic_pair(int(all_pairs[i % len(all_pairs)]) % 64, H, W) for i in range(n_distinct)]
-    pinned = [(a.pin_memory(), b.pin_memory()) for a, b in imgs]
+    n_global = args.pairs if strong else total_steps * world
+    mine = sharder.scatter_pair_indices(torch.arange(n_global, dtype=torch.int64)).tolist()
+    if strong:
+        mine = mine[:1] * Wm + mine                       # warm-up on the first pair of the shard
+    n_distinct = N_DISTINCT if not strong else min(64, max(len(set(mine)), 1))
+    slot_of = {}                                           # synthetic image id -> resident pyramid slot
+    imgs, feats = [], []
     with torch.no_grad():
-        feats = []
-        for a, b in imgs:
-            f1 = net.extract.forward_all(a.to(dev), [], True)
-            f2 = net.extract.forward_all(b.to(dev), [], True)
-            feats.append((f1, f2))
+        for p in mine:
+            key = p % 64
+            if key in slot_of or len(slot_of) >= n_distinct:
+                continue
+            slot_of[key] = len(imgs)
+            a, b = gen(key, H, W)
+            imgs.append((a, b))
+            feats.append((net.extract.forward_all(a.to(dev), [], True), net.extract.forward_all(b.to(dev), [], True)))
+    slots = [slot_of.get(p % 64, i % max(len(imgs), 1)) for i, p in enumerate(mine)]
+    pinned = [(a.pin_memory(), b.pin_memory()) for a, b in imgs]
     n_patches = args.ptmax * PANC_DEF
-    results = torch.zeros(K, n_patches, 5, device=dev)
+    results = torch.zeros(max(K, 1), n_patches, 5, device=dev)
 
     # Two pairs are kept in flight: the coarse stage of pair i is enqueued before the host waits for the
     # mutual-match count of pair i-1 (filter_coarse's host sync), so the GPU never idles on that sync.
     def hot_submit(i):
-        f1, f2 = feats[i % n_distinct]
+        f1, f2 = feats[slots[i]]
         return (i, net.submit_coarse(f1, f2, 2, True))
 
-    def hot_finish(tk, out_slot=None):
+    def hot_finish(tk, out_slot=None, keep=None):
         i, ticket = tk
-        np.random.seed(i)
-        fine, fine_p, _ = net.finish_match(ticket, 0.0, args.ptmax)
+        np.random.seed(mine[i] % (2 ** 31))               # the reference's global numpy RNG, seeded per pair
+        fine, fine_p, cm = net.finish_match(ticket, 0.0, args.ptmax)
         if out_slot is not None:
             results[out_slot, :, :4] = fine[0]
             results[out_slot, :, 4] = fine_p[0]
+        if keep is not None:
+            keep.append(cm[0])
 
-    def hot_loop(first, steps, record):
+    def hot_loop(first, steps, record, keep=None):
         prev = None
         for j in range(steps):
             tk = hot_submit(first + j)
             if prev is not None:
-                hot_finish(prev[0], prev[1])
+                hot_finish(prev[0], prev[1], keep)
             prev = (tk, j if record else None)
-        hot_finish(prev[0], prev[1])
+        if prev is not None:
+            hot_finish(prev[0], prev[1], keep)
 
     def e2e_submit(i):
-        a, b = pinned[i % n_distinct]
+        a, b = pinned[slots[i]]
         f1, f2 = net.extract_pair(a, b, slot=i)    # pinned host images: H2D into the graph's input, then the backbone
         return (i, net.submit_coarse(f1, f2, 2, True))
 
     def e2e_finish(tk, host_out):
         i, ticket = tk
-        np.random.seed(i)
+        np.random.seed(mine[i] % (2 ** 31))
         fine, fine_p, _ = net.finish_match(ticket, 0.0, args.ptmax)
         host_out[:, :4].copy_(fine[0], non_blocking=True)          # D2H read of this step's result
         host_out[:, 4].copy_(fine_p[0], non_blocking=True)
@@ -293,7 +342,8 @@ def run_ours(args):
             if prev is not None:
                 e2e_finish(prev, host_outs[(j - 1) % len(host_outs)])
             prev = tk
-        e2e_finish(prev, host_outs[(steps - 1) % len(host_outs)])
+        if prev is not None:
+            e2e_finish(prev, host_outs[(steps - 1) % len(host_outs)])
         torch.cuda.current_stream().synchronize()
 
     def barrier():
@@ -305,6 +355,7 @@ def run_ours(args):
         barrier()
         if sampler:
             sampler.start()
+            time.sleep(0.02)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn(steps)
@@ -316,41 +367,93 @@ def run_ours(args):
         barrier()
         return ms.item()
 
+    n_mine = len(mine) - Wm                                # timed steps of this rank (strong mode: may be < K)
     with torch.no_grad():
         # ---- hot path, features resident in HBM -------------------------------------------------
         hot_loop(0, Wm, False)
         sharder.gather_results(results)                  # warm-up of the collective (NCCL sets up channels lazily)
         net.set_option('profile', 1)
         net._handle.profile_read()
+        net._handle.get_option('band_calls_rows_total')  # reset the running band totals
         l0 = net._handle.launch_count()
         sampler = ClockSampler(local) if rank == 0 else None
+        anchors_seen = []
 
         def hot_region(steps):
-            hot_loop(Wm, steps, True)
+            hot_loop(Wm, min(steps, n_mine), True, anchors_seen if rank == 0 else None)
             sharder.gather_results(results)              # NCCL gather of the matches (inside the timed region)
         ms_hot = timed(hot_region, K, sampler)
         launches = net._handle.launch_count() - l0
         clocks = sampler.finish() if sampler else None
         prof = net._handle.profile_read()
         net.set_option('profile', 0)
+        band_rows_total = net._handle.get_option('band_rows_total')
+        mid_rows_total = net._handle.get_option('band_calls_rows_total')
+        gathered = sharder.gather_results(results)       # [world, K, patches, 5]
+        distinct = [int(torch.unique(a, dim=0).shape[0]) for a in anchors_seen[:8]]
 
-        band_rows = net._handle.get_option('band_rows')
+        # ---- strong-scaling mode: rank 0 re-computes a sample of the other ranks' pairs, bit-equality ----------
+        cross = None
+        if strong and rank == 0:
+            cross = {'checked_pairs': [], 'bit_equal': True}
+            for r in range(1, world):
+                for step in (0, K // 2):
+                    p = step * world + r
+                    if p >= args.pairs:
+                        continue
+                    a, b = gen(p % 64, H, W)
+                    f1 = net.extract.forward_all(a.to(dev), [], True)
+                    f2 = net.extract.forward_all(b.to(dev), [], True)
+                    np.random.seed(p % (2 ** 31))
+                    fine, fine_p, _ = net.match_from_feats(f1, f2, 2, ptmax=args.ptmax)
+                    ok = bool(torch.equal(fine[0], gathered[r, step, :, :4]) and torch.equal(fine_p[0], gathered[r, step, :, 4]))
+                    cross['checked_pairs'].append(p)
+                    cross['bit_equal'] = cross['bit_equal'] and ok
+            if not cross['bit_equal']:
+                raise RuntimeError(f'cross-rank check failed: {cross}')
+
+        # ---- refine-only arm: refine_matches (networks/patch2pix.py:278-318) on 3200 distinct random float matches ----
+        refine_only = None
+        if not strong:
+            g = torch.Generator().manual_seed(99)
+            rm = (torch.rand(n_patches, 4, generator=g) * torch.tensor([W, H, W, H], dtype=torch.float32)).to(dev)
+            f1, f2 = feats[0]
+
+            def refine_once():
+                net._prepare_pair(f1, f2, 0)
+                mid, _ = net.forward_fine_match(f1, f2, [rm], 16, 'center', net.regress_mid, _prepared=0)
+                return net.forward_fine_match(f1, f2, mid, 16, 'center', net.regress_fine, _prepared=0)
+            for _ in range(3):
+                refine_once()
+            ms_ref = timed(lambda steps: [refine_once() for _ in range(steps)], K)
+            refine_only = {'ms_per_step': ms_ref / K, 'pairs_per_s': K / (ms_ref / 1e3),
+                           'input': f'{n_patches} distinct uniform-random float matches, mid + fine stage'}
+
         # ---- end to end: pinned host images -> matches on the host ------------------------------
-        # backbone in PyTorch's default cuDNN mode (TF32 convolutions allowed, as the reference would run)
-        torch.backends.cudnn.allow_tf32 = not args.backbone_fp32
-        torch.backends.cudnn.benchmark = True
-        net.enable_backbone_graphs(H, W, instances=2)
+        # backbone in PyTorch's default cuDNN mode (TF32 convolutions allowed, as the reference would run on a GPU);
+        # the fp32-backbone variant is measured beside it (parity: tests/test_gpu_parity.py::test_backbone_graph_tf32_path)
+        e2e_ms = {}
         host_outs = [torch.empty(n_patches, 5).pin_memory() for _ in range(2)]
-        e2e_loop(0, max(min(Wm, 3), 1), host_outs)
+        for mode in (['fp32'] if args.backbone_fp32 else ['tf32', 'fp32']):
+            if strong and mode == 'fp32' and not args.backbone_fp32:
+                continue
+            torch.backends.cudnn.allow_tf32 = mode == 'tf32'
+            torch.backends.cudnn.benchmark = True
+            net.enable_backbone_graphs(H, W, instances=2)
+            e2e_loop(0, max(min(Wm, 3), 1), host_outs)
 
-        def e2e_region(steps):
-            e2e_loop(Wm, steps, host_outs)
-        ms_e2e = timed(e2e_region, K)
+            def e2e_region(steps):
+                e2e_loop(Wm, min(steps, n_mine), host_outs)
+            e2e_ms[mode] = timed(e2e_region, K)
+        torch.backends.cudnn.allow_tf32 = False
 
     if rank == 0:
         peaks = load_peaks()
-        pairs = K * world
+        pairs = args.pairs if strong else K * world
         value = pairs / (ms_hot / 1e3)
+        # a seconds-long region under the power cap is compared with the sustained cuBLAS peak, a short one with the burst
+        sustained = ms_hot > 2000.0
+        peak = peaks['tflops_sustained'] if sustained else peaks['tflops_burst']
         # dominant kernel: the conv implicit GEMMs of the refine stage
         kern = {k: {'ms_per_launch': v[0] / v[1], 'launches': v[1]} for k, v in prof.items() if v[1] > 0}
         banded = opts['mid_passes'] == 3 and opts['mid_band'] > 0
@@ -359,14 +462,16 @@ def run_ours(args):
             base, _, stage = k.partition('_')
             if base not in macs:
                 continue
-            rows = band_rows if stage == 'band' else n_patches
+            # rows per launch: band launches process the band rows (running device-side total / launches)
+            rows = band_rows_total / max(kern[k]['launches'], 1) if stage == 'band' else n_patches
             ps = 3 if stage == 'band' else (opts['fine_passes'] if stage == 'fine' else (1 if banded else opts['mid_passes']))
             fl = 2.0 * macs[base] * rows
-            kern[k].update({'rows': rows, 'tensor_passes': ps,
+            kern[k].update({'rows_per_launch': rows, 'tensor_passes': ps,
                             'algorithmic_tflops': fl / (kern[k]['ms_per_launch'] * 1e-3) / 1e12})
             kern[k]['issued_tflops'] = kern[k]['algorithmic_tflops'] * ps
         gemm_names = [k for k in kern if k.startswith('conv')]
         dom = max(gemm_names, key=lambda k: kern[k]['ms_per_launch'] * kern[k]['launches'], default=None)
+        ksum = sum(v['ms_per_launch'] * v['launches'] for v in kern.values())
         roofline = None
         if dom:
             ach = kern[dom]['algorithmic_tflops']
@@ -374,46 +479,56 @@ def run_ours(args):
             kname = 'umma_conv1_fused_kernel' if (dom.startswith('conv1') and not dom.endswith('band') and opts['fuse_gather'] == 1) \
                 else 'umma_gemm_kernel'
             traffic = load_traffic().get(dom if kname == 'umma_gemm_kernel' else 'conv1_fused')
-            roofline = {'kernel': f'{kname} ({dom})', 'bound': 'tensor', 'achieved': ach, 'peak': peaks['tflops'],
-                        'unit': 'TFLOP/s', 'frac': ach / peaks['tflops'], 'traffic': traffic,
+            roofline = {'kernel': f'{kname} ({dom})', 'bound': 'tensor', 'achieved': ach, 'peak': peak,
+                        'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': traffic,
                         'traffic_unit': 'bytes of DRAM read+write per launch (ncu --set full, profiles/)',
-                        'peak_source': peaks['src'] + ' bf16 sustained (fp16 runs at the same tensor rate)',
+                        'peak_source': f"{peaks['src']} cuBLAS bf16 {'sustained' if sustained else 'burst'} (fp16 runs at the same "
+                                       f"tensor rate); timed region {ms_hot / 1e3:.2f} s -> {'sustained' if sustained else 'burst'} denominator",
+                        'frac_vs_burst': ach / peaks['tflops_burst'], 'frac_vs_sustained': ach / peaks['tflops_sustained'],
                         'tensor_passes': kern[dom]['tensor_passes'],
-                        'issued_frac': kern[dom]['issued_tflops'] / peaks['tflops'],
+                        'issued_frac': kern[dom]['issued_tflops'] / peak,
                         'share_of_step': kern[dom]['ms_per_launch'] * kern[dom]['launches'] / ms_hot,
                         'all_umma_gemm_share_of_step': gemm_ms / ms_hot,
-                        'band_rows_recomputed_3pass': band_rows if banded else None}
+                        'kernel_event_sum_ms_per_step': ksum / max(K, 1),
+                        'gap_ms_per_step': (ms_hot - ksum) / max(K, 1) if world == 1 else None,
+                        'band_rows_fraction': band_rows_total / mid_rows_total if (banded and mid_rows_total) else None}
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not strong:
             from oracle import p2p_oracle as O
             threads = cpu_threads()
             torch.set_num_threads(threads)
-            sd_cpu = make_seeded_state_dict(0)
-            cpu_step(O, sd_cpu, *imgs[0], args.ptmax, PANC_DEF, 16, 2)          # warm-up
-            r = cpu_step(O, sd_cpu, *imgs[0], args.ptmax, PANC_DEF, args.cpu_sample_patches, None)
+            cpu_step(O, sd, *imgs[0], args.ptmax, PANC_DEF, 16, 2)          # warm-up
+            r = cpu_step(O, sd, *imgs[0], args.ptmax, PANC_DEF, args.cpu_sample_patches, None)
             cpu = {'value': 1.0 / r['hot_path_s'], 'unit': 'pairs/s', 'cores': threads, 'host_cores': os.cpu_count(),
                    'kind': 'port',
                    'sample': (f'oracle port of the reference, {threads} threads: full coarse stage of one {W}x{H} pair '
                               f'({r["coarse_s"]:.2f} s) + mid/fine refine on {r["n_sample"]} of {r["n_full"]} patches scaled to '
                               f'the full pair ({r["refine_s_extrapolated"]:.2f} s); backbone excluded ({r["backbone_s"]:.2f} s)'),
                    'with_backbone_pairs_per_s': 1.0 / r['e2e_s']}
+        head = 'fp32' if args.backbone_fp32 else 'tf32'
+        e2e = {'value': pairs / (e2e_ms[head] / 1e3), 'unit': 'pairs/s', 'ms_per_step': e2e_ms[head] / K,
+               'h2d_bytes_per_step': 2 * 3 * H * W * 4, 'd2h_bytes_per_step': n_patches * 5 * 4,
+               'path': 'pinned host images -> H2D -> cuDNN ResNet34 pyramid, both images as one batch, CUDA graph ('
+                       + ('fp32' if head == 'fp32' else 'TF32 convs, PyTorch default') + ') -> hot path -> D2H matches+scores'}
+        if 'fp32' in e2e_ms and head != 'fp32':
+            e2e['fp32_backbone_value'] = pairs / (e2e_ms['fp32'] / 1e3)
         line = {
             'metric': 'image-pairs/sec', 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': K, 'warmup': Wm,
-            'ms_per_step': ms_hot / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'ms_per_step': ms_hot / K, 'higher_is_better': True, 'scaling': 'strong' if strong else 'weak', 'vs_baseline': None,
             'dtype': f'f16 tensor-core operands (mid: {opts["mid_passes"]}-pass hi/lo split'
                      f'{" on the risk band, 1-pass elsewhere" if opts["mid_band"] and opts["mid_passes"] == 3 else ""}, '
-                     f'fine: {opts["fine_passes"]}-pass, correlation: {opts["corr_passes"]}-pass), f32 accumulate; f32 NC conv',
+                     f'fine: {opts["fine_passes"]}-pass, correlation + NC conv: 3-pass), f32 accumulate',
             'data': 'synthetic',
-            'config': {'workload': f'{W}x{H} pair, ptmax={args.ptmax} panc={PANC_DEF} -> {n_patches} patches/stage '
-                                   f'(BASELINE configs[2]); hot path = correlation .. fine matches, features resident in HBM',
+            'config': {'workload': workload_string(W, H, args.ptmax),
+                       'hot_path': 'correlation .. fine matches, features resident in HBM',
                        'sequence': 'train_patch2pix.py:97-118 under eval/no_grad', 'pairs_per_step': world,
-                       'l2': 'distinct pair per step, per-step working set (~3 GB) >> 126 MB L2',
+                       'total_pairs': pairs, 'distinct_proposals_first_pairs': distinct,
+                       'l2': f'{len(imgs)} distinct pairs cycled per rank; per-step working set (~3 GB of scratch written and '
+                             f're-read) >> 126 MB L2',
                        'pipelining': 'two pairs in flight per GPU (coarse of pair i is enqueued before the host sync of pair i-1)',
                        'options': opts},
-            'e2e': {'value': pairs / (ms_e2e / 1e3), 'unit': 'pairs/s', 'ms_per_step': ms_e2e / K,
-                    'h2d_bytes_per_step': 2 * 3 * H * W * 4, 'd2h_bytes_per_step': n_patches * 5 * 4,
-                    'path': 'pinned host images -> H2D -> cuDNN ResNet34 pyramid, both images as one batch, CUDA graph (' + ('fp32' if args.backbone_fp32 else 'TF32 convs, PyTorch default') + ') -> hot path -> D2H matches+scores'},
-            'gpu_launches': launches, 'roofline': roofline, 'kernels': kern, 'clocks': clocks, 'cpu_baseline': cpu,
+            'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'kernels': kern, 'clocks': clocks,
+            'cpu_baseline': cpu, 'refine_only': refine_only, 'cross_rank_check': cross,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

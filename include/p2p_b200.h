@@ -134,12 +134,22 @@ P2P_API int p2p_proposals(p2p_handle_t h, const float* corr4d, const uint8_t* de
 
 /* ---- the np.unique part of filter_coarse (networks/utils.py:38-50): lexicographically sorted
  * first-occurrence indices of the distinct rows (mutual != 0: only rows occurring more than once).
- * rows int64 [n,4] with coordinates in [0,65535]; ids_out int32 [n]; count_out int32 [4] =
+ * rows int64 [n,4] with coordinates in [0,65535], n <= 4 Mi (lists beyond 16384 rows sort in global scratch); ids_out int32 [n]; count_out int32 [4] =
  * {number of ids, 1 if a coordinate was out of range, number of those ids whose score > thres,
  * number of ALL rows whose score > thres}; the last two (scores may be NULL -> 0) let the caller
  * evaluate filter_coarse's score threshold (utils.py:53) without a second device sync. */
 P2P_API int p2p_unique_rows(p2p_handle_t h, const int64_t* rows, int n, int mutual, const float* scores, float thres,
                     int32_t* ids_out, int32_t* count_out, void* stream);
+
+/* ---- the index arithmetic that follows np.unique in filter_coarse (networks/utils.py:51-69: matches[ids][ids2],
+ * scores likewise) fused with Patch2Pix.shift_to_anchors (networks/patch2pix.py:377-402).
+ * Output row r <- rows[ids[sel[r]]] (ids, sel int32 DEVICE, either may be NULL = identity); m output rows.
+ * panc 8: anchors_out int64 [m*8,4] = every selected row + the reference's 8-row template
+ * ((-p,-p,0,0),(p,-p,0,0),(-p,p,0,0),(p,p,0,0),(0,0,-p,-p),(0,0,p,-p),(0,0,-p,p),(0,0,p,p)); panc 1: anchors_out unused.
+ * matches_out int64 [m,4] / scores_out fp32 [m] may be NULL. */
+P2P_API int p2p_select_anchor(p2p_handle_t h, const int64_t* rows, const float* scores, const int32_t* ids,
+                      const int32_t* sel, int m, int panc, int pshift, int64_t* matches_out, float* scores_out,
+                      int64_t* anchors_out, void* stream);
 
 /* ---- refine: Patch2Pix.forward_fine_match for one batch item (networks/patch2pix.py:157-218):
  * select_local_patch_feats + L2 normalise + FeatRegressNet + parse_regressor_out.

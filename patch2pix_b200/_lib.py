@@ -43,6 +43,7 @@ _SIGNATURES = {
     'p2p_neigh_consensus': (_I, [_P, _P, _I, _I, _I, _I, _P, _P]),
     'p2p_proposals': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     'p2p_unique_rows': (_I, [_P, _P, _I, _I, _P, _F, _P, _P, _P]),
+    'p2p_select_anchor': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     'p2p_refine_prepare': (_I, [_P, C.POINTER(_P), C.POINTER(_P), _I, _I, _I, _I, _P]),
     'p2p_refine': (_I, [_P, _I, _P, _I, _I, _P, _P, _P]),
     'p2p_profile_read': (_I, [_P, C.POINTER(C.c_float), C.POINTER(_I), _I]),

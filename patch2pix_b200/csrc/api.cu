@@ -70,11 +70,12 @@ struct p2p_handle_s {
   int opt_fuse_gather = 1;  // 1: 1-pass conv1 gathers its A tiles in producer warps (128x512 tiles, lookup tables; no patch
                             // tensor in HBM); 2: first-generation fused kernel (128x256 tiles, producer-bound); 0: gather + TMA
   const int* last_band_count = nullptr;  // device counter of the last risk-band subset
+  unsigned long long* band_totals = nullptr;   // device: {band rows, rows} summed over mid-stage calls
   bool nc_set = false;
   float *nc_w1p = nullptr, *nc_b1p = nullptr, *nc_w2p = nullptr;
   float nc_b2 = 0.f;
   Regressor reg[2];
-  Arena coarse, refine, feat, misc;
+  Arena coarse, refine, feat, misc, uniq;
   PairFeatures pf[2];
   bool prepared = false;
   // optional per-kernel CUDA-event profile (p2p_set_option("profile", 1))
@@ -365,6 +366,13 @@ int p2p_create(int device, p2p_handle_t* out) {
   p2p_handle_s* h = new p2p_handle_s();
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
+  {
+    DeviceGuard g(device);
+    if (cudaMalloc(&h->band_totals, 2 * sizeof(unsigned long long)) == cudaSuccess)
+      cudaMemset(h->band_totals, 0, 2 * sizeof(unsigned long long));
+    else
+      h->band_totals = nullptr;
+  }
   *out = h;
   return 0;
 }
@@ -377,9 +385,11 @@ int p2p_destroy(p2p_handle_t h) {
   h->refine.release();
   h->feat.release();
   h->misc.release();
+  h->uniq.release();
   for (auto& e : h->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   for (auto e : h->event_pool) cudaEventDestroy(e);
   if (h->nc_w1p) cudaFree(h->nc_w1p);
+  if (h->band_totals) cudaFree(h->band_totals);
   for (int i = 0; i < 2; ++i)
     if (h->reg[i].blob) cudaFree(h->reg[i].blob);
   delete h;
@@ -458,6 +468,20 @@ int p2p_get_option(p2p_handle_t h, const char* key, int* value) {
       DeviceGuard g(h->device);
       P2P_CUDA_OK(cudaDeviceSynchronize());
       P2P_CUDA_OK(cudaMemcpy(value, h->last_band_count, sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    return 0;
+  }
+  if (!strcmp(key, "band_rows_total") || !strcmp(key, "band_calls_rows_total")) {
+    // running totals since the last read of "band_calls_rows_total" (synchronises): band rows / all mid-stage rows
+    *value = 0;
+    if (h->band_totals != nullptr) {
+      DeviceGuard g(h->device);
+      P2P_CUDA_OK(cudaDeviceSynchronize());
+      unsigned long long t[2] = {0, 0};
+      P2P_CUDA_OK(cudaMemcpy(t, h->band_totals, sizeof(t), cudaMemcpyDeviceToHost));
+      const bool rows = !strcmp(key, "band_calls_rows_total");
+      *value = (int)(rows ? t[1] : t[0]);
+      if (rows) P2P_CUDA_OK(cudaMemset(h->band_totals, 0, sizeof(t)));
     }
     return 0;
   }
@@ -665,9 +689,29 @@ int p2p_unique_rows(p2p_handle_t h, const int64_t* rows, int n, int mutual, cons
                     int32_t* ids_out, int32_t* count_out, void* stream) {
   P2P_ENTER(h);
   P2P_REQUIRE(rows && ids_out && count_out, "null tensor pointer");
+  unsigned char* scratch = nullptr;
+  const size_t sb = unique_rows_scratch_bytes(n);
+  if (sb > 0) {   // candidate lists beyond 16384 rows sort in global scratch (same kernel, same result)
+    int rc = h->uniq.reserve(sb + 4096);
+    if (rc) return rc;
+    scratch = (unsigned char*)h->uniq.take(sb);
+  }
   ProfScope ps(h, P2P_PROF_PROPOSALS, reinterpret_cast<cudaStream_t>(stream));
-  return launch_unique_rows((const long long*)rows, n, mutual, scores, thres, ids_out, count_out,
+  return launch_unique_rows((const long long*)rows, n, mutual, scores, thres, ids_out, count_out, scratch,
                             reinterpret_cast<cudaStream_t>(stream));
+}
+
+int p2p_select_anchor(p2p_handle_t h, const int64_t* rows, const float* scores, const int32_t* ids, const int32_t* sel,
+                      int m, int panc, int pshift, int64_t* matches_out, float* scores_out, int64_t* anchors_out,
+                      void* stream) {
+  P2P_ENTER(h);
+  P2P_REQUIRE(m >= 0 && rows != nullptr, "bad argument");
+  P2P_REQUIRE(panc == 1 || panc == 8, "panc must be 1 or 8 (networks/patch2pix.py:377-402)");
+  P2P_REQUIRE(scores_out == nullptr || scores != nullptr, "scores_out needs scores");
+  P2P_REQUIRE(panc == 1 || anchors_out != nullptr, "anchors_out is required for panc 8");
+  ProfScope ps(h, P2P_PROF_PROPOSALS, reinterpret_cast<cudaStream_t>(stream));
+  return launch_select_anchor((const long long*)rows, scores, ids, sel, m, panc, pshift, (long long*)matches_out,
+                              scores_out, (long long*)anchors_out, reinterpret_cast<cudaStream_t>(stream));
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -734,7 +778,6 @@ int run_regressor(p2p_handle_s* h, Regressor& R, int which, int passes, const Re
                                   lo ? B.r_lo : nullptr, rowmap, d_count, st)))
       return rc;
   }
-  const size_t qbytes = (size_t)B.npad * 512 * 4;
   if (h->opt_gemm_impl == 1) {
     P2P_REQUIRE(rowmap == nullptr, "the CUDA-core checker GEMM does not support row subsets");
     GemmOperands g1 = {B.p_hi, B.p_lo, B.r_hi, B.r_lo, R.w1_hi, R.w1_lo, 4, kConv1Steps * 64, n, passes, R.d_steps1, kConv1Steps};
@@ -782,6 +825,7 @@ int run_regressor(p2p_handle_s* h, Regressor& R, int which, int passes, const Re
       p.epi.y_scale = R.y_scale;
       p.epi.y_hi = B.y_hi;
       p.epi.y_lo = lo ? B.y_lo : nullptr;
+      p.epi.pooled = B.pooled;       // conv1's epilogue zeroes the max-pool accumulator conv2 merges into
       p.epi.n_patches = n;
       if (fused) {
         for (int s2 = 0; s2 < 2; ++s2) {
@@ -816,7 +860,6 @@ int run_regressor(p2p_handle_s* h, Regressor& R, int which, int passes, const Re
       p.epi.scale = R.scale2;
       p.epi.bias = R.bias2;
       p.epi.pooled = B.pooled;
-      P2P_CUDA_OK(cudaMemsetAsync(B.pooled, 0, qbytes, st));
       ProfScope ps(h, kb + 2, st);
       if ((rc = launch_umma_gemm(p, EPI_CONV2, passes, sms(h), st))) return rc;
     }
@@ -923,7 +966,7 @@ int p2p_refine(p2p_handle_t h, int which, const void* matches_in, int is_float, 
   {
     ProfScope ps(h, P2P_PROF_FLAG, st);
     if ((rc = launch_flag_risky(matches_in, is_float, B.raw, n, h->opt_mid_band * 1e-3f, 0.02f, h->pf[0].W, h->pf[0].H,
-                                h->pf[1].W, h->pf[1].H, B.rowmap, B.d_count, st)))
+                                h->pf[1].W, h->pf[1].H, B.rowmap, B.d_count, h->band_totals, st)))
       return rc;
   }
   return run_regressor(h, R, which, 3, B, matches_in, is_float, n, B.rowmap, B.d_count, matches_out, probs_out,

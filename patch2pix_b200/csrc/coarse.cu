@@ -720,10 +720,14 @@ int launch_proposals(const float* corr, const uint8_t* code, int hA, int wA, int
 // their first-occurrence index.  Output order is lexicographic, like np.unique.
 // count_out[0] = number of ids written, count_out[1] = 1 if a coordinate was out of [0,65535].
 // ------------------------------------------------------------------------------------------------
+// `gscratch` != nullptr: keys / indices live in global scratch instead of shared memory (candidate lists beyond
+// 16384 rows, e.g. ksize 1 at 1024x768; slower, same result).
 __global__ void __launch_bounds__(1024) unique_rows_kernel(const long long* __restrict__ rows, int n, int P, int mutual,
                                                           const float* __restrict__ scores, float thres,
-                                                          int* __restrict__ ids_out, int* __restrict__ count_out) {
-  extern __shared__ __align__(16) unsigned char smraw[];
+                                                          int* __restrict__ ids_out, int* __restrict__ count_out,
+                                                          unsigned char* gscratch) {
+  extern __shared__ __align__(16) unsigned char smraw_[];
+  unsigned char* smraw = gscratch != nullptr ? gscratch : smraw_;
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smraw);
   int* idx = reinterpret_cast<int*>(smraw + (size_t)P * 8);
   __shared__ int s_bad;
@@ -808,18 +812,75 @@ __global__ void __launch_bounds__(1024) unique_rows_kernel(const long long* __re
   }
 }
 
+size_t unique_rows_scratch_bytes(int n) {
+  if (n <= 16384) return 0;
+  size_t P = 2;
+  while (P < (size_t)n) P <<= 1;
+  return P * 12;
+}
+
 int launch_unique_rows(const long long* rows, int n, int mutual, const float* scores, float thres, int* ids_out,
-                       int* count_out, cudaStream_t st) {
-  P2P_REQUIRE(n >= 0 && n <= 16384, "unique_rows: at most 16384 candidate rows");
+                       int* count_out, unsigned char* gscratch, cudaStream_t st) {
+  P2P_REQUIRE(n >= 0 && n <= (1 << 22), "unique_rows: at most 4 Mi candidate rows");
   if (n == 0) {
     P2P_CUDA_OK(cudaMemsetAsync(count_out, 0, 4 * sizeof(int), st));
     return 0;
   }
   int P = 2;
   while (P < n) P <<= 1;
-  const size_t smem = (size_t)P * 12;
-  P2P_CUDA_OK(cudaFuncSetAttribute(unique_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  unique_rows_kernel<<<1, 1024, smem, st>>>(rows, n, P, mutual, scores, thres, ids_out, count_out);
+  if (n > 16384) {
+    P2P_REQUIRE(gscratch != nullptr, "unique_rows: scratch missing for a large candidate list");
+    unique_rows_kernel<<<1, 1024, 0, st>>>(rows, n, P, mutual, scores, thres, ids_out, count_out, gscratch);
+  } else {
+    const size_t smem = (size_t)P * 12;
+    P2P_CUDA_OK(cudaFuncSetAttribute(unique_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unique_rows_kernel<<<1, 1024, smem, st>>>(rows, n, P, mutual, scores, thres, ids_out, count_out, nullptr);
+  }
+  P2P_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8b: the index arithmetic of filter_coarse (networks/utils.py:51-69) + shift_to_anchors
+// (networks/patch2pix.py:377-402) in one launch.  out row r <- rows[ids[sel[r]]] (sel == nullptr: identity;
+// ids == nullptr: identity), scores likewise; with panc == 8 every selected row is also expanded with the
+// reference's 8-row anchor template (+-pshift on point 1 with point 2 fixed, then vice versa).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) select_anchor_kernel(const long long* __restrict__ rows,
+                                                           const float* __restrict__ scores, const int* __restrict__ ids,
+                                                           const int* __restrict__ sel, int m, int panc, int pshift,
+                                                           long long* __restrict__ matches_out,
+                                                           float* __restrict__ scores_out,
+                                                           long long* __restrict__ anchors_out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m) return;
+  int i = sel != nullptr ? sel[r] : r;
+  if (ids != nullptr) i = ids[i];
+  long long v[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) v[c] = rows[(size_t)i * 4 + c];
+  if (matches_out != nullptr) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) matches_out[(size_t)r * 4 + c] = v[c];
+  }
+  if (scores_out != nullptr) scores_out[r] = scores[i];
+  if (anchors_out != nullptr && panc == 8) {
+    const long long p = pshift;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const long long sx = (t & 1) ? p : -p, sy = (t & 2) ? p : -p;
+      long long* o = anchors_out + ((size_t)r * 8 + t) * 4;
+      if (t < 4) { o[0] = v[0] + sx; o[1] = v[1] + sy; o[2] = v[2]; o[3] = v[3]; }
+      else { o[0] = v[0]; o[1] = v[1]; o[2] = v[2] + sx; o[3] = v[3] + sy; }
+    }
+  }
+}
+
+int launch_select_anchor(const long long* rows, const float* scores, const int* ids, const int* sel, int m, int panc,
+                         int pshift, long long* matches_out, float* scores_out, long long* anchors_out, cudaStream_t st) {
+  if (m == 0) return 0;
+  select_anchor_kernel<<<cdiv(m, 256), 256, 0, st>>>(rows, scores, ids, sel, m, panc, pshift, matches_out, scores_out,
+                                                    anchors_out);
   P2P_LAUNCH_OK();
   return 0;
 }

@@ -21,8 +21,11 @@ int launch_neigh_consensus(const float* x, int hA, int wA, int hB, int wB, const
                            const float* w2p, float b2, float* hidden, float* out, cudaStream_t st);
 int launch_proposals(const float* corr, const uint8_t* code, int hA, int wA, int hB, int wB, int ksize, int upsample,
                      int center, int do_softmax, long long* matches, float* scores, cudaStream_t st);
+size_t unique_rows_scratch_bytes(int n);
 int launch_unique_rows(const long long* rows, int n, int mutual, const float* scores, float thres, int* ids_out,
-                       int* count_out, cudaStream_t st);
+                       int* count_out, unsigned char* gscratch, cudaStream_t st);
+int launch_select_anchor(const long long* rows, const float* scores, const int* ids, const int* sel, int m, int panc,
+                         int pshift, long long* matches_out, float* scores_out, long long* anchors_out, cudaStream_t st);
 
 // ---- refine.cu ---------------------------------------------------------------------------------
 // Activation scale applied before the fp16 hi/lo split of the L2-normalised patch features.
@@ -49,7 +52,7 @@ int launch_patch_gather(const PairFeatures& f1, const PairFeatures& f2, const vo
 // Rows whose refined coordinates sit within `tau` px of an integer (and whose offset is not the exact
 // relu-clamped -8) are collected, in ascending order, into rowmap / d_count.
 int launch_flag_risky(const void* matches_in, int is_float, const float* raw, int N, float tau, float eps_o, int W1,
-                      int H1, int W2, int H2, int* rowmap, int* d_count, cudaStream_t st);
+                      int H1, int W2, int H2, int* rowmap, int* d_count, unsigned long long* totals, cudaStream_t st);
 
 struct FcWeights {                // BN folded, transposed to [in][out] for coalesced reads
   float *w1t, *b1, *w2t, *b2, *w3t, *b3;

@@ -350,7 +350,7 @@ __global__ void pooled_split_kernel(const float* __restrict__ pooled, int n, __h
   if (d_count != nullptr) n = *d_count;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)n * 512) return;
-  const float v = pooled[i] * kFcActScale;
+  const float v = fminf(pooled[i] * kFcActScale, 65504.f);   // pooled >= 0 (post-ReLU); saturate, never inf/NaN
   const __half h = __float2half_rn(v);
   hi[i] = h;
   lo[i] = __float2half_rn(v - __half2float(h));
@@ -432,7 +432,8 @@ template <bool IS_FLOAT>
 __global__ void __launch_bounds__(1024) flag_risky_kernel(const void* __restrict__ matches_in,
                                                          const float* __restrict__ raw, int N, float tau, float eps_o,
                                                          float W1, float H1, float W2, float H2,
-                                                         int* __restrict__ rowmap, int* __restrict__ d_count) {
+                                                         int* __restrict__ rowmap, int* __restrict__ d_count,
+                                                         unsigned long long* __restrict__ totals) {
   __shared__ int s_warp[32];
   __shared__ int s_base;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -476,17 +477,23 @@ __global__ void __launch_bounds__(1024) flag_risky_kernel(const void* __restrict
     if (tid == 0) s_base = base + tot;
     __syncthreads();
   }
-  if (tid == 0) *d_count = s_base;
+  if (tid == 0) {
+    *d_count = s_base;
+    if (totals != nullptr) {         // running totals over calls (bench.py: band rows / rows, without a per-step sync)
+      atomicAdd(totals, (unsigned long long)s_base);
+      atomicAdd(totals + 1, (unsigned long long)N);
+    }
+  }
 }
 
 int launch_flag_risky(const void* matches_in, int is_float, const float* raw, int N, float tau, float eps_o, int W1,
-                      int H1, int W2, int H2, int* rowmap, int* d_count, cudaStream_t st) {
+                      int H1, int W2, int H2, int* rowmap, int* d_count, unsigned long long* totals, cudaStream_t st) {
   if (is_float)
     flag_risky_kernel<true><<<1, 1024, 0, st>>>(matches_in, raw, N, tau, eps_o, (float)W1, (float)H1, (float)W2,
-                                                (float)H2, rowmap, d_count);
+                                                (float)H2, rowmap, d_count, totals);
   else
     flag_risky_kernel<false><<<1, 1024, 0, st>>>(matches_in, raw, N, tau, eps_o, (float)W1, (float)H1, (float)W2,
-                                                 (float)H2, rowmap, d_count);
+                                                 (float)H2, rowmap, d_count, totals);
   P2P_LAUNCH_OK();
   return 0;
 }

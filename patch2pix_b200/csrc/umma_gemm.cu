@@ -21,6 +21,8 @@
 // (M = 256 over the two SMs of a TPC, B split between their shared memories); see the kernel comment.
 #include <cuda.h>
 
+#include <vector>
+
 #include "kernels.h"
 #include "umma_gemm.h"
 
@@ -233,6 +235,13 @@ __device__ __forceinline__ void epilogue_piece(const UmmaEpilogue& e, int n_patc
 #pragma unroll
         for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(e.y_lo + o)[q] = reinterpret_cast<const uint4*>(l)[q];
       }
+      // zero this patch's slice of the max-pool accumulator that conv2's epilogue merges into with atomicMax
+      // (replaces a cudaMemsetAsync between the two convolutions)
+      if (e.pooled != nullptr && (row & 63) == 0) {
+        float4* z = reinterpret_cast<float4*>(e.pooled + (size_t)n * 512 + col0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) z[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
   } else if (EPI == EPI_CONV2) {
     // relu + max over the 32 rows held by this warp (half a patch); atomically merged in HBM
@@ -254,7 +263,8 @@ __device__ __forceinline__ void epilogue_piece(const UmmaEpilogue& e, int n_patc
       __align__(16) __half l[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float y = fmaxf(fmaf(v[i], __ldg(e.scale + col0 + i), __ldg(e.bias + col0 + i)), 0.f) * e.y_scale;
+        // saturate instead of overflowing to inf (an activation beyond 65504 / y_scale is outside the fp16 operand range)
+        const float y = fminf(fmaxf(fmaf(v[i], __ldg(e.scale + col0 + i), __ldg(e.bias + col0 + i)), 0.f) * e.y_scale, 65504.f);
         h[i] = __float2half_rn(y);
         l[i] = __float2half_rn(y - __half2float(h[i]));
       }
@@ -967,8 +977,39 @@ static PFN_tmapEncodeTiled get_encode_fn() {
   return fn;
 }
 
+// Encoded tensor maps are cached per host thread (keyed by base pointer + geometry): the scratch arenas are stable
+// after the first pair of a given shape, so the ~36 descriptors of a refine stage are encoded once, not per launch.
+namespace {
+struct TmapKey {
+  const void* base;
+  int rank;
+  uint64_t dims[5];
+  uint64_t strides[4];
+  uint32_t box[5];
+  bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapEntry {
+  TmapKey key;
+  CUtensorMap map;
+};
+constexpr int kTmapCacheSize = 128;
+thread_local std::vector<TmapEntry> g_tmap_cache;
+thread_local int g_tmap_next = 0;
+}  // namespace
+
 int make_tmap_fp16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box) {
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base;
+  key.rank = rank;
+  for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) key.strides[i] = strides_bytes[i];
+  for (const TmapEntry& e : g_tmap_cache)
+    if (e.key == key) {
+      *out = e.map;
+      return 0;
+    }
   PFN_tmapEncodeTiled fn = get_encode_fn();
   if (fn == nullptr) {
     set_last_error("cuTensorMapEncodeTiled is not available from the driver");
@@ -989,6 +1030,12 @@ int make_tmap_fp16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
     return -2;
+  }
+  if ((int)g_tmap_cache.size() < kTmapCacheSize) {
+    g_tmap_cache.push_back(TmapEntry{key, *out});
+  } else {
+    g_tmap_cache[g_tmap_next] = TmapEntry{key, *out};
+    g_tmap_next = (g_tmap_next + 1) % kTmapCacheSize;
   }
   return 0;
 }

@@ -37,31 +37,25 @@ def _check_cuda_f32(t, name):
 
 
 class _UniqueTicket:
-    """unique_rows in flight: ids buffer on the device, counters on their way to pinned host memory."""
+    """unique_rows in flight: ids buffer on the device, counters on their way to pinned host memory.
+    Every ticket owns its pinned counter buffer (PyTorch's caching host allocator recycles it, stream-aware,
+    once the ticket is dropped), so any number of tickets can be outstanding."""
 
     def __init__(self, ids, cnt_host, event, thres):
         self.ids, self.cnt_host, self.event, self.thres = ids, cnt_host, event, thres
-        self.n_pass_selected = self.n_pass_all = None
+        self.n = self.n_pass_selected = self.n_pass_all = None
+
+    def wait_count(self):
+        """-> number of ids (the one host sync of filter_coarse; the reference syncs here too: utils.py:42)."""
+        if self.n is None:
+            self.event.synchronize()
+            self.n, bad, self.n_pass_selected, self.n_pass_all = self.cnt_host.tolist()
+            if bad:
+                raise RuntimeError('filter_coarse: match coordinates must lie in [0, 65535]')
+        return self.n
 
     def wait(self):
-        self.event.synchronize()   # the one host sync of filter_coarse (the reference syncs here too: utils.py:42)
-        n, bad, self.n_pass_selected, self.n_pass_all = self.cnt_host.tolist()
-        if bad:
-            raise RuntimeError('filter_coarse: match coordinates must lie in [0, 65535]')
-        return self.ids[:n].long()
-
-
-_pinned_ring = []
-_pinned_next = [0]
-
-
-def _pinned_count_buffer():
-    """Small ring of pinned int32[4] buffers (cudaHostAlloc per call would cost more than the kernel)."""
-    if len(_pinned_ring) < 16:
-        _pinned_ring.append(torch.empty(4, dtype=torch.int32).pin_memory())
-        return _pinned_ring[-1]
-    _pinned_next[0] = (_pinned_next[0] + 1) % len(_pinned_ring)
-    return _pinned_ring[_pinned_next[0]]
+        return self.ids[:self.wait_count()].long()
 
 
 def unique_rows_submit(rows, mutual=True, handle=None, scores=None, thres=0.0):
@@ -72,7 +66,7 @@ def unique_rows_submit(rows, mutual=True, handle=None, scores=None, thres=0.0):
     h = handle or _lib.default_handle(rows.device)
     ids = torch.empty(max(n, 1), dtype=torch.int32, device=rows.device)
     cnt = torch.empty(4, dtype=torch.int32, device=rows.device)
-    cnt_host = _pinned_count_buffer()
+    cnt_host = torch.empty(4, dtype=torch.int32, pin_memory=True)
     if scores is not None:
         scores = _check_cuda_f32(scores.flatten(), 'scores')
     with torch.cuda.device(rows.device):
@@ -90,35 +84,92 @@ def unique_rows(rows, mutual=True, handle=None):
     return unique_rows_submit(rows, mutual, handle).wait()
 
 
-def filter_coarse(coarse_matches, match_scores, ncn_thres=0.0, mutual=True, ptmax=None, _tickets=None):
-    """networks/utils.py:38-72 with the np.unique step on the device.  Quirks kept: lexicographic
-    output order, first-occurrence scores, 'skip a filter that would empty the set', degenerate
-    [0,0,0,0] ids and global-numpy-RNG shuffle/tile for ptmax."""
-    matches, scores = [], []
+def _select_anchor(rows, scores, ids, sel, m, panc, pshift, handle=None):
+    """One launch: out row r <- rows[ids[sel[r]]] (+ scores) and, for panc 8, the 8-anchor expansion
+    (networks/utils.py:51-69 index arithmetic + networks/patch2pix.py:377-402)."""
+    h = handle or _lib.default_handle(rows.device)
+    dev = rows.device
+    out_m = torch.empty(m, 4, dtype=torch.int64, device=dev)
+    out_s = torch.empty(m, dtype=torch.float32, device=dev) if scores is not None else None
+    anch = torch.empty(m * 8, 4, dtype=torch.int64, device=dev) if panc == 8 else None
+    with torch.cuda.device(dev):
+        _lib.check(h.lib.p2p_select_anchor(h.h, _lib.ptr(rows), _lib.ptr(scores), _lib.ptr(ids), _lib.ptr(sel), m, panc,
+                                           int(pshift), _lib.ptr(out_m), _lib.ptr(out_s), _lib.ptr(anch), h.stream()))
+    return out_m, out_s, anch
+
+
+def _filter_coarse_core(coarse_matches, match_scores, ncn_thres, mutual, ptmax, tickets, anchor):
+    """filter_coarse (networks/utils.py:38-72) with np.unique on the device; `anchor` = (panc, pshift) additionally
+    returns shift_to_anchors of the result from the same launch.  Quirks kept: lexicographic output order,
+    first-occurrence scores, 'skip a filter that would empty the set', degenerate [0,0,0,0] ids and the
+    global-numpy-RNG shuffle/tile for ptmax (drawn on the host from the same count as the reference)."""
+    matches, scores, anchors = [], [], []
+    panc, pshift = anchor if anchor is not None else (1, 0)
     for ib, (imatches, iscores) in enumerate(zip(coarse_matches, match_scores)):
-        tk = _tickets[ib] if _tickets is not None else unique_rows_submit(imatches, mutual, None, iscores, ncn_thres)
-        ids = tk.wait()
-        n_pass = tk.n_pass_selected if len(ids) > 0 else tk.n_pass_all
-        if len(ids) > 0:
-            iscores = iscores[ids]
-            imatches = imatches[ids]
-        if tk.thres == float(ncn_thres) and n_pass == iscores.numel():
-            ids = torch.arange(iscores.numel(), device=iscores.device)   # every row passes: no second sync
+        if not (isinstance(imatches, torch.Tensor) and imatches.is_cuda):
+            raise RuntimeError('filter_coarse expects CUDA tensors (no CPU fallback)')
+        tk = tickets[ib] if tickets is not None else unique_rows_submit(imatches, mutual, None, iscores, ncn_thres)
+        n = tk.wait_count()
+        n_rows = n if n > 0 else imatches.shape[0]            # rows left after the (possibly skipped) mutual step
+        n_pass = tk.n_pass_selected if n > 0 else tk.n_pass_all
+        fast = tk.thres == float(ncn_thres) and n_pass == n_rows and n_rows > 0 and imatches.dtype == torch.int64
+        if fast:
+            # every row passes the score threshold (the normal case: softmax scores > 0): the second index list is
+            # arange(n_rows) and the whole selection is one gather launch
+            ids = tk.ids if n > 0 else None
+            sel, m = None, n_rows
+            if ptmax:
+                iids = np.arange(n_rows)
+                np.random.shuffle(iids)
+                iids = np.tile(iids, (ptmax // n_rows + 1))[:ptmax]
+                stage = torch.empty(ptmax, dtype=torch.int32, pin_memory=True)
+                stage.numpy()[:] = iids
+                sel, m = stage.to(imatches.device, non_blocking=True), int(ptmax)
+            if ids is None and sel is None and panc == 1:
+                om, osc, an = imatches, iscores, None       # nothing filtered: the input passes unchanged
+            else:
+                om, osc, an = _select_anchor(imatches.contiguous(), _check_cuda_f32(iscores.flatten(), 'scores'), ids, sel, m,
+                                             panc, pshift)
         else:
+            ids = tk.ids[:n].long()
+            if len(ids) > 0:
+                iscores = iscores[ids]
+                imatches = imatches[ids]
             ids = torch.nonzero(iscores.flatten() > ncn_thres, as_tuple=False).flatten()
-        if ptmax:
-            if len(ids) == 0:
-                ids = torch.tensor([0, 0, 0, 0]).long()
-            iids = np.arange(len(ids))
-            np.random.shuffle(iids)
-            iids = np.tile(iids, (ptmax // len(ids) + 1))[:ptmax]
-            ids = ids.to(imatches.device)[torch.from_numpy(iids).to(imatches.device)]
-        if len(ids) > 0:
-            iscores = iscores[ids]
-            imatches = imatches[ids]
-        matches.append(imatches)
-        scores.append(iscores)
-    return matches, scores
+            if ptmax:
+                if len(ids) == 0:
+                    ids = torch.tensor([0, 0, 0, 0]).long()
+                iids = np.arange(len(ids))
+                np.random.shuffle(iids)
+                iids = np.tile(iids, (ptmax // len(ids) + 1))[:ptmax]
+                ids = ids.to(imatches.device)[torch.from_numpy(iids).to(imatches.device)]
+            if len(ids) > 0:
+                iscores = iscores[ids]
+                imatches = imatches[ids]
+            om, osc, an = imatches, iscores, None
+            if panc == 8:
+                an = (om.unsqueeze(1) + _anchor_template(om.device, pshift)).reshape(-1, 4)
+        matches.append(om)
+        scores.append(osc)
+        anchors.append(an if panc == 8 else om)
+    return matches, scores, anchors
+
+
+_tmpl_cache = {}
+
+
+def _anchor_template(device, p):
+    key = (str(device), int(p))
+    if key not in _tmpl_cache:
+        _tmpl_cache[key] = torch.tensor([[-p, -p, 0, 0], [p, -p, 0, 0], [-p, p, 0, 0], [p, p, 0, 0],
+                                         [0, 0, -p, -p], [0, 0, p, -p], [0, 0, -p, p], [0, 0, p, p]], device=device)
+    return _tmpl_cache[key]
+
+
+def filter_coarse(coarse_matches, match_scores, ncn_thres=0.0, mutual=True, ptmax=None, _tickets=None):
+    """networks/utils.py:38-72 with the np.unique step and the index arithmetic on the device."""
+    m, s, _ = _filter_coarse_core(coarse_matches, match_scores, ncn_thres, mutual, ptmax, _tickets, None)
+    return m, s
 
 
 def mutual_matching(corr4d, handle=None):
@@ -139,6 +190,11 @@ def _pack_delta(delta4d, ksize, h):
     _lib.check(h.lib.p2p_delta_pack(h.h, _lib.ptr(di), _lib.ptr(dj), _lib.ptr(dk), _lib.ptr(dl), di.numel(), ksize,
                                     _lib.ptr(code), h.stream()))
     return code
+
+
+class _FeatList(list):
+    """Feature pyramid list that remembers the CUDA-graph instance whose static buffers it views."""
+    graph_inst = None
 
 
 class _DeltaTuple(tuple):
@@ -349,10 +405,13 @@ class Patch2PixB200(nn.Module):
         """networks/patch2pix.py:377-402 (8-row template)."""
         if self.panc == 1:
             return matches
-        p = self.pshift
-        tmpl = torch.tensor([[-p, -p, 0, 0], [p, -p, 0, 0], [-p, p, 0, 0], [p, p, 0, 0],
-                             [0, 0, -p, -p], [0, 0, p, -p], [0, 0, -p, p], [0, 0, p, p]], device=self.device)
-        return [(m.unsqueeze(1) + tmpl).reshape(-1, 4) for m in matches]
+        out = []
+        for m in matches:
+            if m.is_cuda and m.dtype == torch.int64 and m.dim() == 2 and m.shape[1] == 4:
+                out.append(_select_anchor(m.contiguous(), None, None, None, m.shape[0], 8, self.pshift, self._handle)[2])
+            else:
+                out.append((m.unsqueeze(1) + _anchor_template(m.device, self.pshift)).reshape(-1, 4))
+        return out
 
     # -- refine --------------------------------------------------------------------------------
     def _which(self, regressor):
@@ -440,18 +499,30 @@ class Patch2PixB200(nn.Module):
             delta.code = code
         cm, sc = self.cal_coarse_matches(corr4d, delta, ksize=ksize, upsample=self.upsample, center=True)
         tickets = [unique_rows_submit(m, mutual, self._handle, sc_i, ncn_thres) for m, sc_i in zip(cm, sc)]
-        return {'feats1': feats1, 'feats2': feats2, 'cm': cm, 'sc': sc, 'tickets': tickets, 'mutual': mutual}
+        inst = getattr(feats1, 'graph_inst', None)
+        if inst is not None:
+            inst['pending'] += 1          # the ticket reads the graph instance's static output buffers until finish_match
+        return {'feats1': feats1, 'feats2': feats2, 'cm': cm, 'sc': sc, 'tickets': tickets, 'mutual': mutual, 'inst': inst}
+
+    @staticmethod
+    def _release(ticket):
+        inst = ticket.get('inst')
+        if inst is not None:
+            inst['pending'] -= 1
+            ticket['inst'] = None
 
     def finish_match(self, ticket, ncn_thres=0.0, ptmax=None, return_all=False):
         """Second half: wait for the count, run filter_coarse's host logic (numpy RNG sampling for
         ptmax exactly as the reference), shift to anchors, mid and fine refine."""
         feats1, feats2, cm, sc = ticket['feats1'], ticket['feats2'], ticket['cm'], ticket['sc']
+        anchor = (self.panc, self.pshift)
         if ptmax:
             if self.panc > 1 and ptmax > 0:
-                cm, sc = filter_coarse(cm, sc, 0.0, True, ptmax=ptmax, _tickets=ticket['tickets'] if ticket['mutual'] else None)
+                _, _, cm = _filter_coarse_core(cm, sc, 0.0, True, ptmax, ticket['tickets'] if ticket['mutual'] else None, anchor)
+            else:
+                cm = self.shift_to_anchors(cm)
         else:
-            cm, sc = filter_coarse(cm, sc, ncn_thres, ticket['mutual'], _tickets=ticket['tickets'])
-        cm = self.shift_to_anchors(cm)
+            _, _, cm = _filter_coarse_core(cm, sc, ncn_thres, ticket['mutual'], None, ticket['tickets'], anchor)
         single = len(cm) == 1
         if single:
             self._ready()
@@ -463,6 +534,7 @@ class Patch2PixB200(nn.Module):
                                                _prepared=0 if single else None)
         if single:
             del keep
+        self._release(ticket)          # everything that reads the pyramids has been enqueued (stream order protects it)
         if return_all:
             return fine, fine_p, mid, mid_p, cm
         return fine, fine_p, cm
@@ -481,7 +553,7 @@ class Patch2PixB200(nn.Module):
         return self.match_from_feats(feats1, feats2, ksize, ncn_thres, mutual, None, return_all)
 
     # -- backbone (feeds the path) ---------------------------------------------------------------
-    def extract_pair(self, im1, im2, slot=0):
+    def extract_pair(self, im1, im2, slot=None):
         """ResNet34 pyramids of both images (networks/patch2pix.py:222-226).  Equal-sized images go
         through the extractor as one batch of 2; with `enable_backbone_graphs` the batch runs as a
         captured CUDA graph (one of two alternating instances, so two pairs can be in flight)."""
@@ -489,7 +561,14 @@ class Patch2PixB200(nn.Module):
             return (self.extract.forward_all(im1, [], early_feat=True), self.extract.forward_all(im2, [], early_feat=True))
         g = getattr(self, '_bb_graphs', None)
         if g is not None and tuple(im1.shape) == g['shape'] and im1.shape[0] == 1:
+            if slot is None:                      # rotate through the instances
+                slot = g['next']
+                g['next'] = (slot + 1) % len(g['inst'])
             inst = g['inst'][slot % len(g['inst'])]
+            if inst['pending'] > 0:
+                raise RuntimeError('extract_pair: this backbone-graph instance still backs a pending submit_coarse ticket '
+                                   '(its static output buffers would be overwritten); call finish_match first or capture '
+                                   'more instances with enable_backbone_graphs(..., instances=n)')
             main = torch.cuda.current_stream(self.device)
             if im1.is_cuda:
                 inst['inp'][0:1].copy_(im1, non_blocking=True)
@@ -507,8 +586,10 @@ class Patch2PixB200(nn.Module):
             inst['graph'].replay()
             inst['consumed'] = main.record_event()
             feats = inst['out']
-        else:
-            feats = self.extract.forward_all(torch.cat([im1, im2], 0), [], early_feat=True)
+            f1, f2 = _FeatList(f[:1] for f in feats), _FeatList(f[1:] for f in feats)
+            f1.graph_inst = f2.graph_inst = inst
+            return f1, f2
+        feats = self.extract.forward_all(torch.cat([im1, im2], 0), [], early_feat=True)
         b = im1.shape[0]
         return [f[:b] for f in feats], [f[b:] for f in feats]
 
@@ -527,12 +608,12 @@ class Patch2PixB200(nn.Module):
                     graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(graph, stream=side):
                         out = self.extract.forward_all(inp, [], early_feat=True)
-                    insts.append({'inp': inp, 'graph': graph, 'out': out})
+                    insts.append({'inp': inp, 'graph': graph, 'out': out, 'pending': 0})
             torch.cuda.current_stream().wait_stream(side)
             for inst in insts:
                 inst['consumed'] = torch.cuda.current_stream().record_event()
             copy_stream = torch.cuda.Stream()
-        self._bb_graphs = {'shape': shape, 'inst': insts, 'copy_stream': copy_stream}
+        self._bb_graphs = {'shape': shape, 'inst': insts, 'copy_stream': copy_stream, 'next': 0}
 
     def predict_train_sequence(self, im1, im2, ksize=2, ptmax=400, return_all=False):
         """train_patch2pix.py:97-118 under eval()/no_grad: forward -> cal_coarse_matches ->
