@@ -58,6 +58,7 @@ def parse():
     ap.add_argument('--mid-band', type=int, default=None)
     ap.add_argument('--fuse-gather', type=int, default=None)
     ap.add_argument('--gemm-pair', type=int, default=None, help='bitmask of GEMM launches on the CTA-pair kernel')
+    ap.add_argument('--nc-impl', type=int, default=None, help='1: tensor-core NeighConsensus (default), 0: fp32 CUDA-core kernels')
     ap.add_argument('--backbone-fp32', action='store_true', help='keep cuDNN TF32 off in the e2e backbone')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--pairs', type=int, default=0,
@@ -268,11 +269,11 @@ def run_ours(args):
     net = Patch2PixB200(cfg)
     for key, v in (('mid_passes', args.mid_passes), ('fine_passes', args.fine_passes), ('corr_passes', args.corr_passes),
                    ('seg_len', args.seg_len), ('mid_band', args.mid_band), ('fuse_gather', args.fuse_gather),
-                   ('gemm_pair', args.gemm_pair)):
+                   ('gemm_pair', args.gemm_pair), ('nc_impl', args.nc_impl)):
         if v is not None:
             net.set_option(key, v)
     opts = {k: net._handle.get_option(k) for k in ('mid_passes', 'fine_passes', 'corr_passes', 'seg_len', 'mid_band', 'fuse_gather',
-                                                    'gemm_pair')}
+                                                    'gemm_pair', 'nc_impl')}
 
     # pair indices: rank 0 decides, NCCL broadcasts (the "scatter pair indices" step); global pair p -> rank p % world
     total_steps = K + Wm

@@ -97,6 +97,10 @@ class Handle:
         h = C.c_void_p()
         check(self.lib.p2p_create(self.device.index, C.byref(h)))
         self.h = h
+        # P2P_OPTIONS="nc_impl=0,mid_band=0": option overrides for A/B measurements (tools/, bench.py)
+        for kv in filter(None, os.environ.get('P2P_OPTIONS', '').split(',')):
+            k, _, v = kv.partition('=')
+            self.set_option(k.strip(), int(v))
 
     def __del__(self):
         try:

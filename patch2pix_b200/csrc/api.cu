@@ -74,6 +74,8 @@ struct p2p_handle_s {
   bool nc_set = false;
   float *nc_w1p = nullptr, *nc_b1p = nullptr, *nc_w2p = nullptr;
   float nc_b2 = 0.f;
+  NcUmmaWeights ncw;            // tensor-core NC operand images
+  int opt_nc_impl = 1;          // 1: NeighConsensus on the tensor cores (nc_umma.cu); 0: fp32 CUDA-core kernels (shape-capped)
   Regressor reg[2];
   Arena coarse, refine, feat, misc, uniq;
   PairFeatures pf[2];
@@ -389,6 +391,7 @@ int p2p_destroy(p2p_handle_t h) {
   for (auto& e : h->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   for (auto e : h->event_pool) cudaEventDestroy(e);
   if (h->nc_w1p) cudaFree(h->nc_w1p);
+  if (h->ncw.blob) cudaFree(h->ncw.blob);
   if (h->band_totals) cudaFree(h->band_totals);
   for (int i = 0; i < 2; ++i)
     if (h->reg[i].blob) cudaFree(h->reg[i].blob);
@@ -422,6 +425,10 @@ int p2p_set_ncn_weights(p2p_handle_t h, const float* w1, const float* b1, const 
   P2P_CUDA_OK(cudaMemcpy(h->nc_w2p, w2p.data(), sizeof(float) * 81 * 32, cudaMemcpyHostToDevice));
   P2P_CUDA_OK(cudaMemcpy(h->nc_b1p, b1p.data(), sizeof(float) * 32, cudaMemcpyHostToDevice));
   h->nc_b2 = b2[0];
+  {
+    int rc = nc_umma_pack(w1p.data(), b1p.data(), w2p.data(), h->ncw);
+    if (rc) return rc;
+  }
   h->nc_set = true;
   return 0;
 }
@@ -446,6 +453,7 @@ static int* option_slot(p2p_handle_t h, const char* key) {
   if (!strcmp(key, "fuse_gather")) return &h->opt_fuse_gather;
   if (!strcmp(key, "fc_impl")) return &h->opt_fc_impl;
   if (!strcmp(key, "gemm_pair")) return &h->opt_gemm_pair;
+  if (!strcmp(key, "nc_impl")) return &h->opt_nc_impl;
   return nullptr;
 }
 
@@ -581,7 +589,7 @@ int p2p_coarse(p2p_handle_t h, const float* feat1, const float* feat2, int c, in
   const bool tc = h->opt_corr_passes > 0;
   if (tc) P2P_REQUIRE(c % 64 == 0 && c / 64 <= kMaxKSteps, "tensor-core correlation needs C % 64 == 0");
   const int n1pad = (int)align_up(n1, 128), n2pad = (int)align_up(n2, 256);
-  size_t need = 4 * V * 4 + (size_t)nA * 32 * nB * 4 + (size_t)(nA + nB) * 8 + (1 << 16);
+  size_t need = 4 * V * 4 + nc_umma_scratch_bytes(V) + (size_t)(nA + nB) * 8 + (1 << 16);
   need += tc ? (size_t)(n1pad + n2pad) * c * 4 : (size_t)(n1 + n2) * c * 4;
   int rc = h->coarse.reserve(need);
   if (rc) return rc;
@@ -589,9 +597,11 @@ int p2p_coarse(p2p_handle_t h, const float* feat1, const float* feat2, int c, in
   float* pooled = pooled_out ? pooled_out : (float*)A.take(V * 4);
   float* m1 = (float*)A.take(V * 4);
   float* nc = ncn_out ? ncn_out : (float*)A.take(V * 4);
-  float* hidden = (float*)A.take((size_t)nA * 32 * nB * 4);
+  float* hidden = (float*)A.take(V * 128);               // fp32 [nA][32][nB] (nc_impl 0) or fp16 hi/lo [V][64] (nc_impl 1)
+  float* partial = (float*)A.take(18 * V * 4);
   float* rowmax = (float*)A.take((size_t)nA * 4);
-  unsigned int* colmax = (unsigned int*)A.take((size_t)nB * 4);
+  unsigned int* colmax = (unsigned int*)A.take((size_t)nB * 4 + 16);
+  unsigned int* xmax = colmax != nullptr ? colmax + nB : nullptr;
   if (tc) {
     __half* a_hi = (__half*)A.take((size_t)n1pad * c * 2);
     __half* a_lo = (__half*)A.take((size_t)n1pad * c * 2);
@@ -619,9 +629,25 @@ int p2p_coarse(p2p_handle_t h, const float* feat1, const float* feat2, int c, in
     ProfScope ps(h, P2P_PROF_CORR, st);
     if ((rc = launch_corr_pool_simt(fa, fb, c, n1, n2, ksize, pooled, delta_code_out, st))) return rc;
   }
+  P2P_REQUIRE(partial != nullptr && xmax != nullptr, "scratch carve failed");
+  if (h->opt_nc_impl == 1) {
+    {
+      ProfScope ps(h, P2P_PROF_MUTUAL, st);
+      if ((rc = launch_mutual_matching(pooled, nA, nB, rowmax, colmax, m1, xmax, st))) return rc;
+    }
+    {
+      // layer 1, layer 2 (tensor cores) and the combine pass, which also yields the maxima of the second MutualMatching
+      ProfScope ps(h, P2P_PROF_NC, st);
+      if ((rc = launch_neigh_consensus_umma(m1, hA, wA, hB, wB, h->ncw, h->nc_b1p, h->nc_b2, xmax, (__half*)hidden, partial,
+                                            nc, rowmax, colmax, sms(h), st)))
+        return rc;
+    }
+    ProfScope ps(h, P2P_PROF_MUTUAL, st);
+    return launch_mutual_apply(nc, nA, nB, rowmax, colmax, corr4d_out, nullptr, st);
+  }
   {
     ProfScope ps(h, P2P_PROF_MUTUAL, st);
-    if ((rc = launch_mutual_matching(pooled, nA, nB, rowmax, colmax, m1, st))) return rc;
+    if ((rc = launch_mutual_matching(pooled, nA, nB, rowmax, colmax, m1, nullptr, st))) return rc;
   }
   {
     ProfScope ps(h, P2P_PROF_NC, st);
@@ -629,7 +655,7 @@ int p2p_coarse(p2p_handle_t h, const float* feat1, const float* feat2, int c, in
       return rc;
   }
   ProfScope ps(h, P2P_PROF_MUTUAL, st);
-  if ((rc = launch_mutual_matching(nc, nA, nB, rowmax, colmax, corr4d_out, st))) return rc;
+  if ((rc = launch_mutual_matching(nc, nA, nB, rowmax, colmax, corr4d_out, nullptr, st))) return rc;
   return 0;
 }
 
@@ -658,19 +684,27 @@ int p2p_mutual_matching(p2p_handle_t h, const float* in, int nA, int nB, float* 
   if (rc) return rc;
   float* rowmax = (float*)h->misc.take((size_t)nA * 4);
   unsigned int* colmax = (unsigned int*)h->misc.take((size_t)nB * 4);
-  return launch_mutual_matching(in, nA, nB, rowmax, colmax, out, reinterpret_cast<cudaStream_t>(stream));
+  return launch_mutual_matching(in, nA, nB, rowmax, colmax, out, nullptr, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int p2p_neigh_consensus(p2p_handle_t h, const float* in, int hA, int wA, int hB, int wB, float* out, void* stream) {
   P2P_ENTER(h);
   P2P_REQUIRE(h->nc_set, "p2p_set_ncn_weights has not been called");
   P2P_REQUIRE(in && out && hA > 0 && wA > 0 && hB > 0 && wB > 0, "bad argument");
-  const size_t hid = (size_t)hA * wA * 32 * hB * wB * 4;
-  int rc = h->misc.reserve(hid + 4096);
+  const size_t V = (size_t)hA * wA * hB * wB;
+  int rc = h->misc.reserve(nc_umma_scratch_bytes(V) + 8192);
   if (rc) return rc;
-  float* hidden = (float*)h->misc.take(hid);
-  return launch_neigh_consensus(in, hA, wA, hB, wB, h->nc_w1p, h->nc_b1p, h->nc_w2p, h->nc_b2, hidden, out,
-                                reinterpret_cast<cudaStream_t>(stream));
+  float* hidden = (float*)h->misc.take(V * 128);
+  float* partial = (float*)h->misc.take(18 * V * 4);
+  unsigned int* xmax = (unsigned int*)h->misc.take(16);
+  P2P_REQUIRE(hidden && partial && xmax, "scratch carve failed");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (h->opt_nc_impl == 1) {
+    if ((rc = launch_absmax(in, V, xmax, st))) return rc;
+    return launch_neigh_consensus_umma(in, hA, wA, hB, wB, h->ncw, h->nc_b1p, h->nc_b2, xmax, (__half*)hidden, partial, out,
+                                       nullptr, nullptr, sms(h), st);
+  }
+  return launch_neigh_consensus(in, hA, wA, hB, wB, h->nc_w1p, h->nc_b1p, h->nc_w2p, h->nc_b2, hidden, out, st);
 }
 
 int p2p_proposals(p2p_handle_t h, const float* corr4d, const uint8_t* delta_code, int hA, int wA, int hB, int wB,

@@ -283,25 +283,38 @@ __global__ void __launch_bounds__(256) rowcolmax_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) mutual_apply_kernel(const float* __restrict__ x, int nA, int nB,
                                                           const float* __restrict__ rowmax,
                                                           const unsigned int* __restrict__ colmax,
-                                                          float* __restrict__ out) {
+                                                          float* __restrict__ out, unsigned int* __restrict__ absmax) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)nA * nB) return;
-  const int a = (int)(i / nB), b = (int)(i - (size_t)a * nB);
-  const float v = x[i];
-  const float ra = __fdiv_rn(v, rowmax[a] + 1e-5f);
-  const float rb = __fdiv_rn(v, ord2f(colmax[b]) + 1e-5f);
-  out[i] = __fmul_rn(v, __fmul_rn(ra, rb));
+  float o = 0.f;
+  if (i < (size_t)nA * nB) {
+    const int a = (int)(i / nB), b = (int)(i - (size_t)a * nB);
+    const float v = x[i];
+    const float ra = __fdiv_rn(v, rowmax[a] + 1e-5f);
+    const float rb = __fdiv_rn(v, ord2f(colmax[b]) + 1e-5f);
+    o = __fmul_rn(v, __fmul_rn(ra, rb));
+    out[i] = o;
+  }
+  if (absmax != nullptr) {      // warp-uniform
+    const float m = warp_max(fabsf(o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(absmax, __float_as_uint(m));
+  }
+}
+
+int launch_mutual_apply(const float* x, int nA, int nB, const float* rowmax, const unsigned int* colmax, float* out,
+                        unsigned int* absmax, cudaStream_t st) {
+  if (absmax != nullptr) P2P_CUDA_OK(cudaMemsetAsync(absmax, 0, sizeof(unsigned int), st));
+  const size_t n = (size_t)nA * nB;
+  mutual_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, nA, nB, rowmax, colmax, out, absmax);
+  P2P_LAUNCH_OK();
+  return 0;
 }
 
 int launch_mutual_matching(const float* x, int nA, int nB, float* rowmax, unsigned int* colmax, float* out,
-                           cudaStream_t st) {
+                           unsigned int* absmax, cudaStream_t st) {
   P2P_CUDA_OK(cudaMemsetAsync(colmax, 0, sizeof(unsigned int) * nB, st));
   rowcolmax_kernel<<<cdiv(nA, 8), 256, 0, st>>>(x, nA, nB, rowmax, colmax);
   P2P_LAUNCH_OK();
-  const size_t n = (size_t)nA * nB;
-  mutual_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, nA, nB, rowmax, colmax, out);
-  P2P_LAUNCH_OK();
-  return 0;
+  return launch_mutual_apply(x, nA, nB, rowmax, colmax, out, absmax, st);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -15,8 +15,12 @@ int launch_corr_pool_simt(const float* fa, const float* fb, int C, int n1, int n
                           uint8_t* code, cudaStream_t st);
 int launch_delta_unpack(const uint8_t* code, size_t n, int ks, long long* di, long long* dj, long long* dk,
                         long long* dl, cudaStream_t st);
+// absmax (optional): device word that receives the float bits of max |out| (activation scale of the tensor-core NC)
 int launch_mutual_matching(const float* x, int nA, int nB, float* rowmax, unsigned int* colmax, float* out,
-                           cudaStream_t st);
+                           unsigned int* absmax, cudaStream_t st);
+// second half only: rowmax / colmax were produced by another kernel (nc_combine_kernel)
+int launch_mutual_apply(const float* x, int nA, int nB, const float* rowmax, const unsigned int* colmax, float* out,
+                        unsigned int* absmax, cudaStream_t st);
 int launch_neigh_consensus(const float* x, int hA, int wA, int hB, int wB, const float* w1p, const float* b1p,
                            const float* w2p, float b2, float* hidden, float* out, cudaStream_t st);
 int launch_proposals(const float* corr, const uint8_t* code, int hA, int wA, int hB, int wB, int ksize, int upsample,
@@ -26,6 +30,21 @@ int launch_unique_rows(const long long* rows, int n, int mutual, const float* sc
                        int* count_out, unsigned char* gscratch, cudaStream_t st);
 int launch_select_anchor(const long long* rows, const float* scores, const int* ids, const int* sel, int m, int panc,
                          int pshift, long long* matches_out, float* scores_out, long long* anchors_out, cudaStream_t st);
+
+// ---- nc_umma.cu: NeighConsensus on the tensor cores -------------------------------------------------------
+struct NcUmmaWeights {
+  char* blob = nullptr;           // one allocation backing the two operand images
+  __half* img1 = nullptr;         // layer 1 weights, laid out exactly as in shared memory
+  __half* img2 = nullptr;         // layer 2 weights
+  float wsum1 = 0.f, b1max = 0.f; // bound of the hidden activations: b1max + wsum1 * max|x|
+  float inv_sw1 = 1.f, inv_sw2 = 1.f;
+};
+int nc_umma_pack(const float* w1p, const float* b1p, const float* w2p, NcUmmaWeights& W);
+size_t nc_umma_scratch_bytes(size_t V);
+int launch_absmax(const float* x, size_t n, unsigned int* out, cudaStream_t st);
+int launch_neigh_consensus_umma(const float* x, int hA, int wA, int hB, int wB, const NcUmmaWeights& W, const float* b1p,
+                                float b2, const unsigned int* xmax, __half* hidden, float* partial, float* out,
+                                float* rowmax, unsigned int* colmax, int num_sms, cudaStream_t st);
 
 // ---- refine.cu ---------------------------------------------------------------------------------
 // Activation scale applied before the fp16 hi/lo split of the L2-normalised patch features.

@@ -1,0 +1,515 @@
+// NeighConsensus (symmetric 2-layer Conv4d 1 -> 16 -> 1, k = 3, ReLU after each layer) on the tcgen05 tensor cores.
+//
+// Reference semantics (file:line relative to the reference repo):
+//   NeighConsensus.forward   networks/ncn/model.py:145-155   conv(x) + conv(x^T)^T, shared weights
+//   Conv4d / conv4d          networks/ncn/conv4d.py:12-130   true 4D cross-correlation, zero "same" padding
+//
+// conv(x) + conv(x^T)^T equals two independent nets on the SAME input, the second with tap axes (a,b) <-> (d,e)
+// swapped (api.cu packs both: w1p / w2p [81 taps][32 = 16 ch of net 0 | 16 ch of net 1]).
+//
+// Both layers are skinny GEMMs whose A operand is an im2col matrix that producer warps build directly in shared
+// memory in the 128B-swizzled K-major layout tcgen05.mma consumes; nothing but x, the hidden tensor and the
+// partial maps touches HBM and no FMA-pipe inner loop is left:
+//
+//   layer 1   rows = 128 consecutive 4D cells, K = 81 taps (padded to 128), N = 32 channels (both nets).
+//             Epilogue: + bias, ReLU, re-scale, fp16 hi/lo split -> hidden[cell][64 fp16] =
+//             [net0 hi 16 | net0 lo 16 | net1 hi 16 | net1 lo 16] (one 128-byte line per cell).
+//   layer 2   16 -> 1 channels would be an N = 1 GEMM.  Instead, per hidden cell a' and per net, the 9 PARTIAL maps
+//             P_(ta,tb)[a'][b] = sum over the 9 B-taps and 16 channels are one GEMM with K = 9 x 16 = 144 (3 swizzle
+//             atoms), N = 9 (padded to 16); the im2col rows are pure 16-byte copies of hidden lines.
+//   combine   out[a][b] = sum_net relu(b2 + sum_(ta,tb) P_(ta,tb)[a + (ta-1, tb-1)][b])  (fixed summation order:
+//             deterministic), fused with the row/column maxima of the MutualMatching that follows.
+//
+// Precision: fp16 hi/lo operand pairs, three MMAs per product (lo*hi + hi*lo + hi*hi, fp32 accumulate in TMEM):
+// products good to ~2^-22, i.e. fp32-grade (chains are 18 / 27 MMAs long, so the accumulator's round-toward-zero
+// stays below 1e-6 relative).  Activations are scaled by powers of two derived ON THE DEVICE from max|x| (and from
+// a weight-norm bound for the hidden tensor), so any input range is safe in fp16.
+//
+// CTA = 512 threads: warp 1 MMA issuer, warp 2 TMEM allocator, warps 4..7 epilogue (one TMEM lane quadrant each),
+// warps 8..15 im2col producers; persistent over 128-row tiles; ring of 4 (layer 1) / 3 (layer 2) operand stages
+// (the stage index always equals the atom index modulo the ring, so never-written chunks stay zero);
+// two TMEM accumulator slots so that the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <math.h>
+
+#include <type_traits>
+#include <vector>
+
+#include "kernels.h"
+#include "umma_ptx.cuh"
+
+namespace p2p {
+
+constexpr int kNcAtom = 128 * 128;   // bytes of one [128 rows x 64 fp16] swizzled operand atom
+
+struct NcParams {
+  int hA, wA, hB, wB, nA, nB;
+  long long V;                 // nA * nB cells
+  const float* x;              // [V] input (after the first MutualMatching)
+  const unsigned int* xmax;    // device: float bits of max |x|
+  __half* hidden;              // [V][64]
+  float* partial;              // [2 nets][9][V]
+  const __half* wimg;          // weight operand image, laid out exactly as in shared memory
+  const float* b1p;            // [32]
+  float wsum1, b1max;          // max_c sum_taps |w1|, max |b1|: bound of the hidden activations
+  float inv_sw1, inv_sw2;      // 1 / (power-of-two weight scales)
+  int tiles;
+};
+
+// Power-of-two activation scales: max|x| * sx and (hidden bound) * sh land in [2048, 4096).
+__device__ __forceinline__ void nc_scales(const NcParams& p, float& sx, float& sh) {
+  float xmax = __uint_as_float(__ldg(p.xmax));
+  if (!(xmax > 0.f) || !isfinite(xmax)) xmax = 1.f;
+  int e;
+  frexpf(xmax, &e);
+  sx = ldexpf(1.f, min(12 - e, 60));
+  float hb = fmaf(p.wsum1, xmax, p.b1max);
+  if (!(hb > 0.f) || !isfinite(hb)) hb = 1.f;
+  frexpf(hb, &e);
+  sh = ldexpf(1.f, min(12 - e, 60));
+}
+
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+  __half2 h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a = fminf(fmaxf(v[2 * i], -65504.f), 65504.f), b = fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f);
+    h[i] = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(h[i]);
+    l[i] = __floats2half2_rn(a - f.x, b - f.y);
+  }
+  hi = *reinterpret_cast<uint4*>(h);
+  lo = *reinterpret_cast<uint4*>(l);
+}
+
+template <int LAYER>
+__global__ void __launch_bounds__(512, 1) nc_umma_kernel(const __grid_constant__ NcParams p) {
+  constexpr int ATOMS = LAYER == 1 ? 2 : 3;        // swizzle atoms (64 K values) per tile
+  constexpr int STAGES = LAYER == 1 ? 4 : 3;       // multiple of ATOMS: stage index == atom index (mod ring)
+  constexpr int NCOL = LAYER == 1 ? 32 : 16;       // accumulator columns
+  constexpr int STAGE_BYTES = 2 * kNcAtom;         // A_hi + A_lo
+  constexpr int WATOM = NCOL * 128;                // bytes of one weight atom
+  constexpr int WBYTES = (LAYER == 1 ? 2 * 2 : 2 * 2 * 3) * WATOM;
+  constexpr uint32_t IDESC = make_idesc_f16(128, NCOL);
+  static_assert(STAGES % ATOMS == 0, "stage <-> atom mapping must be static");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* wsm = smem + STAGES * STAGE_BYTES;
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles = p.tiles;
+
+  // zero the operand ring (chunks the producers never write must read as zero) and stage the weights
+  for (int i = threadIdx.x; i < STAGES * STAGE_BYTES / 16; i += 512) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < WBYTES / 16; i += 512)
+    reinterpret_cast<uint4*>(wsm)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 256);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_smem, 64);
+  fence_proxy_async();               // generic-proxy writes above -> visible to the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
+        const int slot = tl & 1;
+        mbar_wait(&tempty_bar[slot], ((uint32_t)(tl >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(slot * NCOL);
+        const int net = LAYER == 2 ? (tile & 1) : 0;
+        uint32_t acc = 0u;
+#pragma unroll
+        for (int atom = 0; atom < ATOMS; ++atom, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full_bar[s], (uint32_t)(it / STAGES) & 1u);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+          const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + kNcAtom);
+          // weight image: layer 1 [hi|lo][atom]; layer 2 [net][hi|lo][atom]
+          const uint32_t wb = smem_u32(wsm) + (uint32_t)((LAYER == 1 ? atom : (net * 2 * 3 + atom)) * WATOM);
+          const uint64_t w_hi = make_sw128_desc(wb), w_lo = make_sw128_desc(wb + (uint32_t)(ATOMS * WATOM));
+          const int nk = LAYER == 1 ? (atom == 0 ? 4 : 2) : (atom < 2 ? 4 : 1);   // K16 slices that hold data
+          for (int kk = 0; kk < nk; ++kk) {
+            umma_f16(d_tmem, a_lo + 2 * kk, w_hi + 2 * kk, IDESC, acc);
+            acc = 1u;
+          }
+          for (int kk = 0; kk < nk; ++kk) umma_f16(d_tmem, a_hi + 2 * kk, w_lo + 2 * kk, IDESC, 1u);
+          for (int kk = 0; kk < nk; ++kk) umma_f16(d_tmem, a_hi + 2 * kk, w_hi + 2 * kk, IDESC, 1u);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tfull_bar[slot]);
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== im2col producers (256 threads: row = ptid & 127, part = ptid >> 7) =====================
+    const int ptid = threadIdx.x - 256;
+    const int r = ptid & 127;
+    const int part = ptid >> 7;        // warp-uniform
+    float sx, sh;
+    nc_scales(p, sx, sh);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      if (LAYER == 1) {
+        const long long v = (long long)tile * 128 + r;
+        const bool rv = v < p.V;
+        const int a = rv ? (int)(v / p.nB) : 0, b = rv ? (int)(v - (long long)a * p.nB) : 0;
+        const int ia = a / p.wA, ja = a - ia * p.wA, k = b / p.wB, l = b - k * p.wB;
+        // validity bits of the 12 single-axis taps: [0..2] A rows, [3..5] A cols, [6..8] B rows, [9..11] B cols
+        unsigned m = 0;
+        if (rv) {
+          m = (ia > 0 ? 1u : 0u) | 2u | (ia + 1 < p.hA ? 4u : 0u) | (ja > 0 ? 8u : 0u) | 16u | (ja + 1 < p.wA ? 32u : 0u) |
+              (k > 0 ? 64u : 0u) | 128u | (k + 1 < p.hB ? 256u : 0u) | (l > 0 ? 512u : 0u) | 1024u |
+              (l + 1 < p.wB ? 2048u : 0u);
+        }
+        const float* xc = p.x + (rv ? v : 0);
+        const long long oA = (long long)p.wA * p.nB, oB = p.nB;
+        const int oK = p.wB;
+        auto body = [&](auto PART) {
+          constexpr int PT = decltype(PART)::value;
+#pragma unroll
+          for (int atom = 0; atom < 2; ++atom, ++it) {
+            const int s = it % STAGES;
+            constexpr int NCH = 4;                 // chunks of 8 taps per thread and atom (atom 1: 2 resp. 1 hold data)
+            float val[NCH][8];
+#pragma unroll
+            for (int cc = 0; cc < NCH; ++cc) {
+              const int c = PT + 2 * cc;           // chunk inside the atom
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int t = (atom * 8 + c) * 8 + i;      // compile-time after unrolling
+                float f = 0.f;
+                if (t < 81) {
+                  const int ta = t / 27, tb = (t / 9) % 3, tk = (t / 3) % 3, tl = t % 3;
+                  const unsigned need = (1u << ta) | (8u << tb) | (64u << tk) | (512u << tl);
+                  if ((m & need) == need)
+                    f = __ldg(xc + (ta - 1) * oA + (tb - 1) * oB + (tk - 1) * oK + (tl - 1)) * sx;
+                }
+                val[cc][i] = f;
+              }
+            }
+            mbar_wait(&empty_bar[s], ((uint32_t)(it / STAGES) & 1u) ^ 1u);
+            uint8_t* st = smem + (size_t)s * STAGE_BYTES + r * 128;
+#pragma unroll
+            for (int cc = 0; cc < NCH; ++cc) {
+              const int c = PT + 2 * cc;
+              if (atom == 1 && c > 2) continue;    // taps >= 88: those chunks stay zero
+              uint4 hi, lo;
+              split8(val[cc], hi, lo);
+              *reinterpret_cast<uint4*>(st + ((c ^ (r & 7)) << 4)) = hi;
+              *reinterpret_cast<uint4*>(st + kNcAtom + ((c ^ (r & 7)) << 4)) = lo;
+            }
+            fence_proxy_async();
+            mbar_arrive(&full_bar[s]);
+          }
+        };
+        if (part == 0) body(std::integral_constant<int, 0>{});
+        else body(std::integral_constant<int, 1>{});
+      } else {
+        const int net = tile & 1;
+        const long long v = (long long)(tile >> 1) * 128 + r;
+        const bool rv = v < p.V;
+        const int b = rv ? (int)(v % p.nB) : 0;
+        const int k = b / p.wB, l = b - k * p.wB;
+        const __half* base = p.hidden + (rv ? v : 0) * 64 + net * 32;
+#pragma unroll
+        for (int atom = 0; atom < 3; ++atom, ++it) {
+          const int s = it % STAGES;
+          uint4 q[2][4];
+          // taps of this thread: atoms 0,1 -> local taps 2*part, 2*part+1 (hi and lo lines); atom 2 -> tap 8, part 0 = hi, 1 = lo
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int t = atom < 2 ? atom * 4 + 2 * part + j : 8;
+            const int tk = t / 3, tl = t - tk * 3;
+            const int k2 = k + tk - 1, l2 = l + tl - 1;
+            const bool ok = rv && k2 >= 0 && k2 < p.hB && l2 >= 0 && l2 < p.wB && (atom < 2 || j == 0);
+            const uint4* src = reinterpret_cast<const uint4*>(base + ((long long)(tk - 1) * p.wB + (tl - 1)) * 64);
+            if (atom < 2) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) q[j][c] = ok ? __ldg(src + c) : make_uint4(0, 0, 0, 0);   // hi0 hi1 lo0 lo1
+            } else {
+              q[j][0] = ok ? __ldg(src + 2 * part) : make_uint4(0, 0, 0, 0);
+              q[j][1] = ok ? __ldg(src + 2 * part + 1) : make_uint4(0, 0, 0, 0);
+            }
+          }
+          mbar_wait(&empty_bar[s], ((uint32_t)(it / STAGES) & 1u) ^ 1u);
+          uint8_t* st = smem + (size_t)s * STAGE_BYTES + r * 128;
+          if (atom < 2) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int c0 = 2 * (2 * part + j);      // chunk of the tap's channels 0..7; +1: channels 8..15
+              *reinterpret_cast<uint4*>(st + ((c0 ^ (r & 7)) << 4)) = q[j][0];
+              *reinterpret_cast<uint4*>(st + (((c0 + 1) ^ (r & 7)) << 4)) = q[j][1];
+              *reinterpret_cast<uint4*>(st + kNcAtom + ((c0 ^ (r & 7)) << 4)) = q[j][2];
+              *reinterpret_cast<uint4*>(st + kNcAtom + (((c0 + 1) ^ (r & 7)) << 4)) = q[j][3];
+            }
+          } else {
+            uint8_t* dst = st + part * kNcAtom;
+            *reinterpret_cast<uint4*>(dst + ((0 ^ (r & 7)) << 4)) = q[0][0];
+            *reinterpret_cast<uint4*>(dst + ((1 ^ (r & 7)) << 4)) = q[0][1];
+          }
+          fence_proxy_async();
+          mbar_arrive(&full_bar[s]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: 4 warps, one TMEM lane quadrant each =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    float sx, sh;
+    nc_scales(p, sx, sh);
+    int tl = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
+      const int slot = tl & 1;
+      mbar_wait(&tfull_bar[slot], (uint32_t)(tl >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * NCOL);
+      if (LAYER == 1) {
+        float acc[32];
+        tmem_ld32(taddr, acc);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[slot]);     // accumulator is in registers: the slot can be refilled
+        const long long v = (long long)tile * 128 + row;
+        if (v < p.V) {
+          const float inv = p.inv_sw1 / sx;
+          float hval[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) hval[c] = fmaxf(fmaf(acc[c], inv, __ldg(p.b1p + c)), 0.f) * sh;
+          uint4 o[8];
+          split8(hval, o[0], o[2]);            // net 0: hi chunks 0,1 | lo chunks 2,3
+          split8(hval + 8, o[1], o[3]);
+          split8(hval + 16, o[4], o[6]);       // net 1
+          split8(hval + 24, o[5], o[7]);
+          uint4* dst = reinterpret_cast<uint4*>(p.hidden + v * 64);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dst[i] = o[i];
+        }
+      } else {
+        float acc[16];
+        tmem_ld16(taddr, acc);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[slot]);
+        const int net = tile & 1;
+        const long long v = (long long)(tile >> 1) * 128 + row;
+        if (v < p.V) {
+          const float inv = p.inv_sw2 / sh;
+#pragma unroll
+          for (int d = 0; d < 9; ++d) p.partial[(size_t)(net * 9 + d) * p.V + v] = acc[d] * inv;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// max |x| (device-side activation scale of the tensor-core NC path)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, size_t n, unsigned int* __restrict__ out) {
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(x[i]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));   // non-negative floats order like their bits
+}
+
+int launch_absmax(const float* x, size_t n, unsigned int* out, cudaStream_t st) {
+  P2P_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(unsigned int), st));
+  const int blocks = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+  absmax_kernel<<<blocks, 256, 0, st>>>(x, n, out);
+  P2P_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// combine: out[a][b] = sum_net relu(b2 + sum_(ta,tb) P[net][ta*3+tb][a + (ta-1, tb-1)][b]), fused with the
+// row / column maxima of the MutualMatching that follows (rowmax[a] = max_b, colmax[b] = max_a).
+// Block = 8 A cells; the 9 neighbour offsets are block-uniform.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nc_combine_kernel(const float* __restrict__ P, int hA, int wA, int nB, float b2,
+                                                        float* __restrict__ out, float* __restrict__ rowmax,
+                                                        unsigned int* __restrict__ colmax) {
+  constexpr int R = 8;
+  __shared__ float red[8][R];
+  const int nA = hA * wA;
+  const size_t V = (size_t)nA * nB;
+  const int r0 = blockIdx.x * R;
+  float rm[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) rm[r] = -INFINITY;
+  for (int col = threadIdx.x; col < nB; col += 256) {
+    float cm = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int a = r0 + r;
+      if (a >= nA) continue;
+      const int ia = a / wA, ja = a - ia * wA;
+      float tot = 0.f;
+#pragma unroll
+      for (int net = 0; net < 2; ++net) {
+        float acc = b2;
+#pragma unroll
+        for (int d = 0; d < 9; ++d) {
+          const int i2 = ia + d / 3 - 1, j2 = ja + d % 3 - 1;
+          if (i2 >= 0 && i2 < hA && j2 >= 0 && j2 < wA)
+            acc += __ldg(P + (size_t)(net * 9 + d) * V + (size_t)(i2 * wA + j2) * nB + col);
+        }
+        tot += fmaxf(acc, 0.f);
+      }
+      out[(size_t)a * nB + col] = tot;
+      rm[r] = fmaxf(rm[r], tot);
+      cm = fmaxf(cm, tot);
+    }
+    if (colmax != nullptr) atomicMax(colmax + col, f2ord(cm));
+  }
+  if (rowmax == nullptr) return;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const float v = warp_max(rm[r]);
+    if (lane == 0) red[wid][r] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < R && r0 + threadIdx.x < nA) {
+    float v = red[0][threadIdx.x];
+#pragma unroll
+    for (int wv = 1; wv < 8; ++wv) v = fmaxf(v, red[wv][threadIdx.x]);
+    rowmax[r0 + threadIdx.x] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static float pow2_scale_for(float maxabs, float target_hi) {   // power of two s: maxabs * s in [target_hi/2, target_hi)
+  if (!(maxabs > 0.f) || !isfinite(maxabs)) return 1.f;
+  int e, et;
+  frexpf(maxabs, &e);
+  frexpf(target_hi, &et);
+  return ldexpf(1.f, et - 1 - e);
+}
+
+// element (n, k) of a [rows][64] K-major 128B-swizzled atom
+static inline size_t sw128_index(int n, int k) { return (size_t)n * 64 + ((((k >> 3) ^ (n & 7)) << 3) | (k & 7)); }
+
+int nc_umma_pack(const float* w1p, const float* b1p, const float* w2p, NcUmmaWeights& W) {
+  float m1 = 0.f, m2 = 0.f, wsum = 0.f, b1max = 0.f;
+  for (int i = 0; i < 81 * 32; ++i) {
+    m1 = fmaxf(m1, fabsf(w1p[i]));
+    m2 = fmaxf(m2, fabsf(w2p[i]));
+  }
+  for (int c = 0; c < 32; ++c) {
+    float s = 0.f;
+    for (int t = 0; t < 81; ++t) s += fabsf(w1p[t * 32 + c]);
+    wsum = fmaxf(wsum, s);
+    b1max = fmaxf(b1max, fabsf(b1p[c]));
+  }
+  const float s1 = pow2_scale_for(m1, 1024.f), s2 = pow2_scale_for(m2, 1024.f);
+  W.wsum1 = wsum * 1.0001f;
+  W.b1max = b1max;
+  W.inv_sw1 = 1.f / s1;
+  W.inv_sw2 = 1.f / s2;
+  // layer 1: [hi|lo][atom 0..1][32 rows][64]; k = tap (81 used)
+  std::vector<__half> img1((size_t)2 * 2 * 32 * 64, __float2half(0.f));
+  for (int c = 0; c < 32; ++c)
+    for (int t = 0; t < 81; ++t) {
+      const float v = w1p[t * 32 + c] * s1;
+      const __half h = __float2half_rn(v), l = __float2half_rn(v - __half2float(h));
+      const int atom = t >> 6, k = t & 63;
+      img1[(size_t)(0 * 2 + atom) * 32 * 64 + sw128_index(c, k)] = h;
+      img1[(size_t)(1 * 2 + atom) * 32 * 64 + sw128_index(c, k)] = l;
+    }
+  // layer 2: [net][hi|lo][atom 0..2][16 rows][64]; row = partial map (ta,tb) (9 used), k = (B tap - 4*atom) * 16 + channel
+  std::vector<__half> img2((size_t)2 * 2 * 3 * 16 * 64, __float2half(0.f));
+  for (int net = 0; net < 2; ++net)
+    for (int d = 0; d < 9; ++d)
+      for (int t = 0; t < 9; ++t)
+        for (int ch = 0; ch < 16; ++ch) {
+          const float v = w2p[(d * 9 + t) * 32 + net * 16 + ch] * s2;
+          const __half h = __float2half_rn(v), l = __float2half_rn(v - __half2float(h));
+          const int atom = t >> 2, k = (t & 3) * 16 + ch;
+          img2[(size_t)((net * 2 + 0) * 3 + atom) * 16 * 64 + sw128_index(d, k)] = h;
+          img2[(size_t)((net * 2 + 1) * 3 + atom) * 16 * 64 + sw128_index(d, k)] = l;
+        }
+  const size_t b1 = img1.size() * 2, b2 = img2.size() * 2;
+  if (W.blob == nullptr) {
+    if (cudaMalloc(&W.blob, b1 + b2) != cudaSuccess) {
+      cudaGetLastError();
+      set_last_error("out of device memory packing the NC weights");
+      return -3;
+    }
+  }
+  W.img1 = reinterpret_cast<__half*>(W.blob);
+  W.img2 = reinterpret_cast<__half*>(W.blob + b1);
+  P2P_CUDA_OK(cudaMemcpy(W.img1, img1.data(), b1, cudaMemcpyHostToDevice));
+  P2P_CUDA_OK(cudaMemcpy(W.img2, img2.data(), b2, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+size_t nc_umma_scratch_bytes(size_t V) { return V * 128 + 18 * V * 4 + 4096; }
+
+// x [hA*wA][hB*wB] -> out (NeighConsensus output); rowmax / colmax (optional) receive the maxima MutualMatching needs.
+// xmax: device word holding the float bits of max |x| (launch_absmax or the fused mutual_apply pass).
+int launch_neigh_consensus_umma(const float* x, int hA, int wA, int hB, int wB, const NcUmmaWeights& W, const float* b1p,
+                                float b2, const unsigned int* xmax, __half* hidden, float* partial, float* out,
+                                float* rowmax, unsigned int* colmax, int num_sms, cudaStream_t st) {
+  NcParams p;
+  memset(&p, 0, sizeof(p));
+  p.hA = hA; p.wA = wA; p.hB = hB; p.wB = wB;
+  p.nA = hA * wA; p.nB = hB * wB;
+  p.V = (long long)p.nA * p.nB;
+  p.x = x; p.xmax = xmax; p.hidden = hidden; p.partial = partial; p.b1p = b1p;
+  p.wsum1 = W.wsum1; p.b1max = W.b1max; p.inv_sw1 = W.inv_sw1; p.inv_sw2 = W.inv_sw2;
+  const long long vt = (p.V + 127) / 128;
+  P2P_REQUIRE(2 * vt < (1ll << 31), "NeighConsensus: 4D volume too large");
+  {
+    p.wimg = W.img1;
+    p.tiles = (int)vt;
+    const int smem = 4 * 2 * kNcAtom + 2 * 2 * 32 * 128 + 1024;
+    auto k = nc_umma_kernel<1>;
+    P2P_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k<<<p.tiles < num_sms ? p.tiles : num_sms, 512, smem, st>>>(p);
+    P2P_LAUNCH_OK();
+  }
+  {
+    p.wimg = W.img2;
+    p.tiles = (int)(2 * vt);
+    const int smem = 3 * 2 * kNcAtom + 2 * 2 * 3 * 16 * 128 + 1024;
+    auto k = nc_umma_kernel<2>;
+    P2P_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k<<<p.tiles < num_sms ? p.tiles : num_sms, 512, smem, st>>>(p);
+    P2P_LAUNCH_OK();
+  }
+  if (colmax != nullptr) P2P_CUDA_OK(cudaMemsetAsync(colmax, 0, sizeof(unsigned int) * p.nB, st));
+  nc_combine_kernel<<<cdiv(p.nA, 8), 256, 0, st>>>(partial, hA, wA, p.nB, b2, out, rowmax, colmax);
+  P2P_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace p2p

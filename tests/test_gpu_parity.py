@@ -224,6 +224,39 @@ def test_coarse_ksize1_vs_oracle(nets, seeded_sd):
         assert torch.equal(m.cpu(), o_m)
 
 
+@pytest.mark.parametrize('weights', ['uniform', 'consensus'])
+def test_neigh_consensus_tensor_core_vs_oracle(nets, cnets, seeded_sd, consensus_sd, weights):
+    """NeighConsensus on the tensor cores (fp16 hi/lo 3-pass, partial-map formulation, nc_umma.cu) against the oracle
+    (conv3d loop of the reference) and against the fp32 CUDA-core kernels, on odd shapes, inputs of very different
+    magnitude (device-side power-of-two scaling) and an all-zero input."""
+    from oracle import p2p_oracle as O
+    from patch2pix_b200 import _lib
+    net, sd = (cnets[1], consensus_sd) if weights == 'consensus' else (nets[1], seeded_sd)
+    h = net._ready()
+    rep = {}
+    for (hA, wA, hB, wB), amp in (((3, 4, 5, 6), 1.0), ((6, 5, 9, 11), 1e-3), ((8, 10, 8, 10), 37.0), ((15, 20, 15, 20), 1.0),
+                                  ((2, 3, 17, 40), 1.0), ((4, 4, 4, 4), 0.0)):
+        g = torch.Generator().manual_seed(hA * 100 + wB)
+        x = (torch.rand(1, 1, hA, wA, hB, wB, generator=g) - 0.1) * amp
+        ref = O.neigh_consensus(x, sd)
+        xd = x.cuda()
+        outs = {}
+        for impl in (1, 0):
+            net.set_option('nc_impl', impl)
+            out = torch.full_like(xd, float('nan'))
+            _lib.check(h.lib.p2p_neigh_consensus(h.h, _lib.ptr(xd), hA, wA, hB, wB, _lib.ptr(out), h.stream()))
+            torch.cuda.synchronize()
+            outs[impl] = out.cpu()
+        net.set_option('nc_impl', 1)
+        scale = max(ref.abs().max().item(), 1e-30)
+        rep[f'{hA}x{wA}x{hB}x{wB}_amp{amp}'] = {'tc_vs_oracle': (outs[1] - ref).abs().max().item() / scale,
+                                                'simt_vs_oracle': (outs[0] - ref).abs().max().item() / scale}
+        assert torch.isfinite(outs[1]).all()
+        np.testing.assert_allclose(outs[1].numpy(), ref.numpy(), rtol=2e-4, atol=5e-6 * max(amp, 1e-3))
+        np.testing.assert_allclose(outs[0].numpy(), ref.numpy(), rtol=2e-4, atol=5e-6 * max(amp, 1e-3))
+    _report(f'nc_tensor_core_{weights}', rep)
+
+
 def test_mutual_matching_and_unique_rows_ops():
     from oracle import p2p_oracle as O
     from patch2pix_b200.model import mutual_matching, unique_rows
