@@ -163,6 +163,15 @@ P2P_API int p2p_refine_prepare(p2p_handle_t h, const float* const* feats1, const
 P2P_API int p2p_refine(p2p_handle_t h, int which, const void* matches_in, int is_float, int n, float* matches_out,
                float* probs_out, void* stream);
 
+/* ---- image preprocessing: the tensor half of load_im_flexible (utils/datasets/preprocess.py:32-60):
+ * transforms.functional.resize(img, (ht, wt), Image.BICUBIC) -> ToTensor -> Normalize(ImageNet mean/std) for a decoded
+ * 8-bit RGB image.  Pillow's 8-bit resampling (fixed-point, antialiased bicubic, horizontal then vertical pass) is
+ * reproduced bit-exactly.  rgb_hwc: DEVICE uint8 [ho][wo][3]; out_chw: DEVICE fp32 [3][ht][wt];
+ * resized_hwc_out (optional, may be NULL): DEVICE uint8 [ht][wt][3], the resized image before normalisation.
+ * (ht, wt) come from cal_rescale_size (preprocess.py:83-91), computed by the caller. */
+P2P_API int p2p_preprocess_image(p2p_handle_t h, const uint8_t* rgb_hwc, int ho, int wo, int ht, int wt, float* out_chw,
+                         uint8_t* resized_hwc_out, void* stream);
+
 /* ---- bring-up / accuracy probe: C[M,N] = alpha * A[M,K] B[N,K]^T on the tcgen05 path with the
  * same operand format as the hot path (fp32 inputs are split to fp16 hi/lo on the device).
  * a, b, c are DEVICE fp32; K % 64 == 0. */

@@ -77,7 +77,8 @@ struct p2p_handle_s {
   NcUmmaWeights ncw;            // tensor-core NC operand images
   int opt_nc_impl = 1;          // 1: NeighConsensus on the tensor cores (nc_umma.cu); 0: fp32 CUDA-core kernels (shape-capped)
   Regressor reg[2];
-  Arena coarse, refine, feat, misc, uniq;
+  Arena coarse, refine, feat, misc, uniq, pre;
+  std::vector<PreprocessCoefs> pre_coefs;   // cached resampling tables, one per image geometry
   PairFeatures pf[2];
   bool prepared = false;
   // optional per-kernel CUDA-event profile (p2p_set_option("profile", 1))
@@ -388,6 +389,9 @@ int p2p_destroy(p2p_handle_t h) {
   h->feat.release();
   h->misc.release();
   h->uniq.release();
+  h->pre.release();
+  for (auto& c : h->pre_coefs)
+    if (c.d) cudaFree(c.d);
   for (auto& e : h->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   for (auto e : h->event_pool) cudaEventDestroy(e);
   if (h->nc_w1p) cudaFree(h->nc_w1p);
@@ -1005,6 +1009,34 @@ int p2p_refine(p2p_handle_t h, int which, const void* matches_in, int is_float, 
   }
   return run_regressor(h, R, which, 3, B, matches_in, is_float, n, B.rowmap, B.d_count, matches_out, probs_out,
                        nullptr, st);
+}
+
+int p2p_preprocess_image(p2p_handle_t h, const uint8_t* rgb_hwc, int ho, int wo, int ht, int wt, float* out_chw,
+                         uint8_t* resized_hwc_out, void* stream) {
+  P2P_ENTER(h);
+  P2P_REQUIRE(rgb_hwc && out_chw && ho > 0 && wo > 0 && ht > 0 && wt > 0, "bad argument");
+  P2P_REQUIRE((long long)ho * wo < (1ll << 28) && (long long)ht * wt < (1ll << 28), "image too large");
+  const PreprocessCoefs* C = nullptr;
+  for (const auto& c : h->pre_coefs)
+    if (c.ho == ho && c.wo == wo && c.ht == ht && c.wt == wt) C = &c;
+  if (C == nullptr) {
+    if (h->pre_coefs.size() >= 32) {            // drop the oldest table (nothing may still be reading it)
+      P2P_CUDA_OK(cudaDeviceSynchronize());
+      if (h->pre_coefs.front().d) cudaFree(h->pre_coefs.front().d);
+      h->pre_coefs.erase(h->pre_coefs.begin());
+    }
+    PreprocessCoefs c;
+    int rc = preprocess_build_coefs(ho, wo, ht, wt, c);
+    if (rc) return rc;
+    h->pre_coefs.push_back(c);
+    C = &h->pre_coefs.back();
+  }
+  int rc = h->pre.reserve((size_t)ho * wt * 3 + 4096);
+  if (rc) return rc;
+  uint8_t* tmp = (uint8_t*)h->pre.take((size_t)ho * wt * 3);
+  P2P_REQUIRE(tmp != nullptr, "scratch carve failed");
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};   // ImageNet, preprocess.py:93
+  return launch_preprocess(rgb_hwc, *C, mean, stdv, out_chw, resized_hwc_out, tmp, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int p2p_test_gemm(p2p_handle_t h, const float* a, const float* b, float* c, int M, int N, int K, int passes,

@@ -46,6 +46,16 @@ int launch_neigh_consensus_umma(const float* x, int hA, int wA, int hB, int wB, 
                                 float b2, const unsigned int* xmax, __half* hidden, float* partial, float* out,
                                 float* rowmax, unsigned int* colmax, int num_sms, cudaStream_t st);
 
+// ---- preprocess.cu: PIL-exact bicubic resize + ToTensor + Normalize (utils/datasets/preprocess.py:32-60) ----
+struct PreprocessCoefs {
+  int ho = 0, wo = 0, ht = 0, wt = 0, ksx = 0, ksy = 0;
+  size_t o_bx = 0, o_kx = 0, o_by = 0, o_ky = 0;
+  int* d = nullptr;               // device: [bounds x][coefs x][bounds y][coefs y]
+};
+int preprocess_build_coefs(int ho, int wo, int ht, int wt, PreprocessCoefs& C);
+int launch_preprocess(const uint8_t* rgb, const PreprocessCoefs& C, const float mean[3], const float stdv[3], float* out,
+                      uint8_t* resized_u8, uint8_t* tmp, cudaStream_t st);
+
 // ---- refine.cu ---------------------------------------------------------------------------------
 // Activation scale applied before the fp16 hi/lo split of the L2-normalised patch features.
 constexpr float kActScale = 4096.f;

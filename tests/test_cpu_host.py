@@ -153,3 +153,28 @@ def test_load_checkpoint_parses_the_released_file_format(tmp_path, seeded_sd):
         load_checkpoint(str(nc), device='cpu', method='nc', lprint=lines.append)
     with pytest.raises(ValueError):
         load_checkpoint(str(nc), device='cpu', method='other', lprint=lines.append)
+
+
+def test_preprocess_oracle_is_pinned_against_pillow():
+    """the numpy restatement of Pillow's 8-bit bicubic resampling (oracle/preprocess_oracle.py) equals
+    Pillow bit for bit on down-, up- and mixed scaling, and the whole load_im_flexible tensor equals the reference's
+    torchvision formulation."""
+    PIL = pytest.importorskip('PIL')
+    from PIL import Image
+    import numpy as np
+    from oracle import preprocess_oracle as PO
+    rng = np.random.RandomState(0)
+    for ho, wo, ht, wt in ((97, 131, 48, 64), (60, 80, 96, 128), (120, 160, 120, 80), (75, 100, 75, 100), (333, 500, 208, 320)):
+        img = (rng.rand(ho, wo, 3) * 255).astype(np.uint8)
+        ref = np.array(Image.fromarray(img).resize((wt, ht), Image.BICUBIC))
+        assert np.array_equal(PO.resize_bicubic_u8(img, wt, ht), ref), (ho, wo, ht, wt)
+    img = (rng.rand(375, 500, 3) * 255).astype(np.uint8)
+    got, scale = PO.load_im_flexible_array(img, 2, 16, 320)
+    wt, ht = PO.target_size(500, 375, 2, 16, 320)
+    assert (wt, ht) == (320, 224) and scale == (500 / 320, 375 / 224)
+    t = torch.from_numpy(np.array(Image.fromarray(img).resize((wt, ht), Image.BICUBIC))).permute(2, 0, 1).float().div(255)
+    t = (t - torch.tensor([0.485, 0.456, 0.406]).view(3, 1, 1)) / torch.tensor([0.229, 0.224, 0.225]).view(3, 1, 1)
+    assert np.array_equal(got, t.numpy())
+    from patch2pix_b200.preprocess import cal_rescale_size
+    for w, h, s in ((500, 375, 320), (1024, 768, 1024), (640, 480, 1000), (123, 457, 300)):
+        assert cal_rescale_size(s, w, h, 2, 1 / 16) == PO.cal_rescale_size(s, w, h, 2, 1 / 16)

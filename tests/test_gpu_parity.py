@@ -840,3 +840,24 @@ def test_backbone_graph_tf32_path(cnets, consensus_sd):
             assert dev < 2e-2, dev
     finally:
         torch.backends.cudnn.allow_tf32 = False
+
+
+def test_gpu_preprocessing_is_bit_exact():
+    """load_im_flexible's resize + ToTensor + Normalize on the GPU (p2p_preprocess_image) against Pillow /
+    torchvision's formulation (bit-exact: the resampling is integer arithmetic) and against the numpy oracle."""
+    pytest.importorskip('PIL')
+    from PIL import Image
+    from oracle import preprocess_oracle as PO
+    from patch2pix_b200.preprocess import preprocess_image
+    rng = np.random.RandomState(1)
+    for ho, wo, imsize in ((375, 500, 320), (480, 640, None), (200, 150, 1000), (768, 1024, 640), (97, 211, 160)):
+        img = (rng.rand(ho, wo, 3) * 255).astype(np.uint8)
+        out, scale, res = preprocess_image(img, 2, 16, imsize, return_resized=True)
+        want, wscale = PO.load_im_flexible_array(img, 2, 16, imsize)
+        assert scale == wscale and tuple(out.shape) == want.shape
+        ht, wt = want.shape[1:]
+        pil = np.array(Image.fromarray(img).resize((wt, ht), Image.BICUBIC))
+        assert np.array_equal(res.cpu().numpy(), pil), (ho, wo, imsize)
+        assert np.array_equal(out.cpu().numpy(), want), (ho, wo, imsize)
+    with pytest.raises(RuntimeError):
+        preprocess_image(np.zeros((10, 10, 4), np.uint8))
