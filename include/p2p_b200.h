@@ -163,6 +163,14 @@ P2P_API int p2p_refine_prepare(p2p_handle_t h, const float* const* feats1, const
 P2P_API int p2p_refine(p2p_handle_t h, int which, const void* matches_in, int is_float, int n, float* matches_out,
                float* probs_out, void* stream);
 
+/* ---- tail of estimate_matches (utils/eval/model_helper.py:97-109): inlier filter `scores > io_thres` ("keep everything
+ * if nothing passes"), row order preserved, and `upscale * matches` in float64, so that ONE device->host copy returns
+ * the final result.  fine fp32 [n,4] (NULL for eval_type 'coarse': the refined columns repeat the coarse ones), scores
+ * fp32 [n], coarse int64 [n,4], upscale4 HOST double[4] = (sx1, sy1, sx2, sy2).  packed_out DEVICE double [n*9 + 1]:
+ * rows (x1,y1,x2,y2 refined, score, x1,y1,x2,y2 coarse), packed_out[n*9] = number of rows kept. */
+P2P_API int p2p_finalize_matches(p2p_handle_t h, const float* fine, const float* scores, const int64_t* coarse, int n,
+                         float io_thres, const double* upscale4, double* packed_out, void* stream);
+
 /* ---- image preprocessing: the tensor half of load_im_flexible (utils/datasets/preprocess.py:32-60):
  * transforms.functional.resize(img, (ht, wt), Image.BICUBIC) -> ToTensor -> Normalize(ImageNet mean/std) for a decoded
  * 8-bit RGB image.  Pillow's 8-bit resampling (fixed-point, antialiased bicubic, horizontal then vertical pass) is

@@ -1011,6 +1011,14 @@ int p2p_refine(p2p_handle_t h, int which, const void* matches_in, int is_float, 
                        nullptr, st);
 }
 
+int p2p_finalize_matches(p2p_handle_t h, const float* fine, const float* scores, const int64_t* coarse, int n, float io_thres,
+                         const double* upscale4, double* packed_out, void* stream) {
+  P2P_ENTER(h);
+  P2P_REQUIRE(scores && coarse && upscale4 && packed_out && n >= 0, "bad argument");
+  return launch_finalize_matches(fine, scores, (const long long*)coarse, n, io_thres, upscale4, packed_out,
+                                 reinterpret_cast<cudaStream_t>(stream));
+}
+
 int p2p_preprocess_image(p2p_handle_t h, const uint8_t* rgb_hwc, int ho, int wo, int ht, int wt, float* out_chw,
                          uint8_t* resized_hwc_out, void* stream) {
   P2P_ENTER(h);

@@ -90,6 +90,9 @@ int launch_fc_parse(const float* pooled, const FcWeights& fc, const void* matche
                     int H1, int W2, int H2, float* matches_out, float* probs_out, float* raw_out, const int* rowmap,
                     const int* d_count, cudaStream_t st);
 
+int launch_finalize_matches(const float* fine, const float* scores, const long long* coarse, int N, float io_thres,
+                            const double up[4], double* packed, cudaStream_t st);
+
 // Tensor-core FC path helpers: pooled fp32 -> fp16 hi/lo A operand; final Linear(256,5) + parse_regressor_out.
 constexpr float kFcActScale = 16.f;
 int launch_pooled_split(const float* pooled, int n, __half* hi, __half* lo, const int* d_count, cudaStream_t st);

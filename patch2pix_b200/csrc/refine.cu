@@ -499,6 +499,65 @@ int launch_flag_risky(const void* matches_in, int is_float, const float* raw, in
 }
 
 // ------------------------------------------------------------------------------------------------
+// Tail of estimate_matches (utils/eval/model_helper.py:97-109) on the device: inlier filter
+// `scores > io_thres` (keep everything if nothing passes), order preserved, and the rescaling to original-image
+// pixels `upscale * matches` in float64 (numpy promotes float32 / int64 times a float64 array to float64).
+// packed [N][9] doubles = (x1,y1,x2,y2 refined, score, x1,y1,x2,y2 coarse); packed[N*9] = number of rows kept.
+// fine == nullptr (eval_type 'coarse'): the refined columns repeat the coarse ones.  Single block.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) finalize_matches_kernel(const float* __restrict__ fine, const float* __restrict__ scores,
+                                                               const long long* __restrict__ coarse, int N, float io_thres,
+                                                               double u0, double u1, double u2, double u3,
+                                                               double* __restrict__ packed) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base, s_any;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) { s_base = 0; s_any = 0; }
+  __syncthreads();
+  int any = 0;
+  for (int r = tid; r < N; r += 1024) any |= scores[r] > io_thres;
+  if (any) s_any = 1;
+  __syncthreads();
+  const bool keep_all = s_any == 0;
+  const double up[4] = {u0, u1, u2, u3};
+  for (int r0 = 0; r0 < N; r0 += 1024) {
+    const int r = r0 + tid;
+    const int sel = r < N && (keep_all || scores[r] > io_thres);
+    const unsigned int ball = __ballot_sync(0xffffffffu, sel);
+    if (lane == 0) s_warp[wid] = __popc(ball);
+    __syncthreads();
+    int woff = 0, tot = 0;
+    for (int w = 0; w < 32; ++w) {
+      const int c = s_warp[w];
+      if (w < wid) woff += c;
+      tot += c;
+    }
+    const int base = s_base;
+    if (sel) {
+      double* o = packed + (size_t)(base + woff + __popc(ball & ((1u << lane) - 1u))) * 9;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double c = (double)coarse[(size_t)r * 4 + j];
+        o[5 + j] = up[j] * c;
+        o[j] = fine != nullptr ? up[j] * (double)fine[(size_t)r * 4 + j] : up[j] * c;
+      }
+      o[4] = (double)scores[r];
+    }
+    __syncthreads();
+    if (tid == 0) s_base = base + tot;
+    __syncthreads();
+  }
+  if (tid == 0) packed[(size_t)N * 9] = (double)s_base;
+}
+
+int launch_finalize_matches(const float* fine, const float* scores, const long long* coarse, int N, float io_thres,
+                            const double up[4], double* packed, cudaStream_t st) {
+  finalize_matches_kernel<<<1, 1024, 0, st>>>(fine, scores, coarse, N, io_thres, up[0], up[1], up[2], up[3], packed);
+  P2P_LAUNCH_OK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // CUDA-core checker GEMM (bring-up only).  Tile 128 rows (2 patches) x 64 output channels.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) conv_gemm_simt_kernel(GemmOperands g, ConvEpilogue e) {

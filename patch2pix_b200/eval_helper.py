@@ -1,10 +1,10 @@
-"""Tensor-level mirror of the reference's matcher glue (utils/eval/model_helper.py:28-109).
+"""Mirror of the reference's matcher glue (utils/eval/model_helper.py:28-109), device-resident.
 
-Image decoding / resizing (`load_im_flexible`, PIL) is host I/O and out of scope:
-these helpers start from already normalised image tensors [1,3,H,W] plus the (sx, sy) scale factors the
-reference's loader would have returned, and reproduce the rest of `estimate_matches` exactly:
-`predict_coarse` / `predict_fine`, the `io_thres` inlier filter with its "keep everything if nothing
-passes" rule, and the rescaling of the matches to original-image pixels.
+`estimate_matches` starts from normalised image tensors [1,3,H,W] plus the (sx, sy) scale factors of the loader and
+reproduces the reference exactly -- `predict_coarse` / `predict_fine`, the `io_thres` inlier filter with its "keep
+everything if nothing passes" rule, the rescaling to original-image pixels in float64 -- but filter and rescaling run
+in one kernel and the result crosses PCIe in ONE copy.  `estimate_matches_from_files` adds the loader: only the
+file-format decode stays on the host, resize / ToTensor / Normalize run on the GPU (patch2pix_b200.preprocess).
 """
 from argparse import Namespace
 
@@ -54,25 +54,52 @@ def load_checkpoint(ckpt_path, device='cuda:0', method='patch2pix', lprint=print
     raise ValueError('Wrong method name.')
 
 
+def _finalize(net, fine, scores, coarse, io_thres, upscale):
+    """One launch + ONE device->host copy for the tail of estimate_matches (model_helper.py:97-109)."""
+    import ctypes as C
+    from . import _lib
+    h = net._handle
+    n = int(scores.shape[0])
+    dev = scores.device
+    packed = torch.empty(n * 9 + 1, dtype=torch.float64, device=dev)
+    up = (C.c_double * 4)(*[float(v) for v in upscale])
+    fine_c = fine.reshape(-1, 4).contiguous() if fine is not None else None
+    scores_c = scores.reshape(-1).contiguous()
+    coarse_c = coarse.contiguous()
+    with torch.cuda.device(dev):
+        _lib.check(h.lib.p2p_finalize_matches(h.h, _lib.ptr(fine_c), _lib.ptr(scores_c), _lib.ptr(coarse_c), n, float(io_thres),
+                                              up, _lib.ptr(packed), h.stream()))
+    host = packed.cpu().numpy()                      # the single synchronising copy
+    m = int(host[-1])
+    rows = host[:-1].reshape(n, 9)[:m]
+    return rows[:, 0:4].copy(), rows[:, 4].astype(np.float32), rows[:, 5:9].copy()
+
+
 def estimate_matches(net, im1, im2, scale1=(1.0, 1.0), scale2=(1.0, 1.0), ksize=2, ncn_thres=0.0, mutual=True,
                      io_thres=0.25, eval_type='fine'):
-    """utils/eval/model_helper.py:64-109 on image tensors -> (matches, scores, coarse_matches) numpy arrays."""
-    upscale = np.array([tuple(scale1) + tuple(scale2)])
+    """utils/eval/model_helper.py:64-109 on image tensors -> (matches, scores, coarse_matches) numpy arrays
+    (float64 matches in original-image pixels, float32 scores), with the inlier filter and the rescaling on the device
+    and a single device->host copy (the reference does three `.cpu()` round trips)."""
+    upscale = tuple(scale1) + tuple(scale2)
     im1 = im1.to(net.device)
     im2 = im2.to(net.device)
     with torch.no_grad():
         if eval_type == 'coarse':
             coarse_matches, scores = net.predict_coarse(im1, im2, ksize=ksize, ncn_thres=ncn_thres, mutual=mutual)
-            matches = upscale * coarse_matches[0].cpu().data.numpy()
-            return matches, scores[0].cpu().data.numpy(), matches
+            m, s, _ = _finalize(net, None, scores[0], coarse_matches[0], float('-inf'), upscale)
+            return m, s, m
+        if eval_type != 'fine':
+            raise ValueError("eval_type must be 'coarse' or 'fine'")
         fine_matches, fine_scores, coarse_matches = net.predict_fine(im1, im2, ksize=ksize, ncn_thres=ncn_thres,
                                                                     mutual=mutual)
-    coarse_matches = coarse_matches[0].cpu().data.numpy()
-    fine_matches = fine_matches[0].cpu().data.numpy().reshape(-1, 4)
-    fine_scores = fine_scores[0].cpu().data.numpy().reshape(-1)
-    pos_ids = np.where(fine_scores > io_thres)[0]
-    if len(pos_ids) > 0:
-        coarse_matches, matches, scores = coarse_matches[pos_ids], fine_matches[pos_ids], fine_scores[pos_ids]
-    else:
-        matches, scores = fine_matches, fine_scores
-    return upscale * matches, scores, upscale * coarse_matches
+    return _finalize(net, fine_matches[0], fine_scores[0], coarse_matches[0], io_thres, upscale)
+
+
+def estimate_matches_from_files(net, im1_path, im2_path, ksize=2, ncn_thres=0.0, mutual=True, io_thres=0.25,
+                                eval_type='fine', imsize=None):
+    """utils/eval/model_helper.py:64-72 + the above: image files in, numpy matches out.  Only the file decode runs on
+    the host; resize / ToTensor / Normalize are GPU kernels (patch2pix_b200.preprocess)."""
+    from .preprocess import load_im_flexible
+    im1, sc1 = load_im_flexible(im1_path, ksize, net.upsample, imsize=imsize, device=net.device, handle=net._handle)
+    im2, sc2 = load_im_flexible(im2_path, ksize, net.upsample, imsize=imsize, device=net.device, handle=net._handle)
+    return estimate_matches(net, im1.unsqueeze(0), im2.unsqueeze(0), sc1, sc2, ksize, ncn_thres, mutual, io_thres, eval_type)

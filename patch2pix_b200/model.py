@@ -638,8 +638,8 @@ class Patch2PixB200(nn.Module):
         feats2 = self.extract.forward_all(im2, [], early_feat=True)
         mid, _ = self.forward_fine_match(feats1, feats2, cm_, self.psize[0], self.ptype[0], self.regress_mid)
         fine, fine_p = self.forward_fine_match(feats1, feats2, mid, self.psize[1], self.ptype[1], self.regress_fine)
-        refined = fine[0].cpu().data.numpy()
-        scores = fine_p[0].cpu().data.numpy()
+        both = torch.cat([fine[0].reshape(-1, 4), fine_p[0].reshape(-1, 1)], 1).cpu().numpy()   # one device->host copy
+        refined, scores = np.ascontiguousarray(both[:, :4]), np.ascontiguousarray(both[:, 4])
         if io_thres > 0:
             pos = np.where(scores > io_thres)[0]
             if len(pos) > 0:

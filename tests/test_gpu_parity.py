@@ -861,3 +861,44 @@ def test_gpu_preprocessing_is_bit_exact():
         assert np.array_equal(out.cpu().numpy(), want), (ho, wo, imsize)
     with pytest.raises(RuntimeError):
         preprocess_image(np.zeros((10, 10, 4), np.uint8))
+
+
+def test_estimate_matches_from_files(tmp_path, consensus_sd):
+    """Image files in, matches out (utils/eval/model_helper.py:64-109): decode on the host, everything else on the GPU;
+    equals the tensor-level entry fed with the oracle's (Pillow-exact) preprocessing, and the one-copy tail equals the
+    reference's numpy formulation."""
+    pytest.importorskip('PIL')
+    from PIL import Image
+    from oracle import preprocess_oracle as PO
+    from patch2pix_b200.eval_helper import estimate_matches, estimate_matches_from_files, load_model
+    from patch2pix_b200.synth import synthetic_pair_shifted
+    net = load_model(consensus_sd)
+    im1, im2 = synthetic_pair_shifted(4, 300, 400)
+    paths = []
+    for i, im in enumerate((im1, im2)):
+        u8 = ((im[0].permute(1, 2, 0) * 0.25 + 0.5).clamp(0, 1) * 255).byte().numpy()
+        paths.append(str(tmp_path / f'im{i}.png'))
+        Image.fromarray(u8).save(paths[-1])
+    m, s, c = estimate_matches_from_files(net, paths[0], paths[1], io_thres=0.3, imsize=320)
+    ts, scs = [], []
+    for pth in paths:
+        t, sc = PO.load_im_flexible_array(np.asarray(Image.open(pth).convert('RGB')), 2, net.upsample, 320)
+        ts.append(torch.from_numpy(t).unsqueeze(0))
+        scs.append(sc)
+    m2, s2, c2 = estimate_matches(net, ts[0], ts[1], scs[0], scs[1], io_thres=0.3)
+    assert m.dtype == np.float64 and s.dtype == np.float32 and c.dtype == np.float64
+    assert np.array_equal(m, m2) and np.array_equal(s, s2) and np.array_equal(c, c2)
+    # the device-side tail against the reference's numpy formulation on the raw predict_fine outputs
+    with torch.no_grad():
+        fine, fs, cm = net.predict_fine(ts[0].cuda(), ts[1].cuda(), ksize=2)
+    fine, fs, cm = fine[0].cpu().numpy().reshape(-1, 4), fs[0].cpu().numpy().reshape(-1), cm[0].cpu().numpy()
+    up = np.array([scs[0] + scs[1]])
+    n_all = len(fs)
+    pos = np.where(fs > 0.3)[0]
+    if len(pos) > 0:
+        fine, fs, cm = fine[pos], fs[pos], cm[pos]
+    assert np.array_equal(m, up * fine) and np.array_equal(s, fs) and np.array_equal(c, up * cm)
+    assert len(m) > 20
+    # nothing passes -> everything is kept
+    m3, s3, _ = estimate_matches(net, ts[0], ts[1], scs[0], scs[1], io_thres=2.0)
+    assert len(m3) == n_all and len(s3) == n_all
