@@ -99,7 +99,7 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock / power / throttle reasons through NVML every 5 ms while the timed region runs
+    """Samples SM clock / power / throttle reasons through NVML every 8 ms while the timed region runs
     (the region can be ~0.1 s long: nvidia-smi's process start-up alone would miss it)."""
 
     def __init__(self, index):
@@ -116,10 +116,13 @@ class ClockSampler(threading.Thread):
             h = N.nvmlDeviceGetHandleByIndex(phys)
             self.sm_max = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
             reasons = getattr(N, 'nvmlDeviceGetCurrentClocksEventReasons', None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+            i, pw = 0, 0.0
             while not self._halt.is_set():
-                self.rows.append((float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), N.nvmlDeviceGetPowerUsage(h) / 1e3,
-                                  int(reasons(h))))
-                self._halt.wait(0.005)
+                if i % 8 == 0:                       # power changes slowly; keep the per-sample work (GIL time) small
+                    pw = N.nvmlDeviceGetPowerUsage(h) / 1e3
+                self.rows.append((float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), pw, int(reasons(h))))
+                i += 1
+                self._halt.wait(0.008)
         except Exception as e:   # NVML missing: report it, never fake a sample
             self.err = repr(e)
 
@@ -135,7 +138,7 @@ class ClockSampler(threading.Thread):
             allbits |= r[2]
         return {'sm_mhz': statistics.median(r[0] for r in self.rows), 'sm_min_mhz': min(r[0] for r in self.rows),
                 'sm_max_mhz': self.sm_max, 'power_w_max': max(r[1] for r in self.rows), 'samples': len(self.rows),
-                'interval_ms': 5, 'source': 'nvml', 'reasons': [n for n, b in bits.items() if allbits & b]}
+                'interval_ms': 8, 'source': 'nvml', 'reasons': [n for n, b in bits.items() if allbits & b]}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -477,7 +480,7 @@ def run_ours(args):
         if dom:
             ach = kern[dom]['algorithmic_tflops']
             gemm_ms = sum(kern[k]['ms_per_launch'] * kern[k]['launches'] for k in gemm_names)
-            kname = 'umma_conv1_fused_kernel' if (dom.startswith('conv1') and not dom.endswith('band') and opts['fuse_gather'] == 1) \
+            kname = ('umma_conv1_tma_kernel' if opts['fuse_gather'] == 3 else 'umma_conv1_fused_kernel') if (dom.startswith('conv1') and not dom.endswith('band') and opts['fuse_gather'] in (1, 3)) \
                 else 'umma_gemm_kernel'
             traffic = load_traffic().get(dom if kname == 'umma_gemm_kernel' else 'conv1_fused')
             roofline = {'kernel': f'{kname} ({dom})', 'bound': 'tensor', 'achieved': ach, 'peak': peak,

@@ -62,7 +62,8 @@ struct p2p_handle_s {
   int device = 0;
   int num_sms = 148;
   int opt_mid_passes = 3, opt_fine_passes = 1, opt_corr_passes = 3, opt_seg_len = 3, opt_gemm_impl = 0, opt_num_sms = 0;
-  int opt_mid_band = 35;  // thousandths of a pixel; 0 = pure 3-pass mid stage
+  int opt_mid_band = 26;  // thousandths of a pixel (2x the largest 1-pass/3-pass mid difference over 125k distinct coordinates,
+                          // profiles/r02_band_stats.json); 0 = pure 3-pass mid stage
   int opt_gemm_pair = 35;   // bitmask of launches that use the CTA-pair (cta_group::2) GEMM kernel:
                             // 1: 1-pass convs, 2: 3-pass convs, 4: FC, 8: correlation, 16: p2p_test_gemm,
                             // 32: fused-gather conv1
@@ -769,6 +770,9 @@ int p2p_refine_prepare(p2p_handle_t h, const float* const* feats1, const float* 
     const size_t px = (size_t)Hs[s] * Ws[s];
     need += (px / 4 * 64 + px / 16 * 64 + px / 64 * 128) * 6 + (px + px / 4 + px / 16 + px / 64) * 4 + 32768;
   }
+  const bool want_map = h->opt_fuse_gather == 3;
+  if (want_map)
+    for (int s = 0; s < 2; ++s) need += (size_t)(Hs[s] + 2 * kMapPad) * (Ws[s] + 2 * kMapPad) * (512 + 8) + 4096;
   int rc = h->feat.reserve(need);
   if (rc) return rc;
   const int chans[3] = {64, 64, 128};
@@ -785,8 +789,18 @@ int p2p_refine_prepare(p2p_handle_t h, const float* const* feats1, const float* 
       pf.nhwc16[l] = (__half*)h->feat.take((size_t)(Hs[s] / ds) * (Ws[s] / ds) * chans[l] * 2);
       P2P_REQUIRE(pf.nhwc[l] != nullptr && pf.nhwc16[l] != nullptr, "scratch carve failed");
     }
+    pf.wmap = pf.rgbn = nullptr;
+    if (want_map) {
+      const size_t pxp = (size_t)(Hs[s] + 2 * kMapPad) * (Ws[s] + 2 * kMapPad);
+      pf.wmap = (__half*)h->feat.take(pxp * 512);
+      pf.rgbn = (__half*)h->feat.take(pxp * 8);
+      P2P_REQUIRE(pf.wmap != nullptr && pf.rgbn != nullptr, "scratch carve failed");
+    }
+  }
+  {
     ProfScope ps(h, P2P_PROF_PREP, st);
-    if ((rc = launch_feature_prep(s == 0 ? feats1 : feats2, Hs[s], Ws[s], pf, st))) return rc;
+    if ((rc = launch_feature_prep_pair(feats1, feats2, Hs, Ws, h->pf, st))) return rc;
+    if (want_map && (rc = launch_window_map(h->pf, st))) return rc;
   }
   h->prepared = true;
   return 0;
@@ -809,7 +823,10 @@ int run_regressor(p2p_handle_s* h, Regressor& R, int which, int passes, const Re
   const bool lo = passes == 3;
   const int kb = rowmap != nullptr ? P2P_PROF_GATHER_BAND : (which == 0 ? P2P_PROF_GATHER_MID : P2P_PROF_GATHER_FINE);
   int rc;
-  const bool fused = passes == 1 && rowmap == nullptr && h->opt_fuse_gather && h->opt_gemm_impl == 0;
+  const bool mapped = passes == 1 && rowmap == nullptr && h->opt_fuse_gather == 3 && h->opt_gemm_impl == 0;
+  const bool fused = passes == 1 && rowmap == nullptr && h->opt_fuse_gather && h->opt_gemm_impl == 0 && !mapped;
+  if (mapped) P2P_REQUIRE(h->pf[0].wmap != nullptr && h->pf[1].wmap != nullptr,
+                          "fuse_gather = 3 needs p2p_refine_prepare to have run with the same option");
   if (!fused) {
     ProfScope ps(h, kb, st);
     if ((rc = launch_patch_gather(h->pf[0], h->pf[1], matches_in, is_float, n, B.p_hi, lo ? B.p_lo : nullptr, B.r_hi,
@@ -878,7 +895,32 @@ int run_regressor(p2p_handle_s* h, Regressor& R, int which, int passes, const Re
         p.fg.generation = h->opt_fuse_gather == 2 ? 1 : 2;
       }
       ProfScope ps(h, kb + 1, st);
-      if ((rc = launch_umma_gemm(p, EPI_CONV1, passes, sms(h), st, fused))) return rc;
+      if (mapped) {
+        Conv1TmaParams q;
+        memset(&q, 0, sizeof(q));
+        const uint32_t wbox[2] = {64, 128};
+        if ((rc = make_tmap_fp16(&q.b_hi, R.w1_hi, 2, bd, bs, wbox))) return rc;
+        for (int s2 = 0; s2 < 2; ++s2) {
+          const uint64_t Wp = (uint64_t)h->pf[s2].W + 2 * kMapPad, Hp = (uint64_t)h->pf[s2].H + 2 * kMapPad;
+          const uint64_t md[3] = {256, Wp, Hp};
+          const uint64_t ms[2] = {512, Wp * 512};
+          const uint32_t mb[3] = {64, 16, 16};       // 8 elements at traversal stride 2 (box = N * stride)
+          const uint32_t me[3] = {1, 2, 2};
+          if ((rc = make_tmap_fp16(&q.wm.map[s2], h->pf[s2].wmap, 3, md, ms, mb, me))) return rc;
+          q.wm.rgbn[s2] = h->pf[s2].rgbn;
+          q.wm.H[s2] = h->pf[s2].H;
+          q.wm.W[s2] = h->pf[s2].W;
+        }
+        q.wm.matches = matches_in;
+        q.wm.is_float = is_float;
+        q.nsteps = kConv1Steps;
+        memcpy(q.steps, R.steps1, sizeof(R.steps1));
+        q.m_tiles = (n + 1) / 2;
+        q.epi = p.epi;
+        if ((rc = launch_conv1_tma(q, sms(h), st))) return rc;
+      } else if ((rc = launch_umma_gemm(p, EPI_CONV1, passes, sms(h), st, fused))) {
+        return rc;
+      }
     }
     {  // conv2
       const uint64_t ad[5] = {512, 8, 8, 1, npad};

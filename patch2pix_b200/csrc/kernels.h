@@ -71,9 +71,16 @@ struct PairFeatures {             // per image: channels-last copies + squared-n
   __half* nhwc16[3];              // same, fp16, each pixel divided by its own level norm sqrt(nsq[l+1])
   float* nsq[4];                  // levels 0..3: [h][w]
   int H, W;
+  // full-resolution window map (fuse_gather = 3): every pixel's patch-normalised 256-channel vector, replicate-padded by
+  // kMapPad pixels, [H + 2 pad][W + 2 pad][256] fp16; rgbn: the normalised rgb triple [..][4] fp16
+  __half* wmap;
+  __half* rgbn;
 };
+constexpr int kMapPad = 16;
+int launch_window_map(const PairFeatures pf[2], cudaStream_t st);
 
-int launch_feature_prep(const float* const feats[4], int H, int W, PairFeatures& out, cudaStream_t st);
+int launch_feature_prep_pair(const float* const feats1[4], const float* const feats2[4], const int H[2], const int W[2],
+                             PairFeatures out[2], cudaStream_t st);
 // rowmap/d_count (optional, device): process only rows rowmap[0..*d_count) (patch slot b <- row rowmap[b]).
 int launch_patch_gather(const PairFeatures& f1, const PairFeatures& f2, const void* matches, int is_float, int N,
                         __half* p_hi, __half* p_lo, __half* rgb_hi, __half* rgb_lo, const int* rowmap,

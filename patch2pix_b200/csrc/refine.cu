@@ -17,18 +17,36 @@ namespace p2p {
 // ------------------------------------------------------------------------------------------------
 // feature prep
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) nchw_to_nhwc_nsq_kernel(const float* __restrict__ in, int C, int npx,
-                                                              float* __restrict__ out, float* __restrict__ nsq,
-                                                              __half* __restrict__ out16) {
+// One launch for both images and all four levels: segment = (image, level); level 0 (rgb, C = 3) only needs its
+// squared-norm map, levels 1..3 additionally get channels-last fp32 / level-normalised fp16 copies.
+struct PrepSegment {
+  const float* in;     // [C][npx]
+  float* out;          // [npx][C] (nullptr for level 0)
+  __half* out16;       // [npx][C], every pixel divided by its own norm (nullptr for level 0)
+  float* nsq;          // [npx]
+  int C, npx, block0;  // first block of this segment
+};
+struct PrepArgs {
+  PrepSegment seg[8];
+  int nseg;
+};
+
+__global__ void __launch_bounds__(256) feature_prep_kernel(const __grid_constant__ PrepArgs a) {
   extern __shared__ float tile[];  // [C][33]
   __shared__ float part[8][32];
   __shared__ float rinv[32];
+  int si = 0;
+#pragma unroll
+  for (int i = 1; i < 8; ++i)
+    if (i < a.nseg && (int)blockIdx.x >= a.seg[i].block0) si = i;
+  const PrepSegment& g = a.seg[si];
+  const int C = g.C, npx = g.npx;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int px0 = blockIdx.x * 32;
+  const int px0 = ((int)blockIdx.x - g.block0) * 32;
   const int px = px0 + lane;
   float s = 0.f;
   for (int c = wid; c < C; c += 8) {
-    const float v = px < npx ? __ldg(in + (size_t)c * npx + px) : 0.f;
+    const float v = px < npx ? __ldg(g.in + (size_t)c * npx + px) : 0.f;
     tile[c * 33 + lane] = v;
     s = fmaf(v, v, s);
   }
@@ -38,47 +56,120 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_nsq_kernel(const float* __re
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) t += part[w][lane];
-    nsq[px] = t;
+    g.nsq[px] = t;
     rinv[lane] = rsqrtf(t + 1e-30f);
   }
+  if (g.out == nullptr) return;      // block-uniform
   __syncthreads();
   for (int i = threadIdx.x; i < 32 * C; i += 256) {
     const int p = i / C, c = i - p * C;
     if (px0 + p < npx) {
       const float v = tile[c * 33 + p];
-      out[(size_t)(px0 + p) * C + c] = v;
-      out16[(size_t)(px0 + p) * C + c] = __float2half_rn(v * rinv[p]);   // |.| <= 1: no fp16 range issues
+      g.out[(size_t)(px0 + p) * C + c] = v;
+      g.out16[(size_t)(px0 + p) * C + c] = __float2half_rn(v * rinv[p]);   // |.| <= 1: no fp16 range issues
     }
   }
 }
 
-__global__ void nsq_rgb_kernel(const float* __restrict__ img, int npx, float* __restrict__ nsq) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= npx) return;
-  float s = 0.f;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const float v = __ldg(img + (size_t)c * npx + i);
-    s = fmaf(v, v, s);
+int launch_feature_prep_pair(const float* const feats1[4], const float* const feats2[4], const int H[2], const int W[2],
+                             PairFeatures out[2], cudaStream_t st) {
+  PrepArgs a;
+  memset(&a, 0, sizeof(a));
+  const int chans[4] = {3, 64, 64, 128};
+  int blocks = 0;
+  for (int s = 0; s < 2; ++s) {
+    const float* const* f = s == 0 ? feats1 : feats2;
+    out[s].img = f[0];
+    out[s].H = H[s];
+    out[s].W = W[s];
+    for (int l = 0; l < 4; ++l) {
+      PrepSegment& g = a.seg[a.nseg++];
+      const int ds = 1 << l;
+      g.in = f[l];
+      g.C = chans[l];
+      g.npx = (H[s] / ds) * (W[s] / ds);
+      g.nsq = out[s].nsq[l];
+      g.out = l > 0 ? out[s].nhwc[l - 1] : nullptr;
+      g.out16 = l > 0 ? out[s].nhwc16[l - 1] : nullptr;
+      g.block0 = blocks;
+      blocks += cdiv(g.npx, 32);
+    }
   }
-  nsq[i] = s;
+  feature_prep_kernel<<<blocks, 256, sizeof(float) * 128 * 33, st>>>(a);
+  P2P_LAUNCH_OK();
+  return 0;
 }
 
-int launch_feature_prep(const float* const feats[4], int H, int W, PairFeatures& out, cudaStream_t st) {
-  out.img = feats[0];
-  out.H = H;
-  out.W = W;
-  nsq_rgb_kernel<<<cdiv(H * W, 256), 256, 0, st>>>(feats[0], H * W, out.nsq[0]);
-  P2P_LAUNCH_OK();
-  const int chans[3] = {64, 64, 128};
-  for (int l = 0; l < 3; ++l) {
-    const int ds = 2 << l;
-    const int npx = (H / ds) * (W / ds);
-    const int C = chans[l];
-    nchw_to_nhwc_nsq_kernel<<<cdiv(npx, 32), 256, sizeof(float) * C * 33, st>>>(feats[l + 1], C, npx, out.nhwc[l],
-                                                                               out.nsq[l + 1], out.nhwc16[l]);
-    P2P_LAUNCH_OK();
+// ------------------------------------------------------------------------------------------------
+// Window map (fuse_gather = 3).  The 259-channel L2-normalised vector of a window pixel depends only on its absolute
+// (clamped) image position (select_local_patch_feats clamps per level, networks/utils.py:22-23, which equals clamping
+// the full-resolution coordinate first), so it is computed ONCE per image pixel: map[y + pad][x + pad][0..255] =
+// kActScale * concat(l1, l2, l3)(y, x) / sqrt(sum_c f^2 + 1e-6), replicate-padded.  The conv1 implicit GEMM then reads
+// every tap of every patch as one strided TMA box.  One warp per padded pixel; lane = one 16-byte channel chunk.
+// Arithmetic identical to the in-kernel producers of umma_conv1_fused_kernel (bit-identical A operand).
+// ------------------------------------------------------------------------------------------------
+struct WindowMapArgs {
+  const float* img[2];
+  const __half* nhwc16[2][3];
+  const float* nsq[2][4];
+  __half* wmap[2];
+  __half* rgbn[2];
+  int H[2], W[2];
+  long long px0[3];     // first padded-pixel index of image 1; total
+};
+
+__global__ void __launch_bounds__(256) window_map_kernel(const __grid_constant__ WindowMapArgs a) {
+  const int lane = threadIdx.x & 31;
+  long long q = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (q >= a.px0[2]) return;
+  const int si = q >= a.px0[1] ? 1 : 0;
+  q -= a.px0[si];
+  const int W = a.W[si], H = a.H[si], Wp = W + 2 * kMapPad;
+  const int yp = (int)(q / Wp), xp = (int)(q - (long long)yp * Wp);
+  const int Y = min(max(yp - kMapPad, 0), H - 1), X = min(max(xp - kMapPad, 0), W - 1);
+  float t = 0.f;
+#pragma unroll
+  for (int l = 0; l < 4; ++l) t += __ldg(a.nsq[si][l] + (size_t)(Y >> l) * (W >> l) + (X >> l));
+  const float dinv = __fdiv_rn(kActScale, sqrtf(t + 1e-6f));
+  const int lvl = lane < 8 ? 0 : (lane < 16 ? 1 : 2);
+  const int sh = lvl + 1, C = lvl == 2 ? 128 : 64;
+  const int coff = (lane < 16 ? (lane & 7) : (lane - 16)) * 8;
+  const int px = (Y >> sh) * (W >> sh) + (X >> sh);
+  const float sc = dinv * sqrtf(__ldg(a.nsq[si][lvl + 1] + px) + 1e-30f);       // undo the per-level normalisation
+  uint4 v = __ldg(reinterpret_cast<const uint4*>(a.nhwc16[si][lvl] + (size_t)px * C + coff));
+  __half2* h2 = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h2[i]);
+    h2[i] = __floats2half2_rn(f.x * sc, f.y * sc);
   }
+  reinterpret_cast<uint4*>(a.wmap[si] + (size_t)q * 256)[lane] = v;
+  if (lane < 3) {
+    const float r = __ldg(a.img[si] + ((size_t)lane * H + Y) * W + X) * dinv;
+    a.rgbn[si][(size_t)q * 4 + lane] = __float2half_rn(r);
+  } else if (lane == 3) {
+    a.rgbn[si][(size_t)q * 4 + 3] = __float2half_rn(0.f);
+  }
+}
+
+int launch_window_map(const PairFeatures pf[2], cudaStream_t st) {
+  WindowMapArgs a;
+  memset(&a, 0, sizeof(a));
+  long long tot = 0;
+  for (int s = 0; s < 2; ++s) {
+    a.img[s] = pf[s].img;
+    for (int l = 0; l < 3; ++l) a.nhwc16[s][l] = pf[s].nhwc16[l];
+    for (int l = 0; l < 4; ++l) a.nsq[s][l] = pf[s].nsq[l];
+    a.wmap[s] = pf[s].wmap;
+    a.rgbn[s] = pf[s].rgbn;
+    a.H[s] = pf[s].H;
+    a.W[s] = pf[s].W;
+    a.px0[s] = tot;
+    tot += (long long)(pf[s].H + 2 * kMapPad) * (pf[s].W + 2 * kMapPad);
+  }
+  a.px0[2] = tot;
+  window_map_kernel<<<(unsigned)((tot + 7) / 8), 256, 0, st>>>(a);
+  P2P_LAUNCH_OK();
   return 0;
 }
 

@@ -785,6 +785,233 @@ __global__ void __launch_bounds__(512, 1) umma_conv1_fused_kernel(const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------
+// conv1 (1-pass) fed by strided TMA boxes of the per-image window maps (fuse_gather = 3).
+// The patch-normalised 256-channel vector of every image pixel is computed once per pair (window_map_kernel), so a
+// conv tap of one patch is ONE cp.async.bulk.tensor box {64 ch, 8 px stride 2, 8 px stride 2} of the replicate-padded
+// map: no producer warps, no lookup tables, no per-k-step gather latency.  Only two things are left for the four
+// "aux" warps: (a) the conv's zero padding -- window pixel -1 must contribute 0, but the box holds the neighbouring
+// image pixel there -- is restored by zeroing the <= 15 affected rows per patch after the box has landed (taps with
+// tx = 0 or ty = 0); (b) the rgb k-step (54 real K values) is an im2col of the normalised rgb map built with plain
+// loads.  Cluster of two CTAs = 4 patches x 512 channels (tcgen05.mma.cta_group::2, M = 256); every CTA loads its own
+// 2 patches and its own half of the weights to its own shared memory / its own TMA barrier; its aux warps then
+// (fix up and) arrive on the LEADER's operand barrier, which the MMA issuer waits on.
+// 384 threads: warp 0 TMA, 1 MMA, 2 TMEM alloc, 4..7 epilogue, 8..11 aux.  4 stages x (16 KB A + 2 x 16 KB weights).
+// Same MMA sequence per output element as umma_conv1_fused_kernel on a bit-identical A operand -> bit-identical y1.
+// ------------------------------------------------------------------------------------------------
+constexpr int kC1Stages = 4;
+constexpr int kC1StageBytes = kATile + kBTile;
+
+__global__ void __launch_bounds__(384, 1) umma_conv1_tma_kernel(const __grid_constant__ Conv1TmaParams p) {
+  constexpr uint32_t IDESC = make_idesc_f16(256, 256);
+  constexpr int BH = kBTile / 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_tma[kC1Stages];    // local: this CTA's A boxes + weight halves have landed
+  __shared__ __align__(8) uint64_t full_mma[kC1Stages];    // leader's: both CTAs' operands are ready (8 arrivals)
+  __shared__ __align__(8) uint64_t empty_bar[kC1Stages];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_units = p.epi.n_patches;
+  const int rank = (int)cluster_ctarank();
+  const int cta0 = (int)(blockIdx.x >> 1), ctas = (int)(gridDim.x >> 1);
+  const int total_tiles = (p.m_tiles + 1) / 2;
+  const int nsteps = p.nsteps;
+  const WindowMaps& wm = p.wm;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.b_hi);
+    tma_prefetch_desc(&wm.map[0]);
+    tma_prefetch_desc(&wm.map[1]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kC1Stages; ++i) {
+      mbar_init(&full_tma[i], 1);
+      mbar_init(&full_mma[i], 8);      // 4 aux warps x 2 CTAs
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair(&tmem_base_smem, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  // window origin of patch n in padded map coordinates: window pixel (wy, wx) lives at (oy + wy, ox + wx).
+  // Truncation = `.long()` (networks/utils.py:19); clamping the origin to [-7, W + 8] leaves every clamped window
+  // pixel unchanged (beyond that all of them sit on the border pixel) and keeps the boxes inside the padded map.
+  auto origin = [&](int n, int j) -> int {
+    if (n >= n_units) n = 0;      // past the end (odd tile counts): any valid patch, the epilogue discards the rows
+    int v;
+    if (wm.is_float) v = (int)reinterpret_cast<const float*>(wm.matches)[(size_t)n * 4 + j];
+    else v = (int)reinterpret_cast<const long long*>(wm.matches)[(size_t)n * 4 + j];
+    const int lim = (j & 1) ? wm.H[j >> 1] : wm.W[j >> 1];
+    v = v < -7 ? -7 : (v > lim + 8 ? lim + 8 : v);
+    return v - 8 + kMapPad;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int ctile = cta0; ctile < total_tiles; ctile += ctas) {
+        const int tile = ctile * 2 + rank;
+        int o[2][4];
+#pragma unroll
+        for (int pp = 0; pp < 2; ++pp)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[pp][j] = origin(tile * 2 + pp, j);
+        for (int ks = 0; ks < nsteps; ++ks, ++it) {
+          const int s = it % kC1Stages;
+          mbar_wait(&empty_bar[s], ((uint32_t)(it / kC1Stages) & 1u) ^ 1u);
+          const KStep k = p.steps[ks];
+          uint8_t* st = smem + (size_t)s * kC1StageBytes;
+          mbar_expect_tx(&full_tma[s], k.kind == 0 ? kATile + kBTile : kBTile);
+          tma_load_2d(&p.b_hi, &full_tma[s], st + kATile, k.bk, rank * 128);
+          tma_load_2d(&p.b_hi, &full_tma[s], st + kATile + BH, k.bk, 256 + rank * 128);
+          if (k.kind == 0) {
+            const int ty = (k.plane & 2) ? 1 : (k.y < 0 ? 0 : 2), tx = (k.plane & 1) ? 1 : (k.x < 0 ? 0 : 2);
+            const int chunk = k.c0 >> 6, si = chunk >> 2, c0 = (chunk & 3) * 64;
+#pragma unroll
+            for (int pp = 0; pp < 2; ++pp)
+              tma_load_3d(&wm.map[si], &full_tma[s], st + pp * 8192, c0, o[pp][2 * si] - 1 + tx, o[pp][2 * si + 1] - 1 + ty);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA) =====================
+    if (lane == 0 && rank == 0) {
+      int it = 0, t = 0;
+      for (int ctile = cta0; ctile < total_tiles; ctile += ctas, ++t) {
+        const uint32_t tph = (uint32_t)t & 1u;
+        for (int ks = 0; ks < nsteps; ++ks, ++it) {
+          const int s = it % kC1Stages;
+          mbar_wait(&full_mma[s], (uint32_t)(it / kC1Stages) & 1u);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * kC1StageBytes);
+          const uint64_t a = make_sw128_desc(sa);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (ks == 0) {
+              mbar_wait(&tempty_bar[h], tph ^ 1u);
+              tc_fence_after();
+            }
+            const uint64_t b = make_sw128_desc(sa + kATile + h * BH);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16_pair(tmem_base + (uint32_t)h * 256u, a + 2 * kk, b + 2 * kk, IDESC, (ks > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[s]);
+          if (ks + 1 == nsteps) {
+            umma_commit_pair(&tfull_bar[0]);
+            umma_commit_pair(&tfull_bar[1]);
+          }
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== aux warps: zero-padding fix-up (warp 8) and the rgb im2col k-step (all four) =====================
+    const int row = threadIdx.x - 256;               // 0..127: tile row owned in the rgb step
+    int it = 0;
+    for (int ctile = cta0; ctile < total_tiles; ctile += ctas) {
+      const int tile = ctile * 2 + rank;
+      for (int ks = 0; ks < nsteps; ++ks, ++it) {
+        const int s = it % kC1Stages;
+        const uint32_t ph = (uint32_t)(it / kC1Stages) & 1u;
+        const KStep k = p.steps[ks];
+        uint8_t* st = smem + (size_t)s * kC1StageBytes;
+        if (k.kind == 0) {
+          // every aux warp follows every stage (wait + arrive): parity waits are only valid within one ring
+          // revolution, so no warp may run ahead of -- or fall behind -- the pipeline
+          mbar_wait(&full_tma[s], ph);
+          const bool zx = !(k.plane & 1) && k.x < 0, zy = !(k.plane & 2) && k.y < 0;      // tap tx = 0 / ty = 0
+          if (zx || zy) {
+            const int r = threadIdx.x - 256;          // one tile row per aux thread
+            if ((zx && (r & 7) == 0) || (zy && ((r >> 3) & 7) == 0)) {
+              uint4* d = reinterpret_cast<uint4*>(st + r * 128);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) d[c] = make_uint4(0, 0, 0, 0);
+            }
+            fence_proxy_async();
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&full_mma[s]);
+        } else {
+          // rgb im2col row: k = tap*6 + img*3 + ch (54 used, rest zero); window pixel -1 = conv zero padding
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          const int pp = row >> 6, oy = (row >> 3) & 7, ox = row & 7;
+          const int n = tile * 2 + pp;
+          __align__(16) __half hv[64];
+#pragma unroll
+          for (int i = 0; i < 64; ++i) hv[i] = __float2half_rn(0.f);
+#pragma unroll
+          for (int si = 0; si < 2; ++si) {
+            const int bx = origin(n, 2 * si), by = origin(n, 2 * si + 1);
+            const int Wp = wm.W[si] + 2 * kMapPad;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const int wx = 2 * ox - 1 + tap % 3, wy = 2 * oy - 1 + tap / 3;
+              if (wx >= 0 && wy >= 0 && n < n_units) {
+                const uint2 q = __ldg(reinterpret_cast<const uint2*>(wm.rgbn[si] + ((size_t)(by + wy) * Wp + bx + wx) * 4));
+                const __half* hq = reinterpret_cast<const __half*>(&q);
+                hv[tap * 6 + si * 3 + 0] = hq[0];
+                hv[tap * 6 + si * 3 + 1] = hq[1];
+                hv[tap * 6 + si * 3 + 2] = hq[2];
+              }
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(st + row * 128 + ((c ^ (row & 7)) << 4)) = reinterpret_cast<const uint4*>(hv)[c];
+          fence_proxy_async();
+          mbar_wait(&full_tma[s], ph);            // this CTA's weight halves
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&full_mma[s]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: 4 warps, one TMEM lane quadrant each, 512 columns =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int t = 0;
+    for (int ctile = cta0; ctile < total_tiles; ctile += ctas, ++t) {
+      const int tile = ctile * 2 + rank;
+      const uint32_t tph = (uint32_t)t & 1u;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait(&tfull_bar[h], tph);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 256);
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          float v[32];
+          tmem_ld32(taddr + c * 32, v);
+          epilogue_piece<EPI_CONV1>(p.epi, n_units, tile, row, h * 256 + c * 32, v);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&tempty_bar[h]);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -812,6 +1039,7 @@ struct TmapKey {
   uint64_t dims[5];
   uint64_t strides[4];
   uint32_t box[5];
+  uint32_t es[5];
   bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
 };
 struct TmapEntry {
@@ -824,12 +1052,12 @@ thread_local int g_tmap_next = 0;
 }  // namespace
 
 int make_tmap_fp16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box) {
+                   const uint32_t* box, const uint32_t* estrides) {
   TmapKey key;
   memset(&key, 0, sizeof(key));
   key.base = base;
   key.rank = rank;
-  for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; }
+  for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; key.es[i] = estrides ? estrides[i] : 1; }
   for (int i = 0; i + 1 < rank; ++i) key.strides[i] = strides_bytes[i];
   for (const TmapEntry& e : g_tmap_cache)
     if (e.key == key) {
@@ -847,7 +1075,7 @@ int make_tmap_fp16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   for (int i = 0; i < rank; ++i) {
     gd[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = estrides ? estrides[i] : 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
@@ -962,6 +1190,31 @@ int launch_umma_gemm(const UmmaGemmParams& p, int epi, int passes, int num_sms, 
   }
   set_last_error("umma gemm: unknown epilogue");
   return -1;
+}
+
+int launch_conv1_tma(const Conv1TmaParams& p, int num_sms, cudaStream_t st) {
+  P2P_REQUIRE(p.nsteps > 0 && p.m_tiles > 0, "conv1 (window-map TMA): empty problem");
+  const int smem = kC1Stages * kC1StageBytes + 1024;
+  auto kern = umma_conv1_tma_kernel;
+  P2P_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int ptiles = (p.m_tiles + 1) / 2;
+  const int max_clusters = num_sms >= 2 ? num_sms / 2 : 1;
+  const int clusters = ptiles < max_clusters ? ptiles : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * clusters));
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  P2P_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
+  P2P_LAUNCH_OK();
+  return 0;
 }
 
 }  // namespace p2p

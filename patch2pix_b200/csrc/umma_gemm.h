@@ -39,6 +39,15 @@ struct FusedGather {
   int generation;                 // 2: 128x512 tiles + lookup tables (default); 1: first version (128x256 tiles)
 };
 
+// conv1 fed by strided TMA boxes of the per-image window maps (fuse_gather = 3)
+struct WindowMaps {
+  CUtensorMap map[2];             // [H + 2 pad][W + 2 pad][256] fp16 per image; box = 64 ch x 8 (stride 2) x 8 (stride 2)
+  const __half* rgbn[2];          // [H + 2 pad][W + 2 pad][4]
+  int H[2], W[2];
+  const void* matches;
+  int is_float;
+};
+
 struct UmmaGemmParams {
   CUtensorMap a_main_hi, a_main_lo, a_rgb_hi, a_rgb_lo, b_hi, b_lo;
   KStep steps[kMaxKSteps];
@@ -53,8 +62,19 @@ struct UmmaGemmParams {
   FusedGather fg;
 };
 
+struct Conv1TmaParams {
+  CUtensorMap b_hi;               // weights [512][73*64], 128-row boxes
+  WindowMaps wm;
+  KStep steps[kMaxKSteps];
+  int nsteps;
+  int m_tiles;                    // 128-row tiles (2 patches)
+  UmmaEpilogue epi;
+};
+int launch_conv1_tma(const Conv1TmaParams& p, int num_sms, cudaStream_t st);
+
+// estrides (optional): traversal strides; with stride s the box must be N * s to load N elements.
 int make_tmap_fp16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box);
+                   const uint32_t* box, const uint32_t* estrides = nullptr);
 int launch_umma_gemm(const UmmaGemmParams& p, int epi, int passes, int num_sms, cudaStream_t st, bool fused = false);
 
 }  // namespace p2p

@@ -25,7 +25,7 @@ def preprocess_image(rgb, k_size=2, upsample=16, imsize=None, device='cuda:0', h
     """The tensor half of load_im_flexible (preprocess.py:41-60) for a decoded RGB uint8 image [H,W,3]
     (numpy array, CPU or CUDA tensor) -> (img [3,ht,wt] float32 on `device`, scale (wo/wt, ho/ht))."""
     if isinstance(rgb, np.ndarray):
-        rgb = torch.from_numpy(np.ascontiguousarray(rgb))
+        rgb = torch.from_numpy(np.array(rgb, copy=True, order='C'))     # own, writable copy (PIL arrays are read-only)
     if rgb.dtype != torch.uint8 or rgb.dim() != 3 or rgb.shape[2] != 3:
         raise RuntimeError('preprocess_image expects an RGB uint8 image [H,W,3]')
     device = torch.device(device)
