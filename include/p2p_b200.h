@@ -77,9 +77,9 @@ P2P_API int p2p_set_regressor_weights(p2p_handle_t h, int which, const p2p_regre
  * "mid_band" (thousandths of a pixel, default 26 = 2x the largest 1-pass/3-pass difference measured over 125k DISTINCT
  * coordinates, profiles/r02_band_stats.json; with mid_passes = 3 every row is first computed 1-pass and
  * only rows with a coordinate within the band of an integer -- where trunc(mid) could differ from the
- * reference -- are re-computed 3-pass; 0 = 3-pass for every row), "fuse_gather" (1: 1-pass conv1 launches
- * gather their A tiles in producer warps instead of reading a materialised patch tensor; 2 = first-generation
- * fused kernel, 0 = separate gather kernel + TMA, 3 = per-image window map + strided TMA boxes, no producer warps),
+ * reference -- are re-computed 3-pass; 0 = 3-pass for every row), "fuse_gather" (conv1 A operand of the 1-pass launches; default 3 = per-image window map + strided TMA boxes, no
+ * producer warps; 1 = gathered in producer warps; 2 = first-generation fused kernel; 0 = separate gather kernel + TMA
+ * of a materialised patch tensor; all four give bit-identical results except 0, which skips one fp16 rounding),
  * "nc_impl" (default 1: NeighConsensus on the tensor cores, nc_umma.cu; 0: fp32 CUDA-core kernels, B grid <= 3072 cells), "fc_impl" (default 1: the 512-512 and 512-256 Linear layers run on
  * the tensor cores, 3-pass; 0: fp32 CUDA-core FC kernel), "gemm_pair" (bitmask of GEMM launches that run
  * on the CTA-pair kernel -- tcgen05.mma.cta_group::2, one M=256 tile over the two SMs of a TPC, bit-identical

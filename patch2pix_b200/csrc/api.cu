@@ -68,8 +68,9 @@ struct p2p_handle_s {
                             // 1: 1-pass convs, 2: 3-pass convs, 4: FC, 8: correlation, 16: p2p_test_gemm,
                             // 32: fused-gather conv1
   int opt_fc_impl = 1;      // 1: the two big Linear layers on the tensor cores (3-pass); 0: CUDA-core FC kernel
-  int opt_fuse_gather = 1;  // 1: 1-pass conv1 gathers its A tiles in producer warps (128x512 tiles, lookup tables; no patch
-                            // tensor in HBM); 2: first-generation fused kernel (128x256 tiles, producer-bound); 0: gather + TMA
+  int opt_fuse_gather = 3;  // conv1 A operand of the 1-pass launches: 3 (default): strided TMA boxes of a per-image window map
+                            // (umma_conv1_tma_kernel); 1: gathered by producer warps (128x512 tiles, lookup tables); 2: first-
+                            // generation fused kernel (128x256 tiles); 0: separate gather kernel + TMA of the patch tensor
   const int* last_band_count = nullptr;  // device counter of the last risk-band subset
   unsigned long long* band_totals = nullptr;   // device: {band rows, rows} summed over mid-stage calls
   bool nc_set = false;
@@ -616,8 +617,9 @@ int p2p_coarse(p2p_handle_t h, const float* feat1, const float* feat2, int c, in
     const bool lo = h->opt_corr_passes == 3;
     {
       ProfScope ps(h, P2P_PROF_L2NORM, st);
-      if ((rc = launch_l2norm_perm_kmajor(feat1, a_hi, lo ? a_lo : nullptr, c, h1, w1, ksize, st))) return rc;
-      if ((rc = launch_l2norm_perm_kmajor(feat2, b_hi, lo ? b_lo : nullptr, c, h2, w2, ksize, st))) return rc;
+      if ((rc = launch_l2norm_perm_kmajor_pair(feat1, feat2, a_hi, lo ? a_lo : nullptr, b_hi, lo ? b_lo : nullptr, c, h1, w1, h2,
+                                               w2, ksize, st)))
+        return rc;
     }
     ProfScope ps(h, P2P_PROF_CORR, st);
     if ((rc = corr_umma(h, a_hi, a_lo, b_hi, b_lo, c, n1, n2, n1pad, n2pad, ksize, pooled, delta_code_out, st)))
@@ -827,7 +829,7 @@ int run_regressor(p2p_handle_s* h, Regressor& R, int which, int passes, const Re
   const bool fused = passes == 1 && rowmap == nullptr && h->opt_fuse_gather && h->opt_gemm_impl == 0 && !mapped;
   if (mapped) P2P_REQUIRE(h->pf[0].wmap != nullptr && h->pf[1].wmap != nullptr,
                           "fuse_gather = 3 needs p2p_refine_prepare to have run with the same option");
-  if (!fused) {
+  if (!fused && !mapped) {
     ProfScope ps(h, kb, st);
     if ((rc = launch_patch_gather(h->pf[0], h->pf[1], matches_in, is_float, n, B.p_hi, lo ? B.p_lo : nullptr, B.r_hi,
                                   lo ? B.r_lo : nullptr, rowmap, d_count, st)))

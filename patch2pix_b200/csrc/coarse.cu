@@ -122,45 +122,88 @@ __global__ void __launch_bounds__(256) corr_pool_kernel(const float* __restrict_
   }
 }
 
-// K-major fp16 hi/lo output for the tcgen05 correlation: one warp per output position.
+// K-major fp16 hi/lo output for the tcgen05 correlation.  Block = 32 consecutive output positions x all channels:
+// coalesced reads along the positions (NCHW input), transposed through shared memory, 64-byte row segments out.
+// Both images in one launch (blockIdx.y).
+struct L2NormArgs {
+  const float* in[2];
+  __half* hi[2];
+  __half* lo[2];
+  int h[2], w[2];
+};
+
 template <int KS>
-__global__ void __launch_bounds__(256) l2norm_perm_kmajor_kernel(const float* __restrict__ in, __half* __restrict__ hi,
-                                                                __half* __restrict__ lo, int C, int h, int w) {
-  const int n = h * w;
-  const int lane = threadIdx.x & 31;
-  const int q = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (q >= n) return;
-  int pos;
-  if (KS == 2) {
-    const int wp = w >> 1;
-    const int cell = q >> 2, m = q & 3;
-    const int pi = cell / wp, pj = cell - pi * wp;
-    pos = (2 * pi + (m >> 1)) * w + 2 * pj + (m & 1);
-  } else {
-    pos = q;
+__global__ void __launch_bounds__(256) l2norm_perm_kmajor_kernel(const __grid_constant__ L2NormArgs a, int C) {
+  extern __shared__ float tile[];      // [C][33]
+  __shared__ float part[8][32];
+  __shared__ float dinv[32];
+  const int im = blockIdx.y;
+  const int h = a.h[im], w = a.w[im], n = h * w;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int q0 = blockIdx.x * 32;
+  if (q0 >= n) return;
+  const int q = q0 + lane;
+  int pos = 0;
+  if (q < n) {
+    if (KS == 2) {
+      const int wp = w >> 1;
+      const int cell = q >> 2, m = q & 3;
+      const int pi = cell / wp, pj = cell - pi * wp;
+      pos = (2 * pi + (m >> 1)) * w + 2 * pj + (m & 1);
+    } else {
+      pos = q;
+    }
   }
+  const float* in = a.in[im];
   float s = 0.f;
-  for (int c = lane; c < C; c += 32) {
-    const float v = __ldg(in + (size_t)c * n + pos);
+  for (int c = wid; c < C; c += 8) {
+    const float v = q < n ? __ldg(in + (size_t)c * n + pos) : 0.f;
+    tile[c * 33 + lane] = v;
     s = fmaf(v, v, s);
   }
-  s = warp_sum(s);
-  const float d = sqrtf(s + 1e-6f);
-  for (int c = lane; c < C; c += 32) {
-    const float v = __fdiv_rn(__ldg(in + (size_t)c * n + pos), d) * kActScale;
-    const __half hh = __float2half_rn(v);
-    hi[(size_t)q * C + c] = hh;
-    if (lo != nullptr) lo[(size_t)q * C + c] = __float2half_rn(v - __half2float(hh));
+  part[wid][lane] = s;
+  __syncthreads();
+  if (wid == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][lane];
+    dinv[lane] = sqrtf(t + 1e-6f);
+  }
+  __syncthreads();
+  __half* hi = a.hi[im];
+  __half* lo = a.lo[im];
+  for (int i = threadIdx.x; i < 32 * (C / 2); i += 256) {
+    const int p = i / (C / 2), c = (i - p * (C / 2)) * 2;
+    if (q0 + p >= n) continue;
+    const float d = dinv[p];
+    const float v0 = __fdiv_rn(tile[c * 33 + p], d) * kActScale, v1 = __fdiv_rn(tile[(c + 1) * 33 + p], d) * kActScale;
+    const __half2 hh = __floats2half2_rn(v0, v1);
+    *reinterpret_cast<__half2*>(hi + (size_t)(q0 + p) * C + c) = hh;
+    if (lo != nullptr) {
+      const float2 f = __half22float2(hh);
+      *reinterpret_cast<__half2*>(lo + (size_t)(q0 + p) * C + c) = __floats2half2_rn(v0 - f.x, v1 - f.y);
+    }
   }
 }
 
-int launch_l2norm_perm_kmajor(const float* in, __half* hi, __half* lo, int C, int h, int w, int ksize,
-                              cudaStream_t st) {
-  const int n = h * w;
-  if (ksize == 2)
-    l2norm_perm_kmajor_kernel<2><<<cdiv(n, 8), 256, 0, st>>>(in, hi, lo, C, h, w);
-  else
-    l2norm_perm_kmajor_kernel<1><<<cdiv(n, 8), 256, 0, st>>>(in, hi, lo, C, h, w);
+int launch_l2norm_perm_kmajor_pair(const float* in1, const float* in2, __half* hi1, __half* lo1, __half* hi2, __half* lo2,
+                                   int C, int h1, int w1, int h2, int w2, int ksize, cudaStream_t st) {
+  P2P_REQUIRE(C % 2 == 0 && C <= 1024, "l2norm: channel count must be even and at most 1024");
+  L2NormArgs a;
+  a.in[0] = in1; a.in[1] = in2;
+  a.hi[0] = hi1; a.hi[1] = hi2;
+  a.lo[0] = lo1; a.lo[1] = lo2;
+  a.h[0] = h1; a.w[0] = w1; a.h[1] = h2; a.w[1] = w2;
+  const int nmax = h1 * w1 > h2 * w2 ? h1 * w1 : h2 * w2;
+  dim3 grid(cdiv(nmax, 32), 2);
+  const size_t smem = sizeof(float) * C * 33;
+  if (ksize == 2) {
+    P2P_CUDA_OK(cudaFuncSetAttribute(l2norm_perm_kmajor_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    l2norm_perm_kmajor_kernel<2><<<grid, 256, smem, st>>>(a, C);
+  } else {
+    P2P_CUDA_OK(cudaFuncSetAttribute(l2norm_perm_kmajor_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    l2norm_perm_kmajor_kernel<1><<<grid, 256, smem, st>>>(a, C);
+  }
   P2P_LAUNCH_OK();
   return 0;
 }
@@ -294,9 +337,17 @@ __global__ void __launch_bounds__(256) mutual_apply_kernel(const float* __restri
     o = __fmul_rn(v, __fmul_rn(ra, rb));
     out[i] = o;
   }
-  if (absmax != nullptr) {      // warp-uniform
+  if (absmax != nullptr) {      // block-uniform: one atomic per block (non-negative floats order like their bits)
+    __shared__ float s_m[8];
     const float m = warp_max(fabsf(o));
-    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(absmax, __float_as_uint(m));
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = s_m[0];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) t = fmaxf(t, s_m[i]);
+      if (t > 0.f) atomicMax(absmax, __float_as_uint(t));
+    }
   }
 }
 

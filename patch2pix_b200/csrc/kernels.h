@@ -7,7 +7,8 @@ namespace p2p {
 // ---- coarse.cu ---------------------------------------------------------------------------------
 int launch_l2norm_perm(const float* in, float* out, int C, int h, int w, int ksize, cudaStream_t st);
 // K-major fp16 hi/lo variant for the tensor-core correlation: out[q][c] = split(kActScale * f/|f|)
-int launch_l2norm_perm_kmajor(const float* in, __half* hi, __half* lo, int C, int h, int w, int ksize, cudaStream_t st);
+int launch_l2norm_perm_kmajor_pair(const float* in1, const float* in2, __half* hi1, __half* lo1, __half* hi2, __half* lo2,
+                                   int C, int h1, int w1, int h2, int w2, int ksize, cudaStream_t st);
 int launch_split_rows(const float* in, __half* hi, __half* lo, size_t n, float scale, cudaStream_t st);
 int launch_delta_pack(const long long* di, const long long* dj, const long long* dk, const long long* dl, size_t n,
                       int ks, uint8_t* code, cudaStream_t st);

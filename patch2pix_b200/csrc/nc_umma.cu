@@ -31,7 +31,6 @@
 // two TMEM accumulator slots so that the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <math.h>
 
-#include <type_traits>
 #include <vector>
 
 #include "kernels.h"
@@ -81,36 +80,39 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
   lo = *reinterpret_cast<uint4*>(l);
 }
 
-template <int LAYER>
-__global__ void __launch_bounds__(512, 1) nc_umma_kernel(const __grid_constant__ NcParams p) {
-  constexpr int ATOMS = LAYER == 1 ? 2 : 3;        // swizzle atoms (64 K values) per tile
-  constexpr int STAGES = LAYER == 1 ? 4 : 3;       // multiple of ATOMS: stage index == atom index (mod ring)
-  constexpr int NCOL = LAYER == 1 ? 32 : 16;       // accumulator columns
-  constexpr int STAGE_BYTES = 2 * kNcAtom;         // A_hi + A_lo
-  constexpr int WATOM = NCOL * 128;                // bytes of one weight atom
-  constexpr int WBYTES = (LAYER == 1 ? 2 * 2 : 2 * 2 * 3) * WATOM;
-  constexpr uint32_t IDESC = make_idesc_f16(128, NCOL);
-  static_assert(STAGES % ATOMS == 0, "stage <-> atom mapping must be static");
+// ------------------------------------------------------------------------------------------------
+// layer 1.  Tile = (A cell a, 128 consecutive B cells).  The 9 A-neighbours' B segments (with a one-row halo) are
+// staged in shared memory with coalesced loads; four producer warps (one tile row per thread) then build the 81-tap
+// im2col row from shared memory, scale, split to fp16 hi/lo and store the swizzled operand chunks.
+// 384 threads (warp 1 MMA, 2 TMEM, 4..7 epilogue, 8..11 producers), 2 CTAs per SM (2 x 32 KB operand stages).
+// ------------------------------------------------------------------------------------------------
+constexpr int kL1Stages = 2;
 
+__global__ void __launch_bounds__(384, 2) nc_l1_umma_kernel(const __grid_constant__ NcParams p) {
+  constexpr int STAGE_BYTES = 2 * kNcAtom;         // A_hi + A_lo of one atom
+  constexpr int WATOM = 32 * 128;
+  constexpr uint32_t IDESC = make_idesc_f16(128, 32);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* wsm = smem + STAGES * STAGE_BYTES;
-  __shared__ __align__(8) uint64_t full_bar[STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  uint8_t* wsm = smem + kL1Stages * STAGE_BYTES;                          // [hi|lo][atom] weight images, 16 KB
+  float* xs = reinterpret_cast<float*>(wsm + 4 * WATOM);                  // [9][span]
+  __shared__ __align__(8) uint64_t full_bar[kL1Stages];
+  __shared__ __align__(8) uint64_t empty_bar[kL1Stages];
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles = p.tiles;
+  const int TB = (p.nB + 127) >> 7;
+  const int span = 128 + 2 * p.wB + 2;
 
-  // zero the operand ring (chunks the producers never write must read as zero) and stage the weights
-  for (int i = threadIdx.x; i < STAGES * STAGE_BYTES / 16; i += 512) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = threadIdx.x; i < WBYTES / 16; i += 512)
+  for (int i = threadIdx.x; i < kL1Stages * STAGE_BYTES / 16; i += 384) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < 4 * WATOM / 16; i += 384)
     reinterpret_cast<uint4*>(wsm)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], 256);
+    for (int i = 0; i < kL1Stages; ++i) {
+      mbar_init(&full_bar[i], 128);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -120,34 +122,31 @@ __global__ void __launch_bounds__(512, 1) nc_umma_kernel(const __grid_constant__
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, 64);
-  fence_proxy_async();               // generic-proxy writes above -> visible to the tensor core (async proxy)
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 1) {
-    // ===================== MMA issuer =====================
     if (lane == 0) {
       int it = 0, tl = 0;
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
         const int slot = tl & 1;
         mbar_wait(&tempty_bar[slot], ((uint32_t)(tl >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(slot * NCOL);
-        const int net = LAYER == 2 ? (tile & 1) : 0;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(slot * 32);
         uint32_t acc = 0u;
 #pragma unroll
-        for (int atom = 0; atom < ATOMS; ++atom, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&full_bar[s], (uint32_t)(it / STAGES) & 1u);
+        for (int atom = 0; atom < 2; ++atom, ++it) {
+          const int s = it % kL1Stages;
+          mbar_wait(&full_bar[s], (uint32_t)(it / kL1Stages) & 1u);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
           const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + kNcAtom);
-          // weight image: layer 1 [hi|lo][atom]; layer 2 [net][hi|lo][atom]
-          const uint32_t wb = smem_u32(wsm) + (uint32_t)((LAYER == 1 ? atom : (net * 2 * 3 + atom)) * WATOM);
-          const uint64_t w_hi = make_sw128_desc(wb), w_lo = make_sw128_desc(wb + (uint32_t)(ATOMS * WATOM));
-          const int nk = LAYER == 1 ? (atom == 0 ? 4 : 2) : (atom < 2 ? 4 : 1);   // K16 slices that hold data
+          const uint32_t wb = smem_u32(wsm) + (uint32_t)(atom * WATOM);
+          const uint64_t w_hi = make_sw128_desc(wb), w_lo = make_sw128_desc(wb + 2 * WATOM);
+          const int nk = atom == 0 ? 4 : 2;           // taps 64..80 live in the first two K16 slices of atom 1
           for (int kk = 0; kk < nk; ++kk) {
             umma_f16(d_tmem, a_lo + 2 * kk, w_hi + 2 * kk, IDESC, acc);
             acc = 1u;
@@ -160,163 +159,242 @@ __global__ void __launch_bounds__(512, 1) nc_umma_kernel(const __grid_constant__
       }
     }
   } else if (warp >= 8) {
-    // ===================== im2col producers (256 threads: row = ptid & 127, part = ptid >> 7) =====================
-    const int ptid = threadIdx.x - 256;
-    const int r = ptid & 127;
-    const int part = ptid >> 7;        // warp-uniform
+    // ===================== producers: 128 threads, one tile row each =====================
+    const int r = threadIdx.x - 256;
     float sx, sh;
     nc_scales(p, sx, sh);
     int it = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      if (LAYER == 1) {
-        const long long v = (long long)tile * 128 + r;
-        const bool rv = v < p.V;
-        const int a = rv ? (int)(v / p.nB) : 0, b = rv ? (int)(v - (long long)a * p.nB) : 0;
-        const int ia = a / p.wA, ja = a - ia * p.wA, k = b / p.wB, l = b - k * p.wB;
-        // validity bits of the 12 single-axis taps: [0..2] A rows, [3..5] A cols, [6..8] B rows, [9..11] B cols
-        unsigned m = 0;
-        if (rv) {
-          m = (ia > 0 ? 1u : 0u) | 2u | (ia + 1 < p.hA ? 4u : 0u) | (ja > 0 ? 8u : 0u) | 16u | (ja + 1 < p.wA ? 32u : 0u) |
-              (k > 0 ? 64u : 0u) | 128u | (k + 1 < p.hB ? 256u : 0u) | (l > 0 ? 512u : 0u) | 1024u |
-              (l + 1 < p.wB ? 2048u : 0u);
+      const int a = tile / TB, b0 = (tile - a * TB) << 7;
+      const int ia = a / p.wA, ja = a - ia * p.wA;
+      // stage the 9 A-neighbour segments [b0 - wB - 1, b0 + 128 + wB + 1) (zero outside the volume), pre-scaled by sx
+      asm volatile("bar.sync 1, 128;" ::: "memory");          // everyone is done reading the previous tile's segments
+      for (int d = 0; d < 9; ++d) {
+        const int i2 = ia + d / 3 - 1, j2 = ja + d % 3 - 1;
+        const bool av = i2 >= 0 && i2 < p.hA && j2 >= 0 && j2 < p.wA;
+        const float* src = p.x + (size_t)(av ? i2 * p.wA + j2 : 0) * p.nB;
+        for (int j = r; j < span; j += 128) {
+          const int b = b0 - p.wB - 1 + j;
+          xs[d * span + j] = (av && b >= 0 && b < p.nB) ? __ldg(src + b) * sx : 0.f;
         }
-        const float* xc = p.x + (rv ? v : 0);
-        const long long oA = (long long)p.wA * p.nB, oB = p.nB;
-        const int oK = p.wB;
-        auto body = [&](auto PART) {
-          constexpr int PT = decltype(PART)::value;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int b = b0 + r;
+      const bool rv = b < p.nB;
+      const int k = rv ? b / p.wB : 0, l = rv ? b - k * p.wB : 0;
+      // validity of the B-side taps: bits 0..2 rows (k-1, k, k+1), bits 3..5 columns (l-1, l, l+1)
+      const unsigned m = rv ? ((k > 0 ? 1u : 0u) | 2u | (k + 1 < p.hB ? 4u : 0u) | (l > 0 ? 8u : 0u) | 16u | (l + 1 < p.wB ? 32u : 0u)) : 0u;
+      const float* xr = xs + r;
 #pragma unroll
-          for (int atom = 0; atom < 2; ++atom, ++it) {
-            const int s = it % STAGES;
-            constexpr int NCH = 4;                 // chunks of 8 taps per thread and atom (atom 1: 2 resp. 1 hold data)
-            float val[NCH][8];
+      for (int atom = 0; atom < 2; ++atom, ++it) {
+        const int s = it % kL1Stages;
+        mbar_wait(&empty_bar[s], ((uint32_t)(it / kL1Stages) & 1u) ^ 1u);
+        uint8_t* st = smem + (size_t)s * STAGE_BYTES + r * 128;
 #pragma unroll
-            for (int cc = 0; cc < NCH; ++cc) {
-              const int c = PT + 2 * cc;           // chunk inside the atom
+        for (int c = 0; c < (atom == 0 ? 8 : 3); ++c) {          // chunks of 8 taps; atom 1 holds taps 64..80 (+ zeros)
+          float val[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int t = (atom * 8 + c) * 8 + i;      // compile-time after unrolling
-                float f = 0.f;
-                if (t < 81) {
-                  const int ta = t / 27, tb = (t / 9) % 3, tk = (t / 3) % 3, tl = t % 3;
-                  const unsigned need = (1u << ta) | (8u << tb) | (64u << tk) | (512u << tl);
-                  if ((m & need) == need)
-                    f = __ldg(xc + (ta - 1) * oA + (tb - 1) * oB + (tk - 1) * oK + (tl - 1)) * sx;
-                }
-                val[cc][i] = f;
-              }
+          for (int i = 0; i < 8; ++i) {
+            const int t = (atom * 8 + c) * 8 + i;                // compile-time after unrolling
+            float f = 0.f;
+            if (t < 81) {
+              const int d = t / 9, tk = (t / 3) % 3, tl = t % 3;
+              const unsigned need = (1u << tk) | (8u << tl);
+              f = ((m & need) == need) ? xr[d * span + tk * p.wB + tl] : 0.f;     // A-invalid segments hold zeros
             }
-            mbar_wait(&empty_bar[s], ((uint32_t)(it / STAGES) & 1u) ^ 1u);
-            uint8_t* st = smem + (size_t)s * STAGE_BYTES + r * 128;
-#pragma unroll
-            for (int cc = 0; cc < NCH; ++cc) {
-              const int c = PT + 2 * cc;
-              if (atom == 1 && c > 2) continue;    // taps >= 88: those chunks stay zero
-              uint4 hi, lo;
-              split8(val[cc], hi, lo);
-              *reinterpret_cast<uint4*>(st + ((c ^ (r & 7)) << 4)) = hi;
-              *reinterpret_cast<uint4*>(st + kNcAtom + ((c ^ (r & 7)) << 4)) = lo;
-            }
-            fence_proxy_async();
-            mbar_arrive(&full_bar[s]);
+            val[i] = f;
           }
-        };
-        if (part == 0) body(std::integral_constant<int, 0>{});
-        else body(std::integral_constant<int, 1>{});
-      } else {
-        const int net = tile & 1;
-        const long long v = (long long)(tile >> 1) * 128 + r;
-        const bool rv = v < p.V;
-        const int b = rv ? (int)(v % p.nB) : 0;
-        const int k = b / p.wB, l = b - k * p.wB;
-        const __half* base = p.hidden + (rv ? v : 0) * 64 + net * 32;
-#pragma unroll
-        for (int atom = 0; atom < 3; ++atom, ++it) {
-          const int s = it % STAGES;
-          uint4 q[2][4];
-          // taps of this thread: atoms 0,1 -> local taps 2*part, 2*part+1 (hi and lo lines); atom 2 -> tap 8, part 0 = hi, 1 = lo
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int t = atom < 2 ? atom * 4 + 2 * part + j : 8;
-            const int tk = t / 3, tl = t - tk * 3;
-            const int k2 = k + tk - 1, l2 = l + tl - 1;
-            const bool ok = rv && k2 >= 0 && k2 < p.hB && l2 >= 0 && l2 < p.wB && (atom < 2 || j == 0);
-            const uint4* src = reinterpret_cast<const uint4*>(base + ((long long)(tk - 1) * p.wB + (tl - 1)) * 64);
-            if (atom < 2) {
-#pragma unroll
-              for (int c = 0; c < 4; ++c) q[j][c] = ok ? __ldg(src + c) : make_uint4(0, 0, 0, 0);   // hi0 hi1 lo0 lo1
-            } else {
-              q[j][0] = ok ? __ldg(src + 2 * part) : make_uint4(0, 0, 0, 0);
-              q[j][1] = ok ? __ldg(src + 2 * part + 1) : make_uint4(0, 0, 0, 0);
-            }
-          }
-          mbar_wait(&empty_bar[s], ((uint32_t)(it / STAGES) & 1u) ^ 1u);
-          uint8_t* st = smem + (size_t)s * STAGE_BYTES + r * 128;
-          if (atom < 2) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const int c0 = 2 * (2 * part + j);      // chunk of the tap's channels 0..7; +1: channels 8..15
-              *reinterpret_cast<uint4*>(st + ((c0 ^ (r & 7)) << 4)) = q[j][0];
-              *reinterpret_cast<uint4*>(st + (((c0 + 1) ^ (r & 7)) << 4)) = q[j][1];
-              *reinterpret_cast<uint4*>(st + kNcAtom + ((c0 ^ (r & 7)) << 4)) = q[j][2];
-              *reinterpret_cast<uint4*>(st + kNcAtom + (((c0 + 1) ^ (r & 7)) << 4)) = q[j][3];
-            }
-          } else {
-            uint8_t* dst = st + part * kNcAtom;
-            *reinterpret_cast<uint4*>(dst + ((0 ^ (r & 7)) << 4)) = q[0][0];
-            *reinterpret_cast<uint4*>(dst + ((1 ^ (r & 7)) << 4)) = q[0][1];
-          }
-          fence_proxy_async();
-          mbar_arrive(&full_bar[s]);
+          uint4 hi, lo;
+          split8(val, hi, lo);
+          *reinterpret_cast<uint4*>(st + ((c ^ (r & 7)) << 4)) = hi;
+          *reinterpret_cast<uint4*>(st + kNcAtom + ((c ^ (r & 7)) << 4)) = lo;
         }
+        fence_proxy_async();
+        mbar_arrive(&full_bar[s]);
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue: 4 warps, one TMEM lane quadrant each =====================
+    // ===================== epilogue =====================
     const int q = warp & 3;
     const int row = q * 32 + lane;
     float sx, sh;
     nc_scales(p, sx, sh);
+    const float inv = p.inv_sw1 / sx;
     int tl = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
       const int slot = tl & 1;
       mbar_wait(&tfull_bar[slot], (uint32_t)(tl >> 1) & 1u);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * NCOL);
-      if (LAYER == 1) {
-        float acc[32];
-        tmem_ld32(taddr, acc);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[slot]);     // accumulator is in registers: the slot can be refilled
-        const long long v = (long long)tile * 128 + row;
-        if (v < p.V) {
-          const float inv = p.inv_sw1 / sx;
-          float hval[32];
+      float acc[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 32), acc);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[slot]);     // accumulator is in registers: the slot can be refilled
+      const int a = tile / TB, b = ((tile - a * TB) << 7) + row;
+      if (b < p.nB) {
+        const long long v = (long long)a * p.nB + b;
+        uint4 o[8];
 #pragma unroll
-          for (int c = 0; c < 32; ++c) hval[c] = fmaxf(fmaf(acc[c], inv, __ldg(p.b1p + c)), 0.f) * sh;
-          uint4 o[8];
-          split8(hval, o[0], o[2]);            // net 0: hi chunks 0,1 | lo chunks 2,3
-          split8(hval + 8, o[1], o[3]);
-          split8(hval + 16, o[4], o[6]);       // net 1
-          split8(hval + 24, o[5], o[7]);
-          uint4* dst = reinterpret_cast<uint4*>(p.hidden + v * 64);
+        for (int g = 0; g < 4; ++g) {                    // 8 channels at a time: net 0 ch 0-7, 8-15, net 1 ch 0-7, 8-15
+          float hval[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dst[i] = o[i];
+          for (int c = 0; c < 8; ++c) hval[c] = fmaxf(fmaf(acc[g * 8 + c], inv, __ldg(p.b1p + g * 8 + c)), 0.f) * sh;
+          split8(hval, o[(g >> 1) * 4 + (g & 1)], o[(g >> 1) * 4 + 2 + (g & 1)]);   // [net][hi0 hi1 lo0 lo1]
         }
-      } else {
-        float acc[16];
-        tmem_ld16(taddr, acc);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[slot]);
-        const int net = tile & 1;
-        const long long v = (long long)(tile >> 1) * 128 + row;
-        if (v < p.V) {
-          const float inv = p.inv_sw2 / sh;
+        uint4* dst = reinterpret_cast<uint4*>(p.hidden + v * 64);
 #pragma unroll
-          for (int d = 0; d < 9; ++d) p.partial[(size_t)(net * 9 + d) * p.V + v] = acc[d] * inv;
+        for (int i = 0; i < 8; ++i) dst[i] = o[i];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// layer 2.  Tile = 128 consecutive 4D cells, BOTH nets.  Producers: 8 lanes per tile row, lane = one 16-byte chunk
+// of the 128-byte hidden line [net0 hi0 hi1 lo0 lo1 | net1 hi0 hi1 lo0 lo1], so every warp load instruction reads four
+// complete lines; the chunk goes to the (net, hi|lo) operand tile of the tap's K range.
+// 512 threads (warp 1 MMA, 2 TMEM, 4..7 epilogue, 8..15 producers); 3 stages x 64 KB (stage == atom).
+// ------------------------------------------------------------------------------------------------
+constexpr int kL2Stages = 3;
+
+__global__ void __launch_bounds__(512, 1) nc_l2_umma_kernel(const __grid_constant__ NcParams p) {
+  constexpr int STAGE_BYTES = 4 * kNcAtom;         // [net][hi|lo] x 16 KB
+  constexpr int WATOM = 16 * 128;
+  constexpr uint32_t IDESC = make_idesc_f16(128, 16);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* wsm = smem + kL2Stages * STAGE_BYTES;   // [net][hi|lo][atom] weight images, 24 KB
+  __shared__ __align__(8) uint64_t full_bar[kL2Stages];
+  __shared__ __align__(8) uint64_t empty_bar[kL2Stages];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles = p.tiles;
+
+  for (int i = threadIdx.x; i < kL2Stages * STAGE_BYTES / 16; i += 512) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < 12 * WATOM / 16; i += 512)
+    reinterpret_cast<uint4*>(wsm)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kL2Stages; ++i) {
+      mbar_init(&full_bar[i], 8);                  // one arrival per producer warp
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_smem, 64);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 1) {
+    if (lane == 0) {
+      int it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
+        const int slot = tl & 1;
+        mbar_wait(&tempty_bar[slot], ((uint32_t)(tl >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int atom = 0; atom < 3; ++atom, ++it) {
+          const int s = it % kL2Stages;
+          mbar_wait(&full_bar[s], (uint32_t)(it / kL2Stages) & 1u);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+          const int nk = atom < 2 ? 4 : 1;           // atom 2 holds tap 8 only (one K16 slice)
+#pragma unroll
+          for (int net = 0; net < 2; ++net) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)(slot * 32 + net * 16);
+            const uint64_t a_hi = make_sw128_desc(sa + (net * 2) * kNcAtom), a_lo = make_sw128_desc(sa + (net * 2 + 1) * kNcAtom);
+            const uint32_t wb = smem_u32(wsm) + (uint32_t)((net * 6 + atom) * WATOM);
+            const uint64_t w_hi = make_sw128_desc(wb), w_lo = make_sw128_desc(wb + 3 * WATOM);
+            for (int kk = 0; kk < nk; ++kk) umma_f16(d_tmem, a_lo + 2 * kk, w_hi + 2 * kk, IDESC, (atom > 0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < nk; ++kk) umma_f16(d_tmem, a_hi + 2 * kk, w_lo + 2 * kk, IDESC, 1u);
+            for (int kk = 0; kk < nk; ++kk) umma_f16(d_tmem, a_hi + 2 * kk, w_hi + 2 * kk, IDESC, 1u);
+          }
+          umma_commit(&empty_bar[s]);
         }
+        umma_commit(&tfull_bar[slot]);
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== producers: 256 threads = 32 rows x 8 chunks per pass, 4 passes =====================
+    const int ptid = threadIdx.x - 256;
+    const int c = ptid & 7, r0 = ptid >> 3;
+    // destination of this lane's chunk: operand sub-tile (net, hi|lo) and the half (channels 0-7 / 8-15) inside a tap
+    const int sub = (c >> 2) * 2 + ((c >> 1) & 1), half = c & 1;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      unsigned mask[4];
+      const uint4* base[4];
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps) {
+        const long long v = (long long)tile * 128 + ps * 32 + r0;
+        const bool rv = v < p.V;
+        const int b = rv ? (int)(v % p.nB) : 0;
+        const int k = b / p.wB, l = b - k * p.wB;
+        mask[ps] = rv ? ((k > 0 ? 1u : 0u) | 2u | (k + 1 < p.hB ? 4u : 0u) | (l > 0 ? 8u : 0u) | 16u | (l + 1 < p.wB ? 32u : 0u)) : 0u;
+        base[ps] = reinterpret_cast<const uint4*>(p.hidden + (rv ? v : 0) * 64) + c;
+      }
+#pragma unroll
+      for (int atom = 0; atom < 3; ++atom, ++it) {
+        const int s = it % kL2Stages;
+        mbar_wait(&empty_bar[s], ((uint32_t)(it / kL2Stages) & 1u) ^ 1u);
+        uint8_t* st = smem + (size_t)s * STAGE_BYTES + sub * kNcAtom;
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) {
+          const int row = ps * 32 + r0;
+          uint4 q[4];
+#pragma unroll
+          for (int j = 0; j < (atom < 2 ? 4 : 1); ++j) {
+            const int t = atom * 4 + j, tk = t / 3, tl = t % 3;
+            const unsigned need = (1u << tk) | (8u << tl);
+            q[j] = ((mask[ps] & need) == need) ? __ldg(base[ps] + ((long long)(tk - 1) * p.wB + (tl - 1)) * 8) : make_uint4(0, 0, 0, 0);
+          }
+#pragma unroll
+          for (int j = 0; j < (atom < 2 ? 4 : 1); ++j)
+            *reinterpret_cast<uint4*>(st + row * 128 + (((2 * j + half) ^ (row & 7)) << 4)) = q[j];
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_bar[s]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    float sx, sh;
+    nc_scales(p, sx, sh);
+    const float inv = p.inv_sw2 / sh;
+    int tl = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
+      const int slot = tl & 1;
+      mbar_wait(&tfull_bar[slot], (uint32_t)(tl >> 1) & 1u);
+      tc_fence_after();
+      float acc[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 32), acc);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[slot]);
+      const long long v = (long long)tile * 128 + row;
+      if (v < p.V) {
+#pragma unroll
+        for (int net = 0; net < 2; ++net)
+#pragma unroll
+          for (int d = 0; d < 9; ++d) p.partial[(size_t)(net * 9 + d) * p.V + v] = acc[net * 16 + d] * inv;
       }
     }
   }
@@ -365,7 +443,7 @@ __global__ void __launch_bounds__(256) nc_combine_kernel(const float* __restrict
   for (int r = 0; r < R; ++r) rm[r] = -INFINITY;
   for (int col = threadIdx.x; col < nB; col += 256) {
     float cm = -INFINITY;
-#pragma unroll
+#pragma unroll 2
     for (int r = 0; r < R; ++r) {
       const int a = r0 + r;
       if (a >= nA) continue;
@@ -487,21 +565,24 @@ int launch_neigh_consensus_umma(const float* x, int hA, int wA, int hB, int wB, 
   p.x = x; p.xmax = xmax; p.hidden = hidden; p.partial = partial; p.b1p = b1p;
   p.wsum1 = W.wsum1; p.b1max = W.b1max; p.inv_sw1 = W.inv_sw1; p.inv_sw2 = W.inv_sw2;
   const long long vt = (p.V + 127) / 128;
-  P2P_REQUIRE(2 * vt < (1ll << 31), "NeighConsensus: 4D volume too large");
+  const long long t1 = (long long)p.nA * ((p.nB + 127) / 128);
+  P2P_REQUIRE(vt < (1ll << 31) && t1 < (1ll << 31), "NeighConsensus: 4D volume too large");
   {
     p.wimg = W.img1;
-    p.tiles = (int)vt;
-    const int smem = 4 * 2 * kNcAtom + 2 * 2 * 32 * 128 + 1024;
-    auto k = nc_umma_kernel<1>;
+    p.tiles = (int)t1;
+    const int smem = kL1Stages * 2 * kNcAtom + 2 * 2 * 32 * 128 + 9 * (128 + 2 * wB + 2) * 4 + 1024;
+    P2P_REQUIRE(smem <= 200 * 1024, "NeighConsensus layer 1: B grid too wide for the shared-memory staging (wB <= ~1400)");
+    auto k = nc_l1_umma_kernel;
     P2P_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    k<<<p.tiles < num_sms ? p.tiles : num_sms, 512, smem, st>>>(p);
+    const int grid = p.tiles < 2 * num_sms ? p.tiles : 2 * num_sms;       // 2 CTAs per SM
+    k<<<grid, 384, smem, st>>>(p);
     P2P_LAUNCH_OK();
   }
   {
     p.wimg = W.img2;
-    p.tiles = (int)(2 * vt);
-    const int smem = 3 * 2 * kNcAtom + 2 * 2 * 3 * 16 * 128 + 1024;
-    auto k = nc_umma_kernel<2>;
+    p.tiles = (int)vt;
+    const int smem = kL2Stages * 4 * kNcAtom + 2 * 2 * 3 * 16 * 128 + 1024;
+    auto k = nc_l2_umma_kernel;
     P2P_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     k<<<p.tiles < num_sms ? p.tiles : num_sms, 512, smem, st>>>(p);
     P2P_LAUNCH_OK();

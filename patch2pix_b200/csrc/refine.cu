@@ -118,37 +118,52 @@ struct WindowMapArgs {
   long long px0[3];     // first padded-pixel index of image 1; total
 };
 
+constexpr int kMapPxPerWarp = 4;
+
 __global__ void __launch_bounds__(256) window_map_kernel(const __grid_constant__ WindowMapArgs a) {
   const int lane = threadIdx.x & 31;
-  long long q = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (q >= a.px0[2]) return;
-  const int si = q >= a.px0[1] ? 1 : 0;
-  q -= a.px0[si];
-  const int W = a.W[si], H = a.H[si], Wp = W + 2 * kMapPad;
-  const int yp = (int)(q / Wp), xp = (int)(q - (long long)yp * Wp);
-  const int Y = min(max(yp - kMapPad, 0), H - 1), X = min(max(xp - kMapPad, 0), W - 1);
-  float t = 0.f;
-#pragma unroll
-  for (int l = 0; l < 4; ++l) t += __ldg(a.nsq[si][l] + (size_t)(Y >> l) * (W >> l) + (X >> l));
-  const float dinv = __fdiv_rn(kActScale, sqrtf(t + 1e-6f));
+  const long long q0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * kMapPxPerWarp;
   const int lvl = lane < 8 ? 0 : (lane < 16 ? 1 : 2);
   const int sh = lvl + 1, C = lvl == 2 ? 128 : 64;
   const int coff = (lane < 16 ? (lane & 7) : (lane - 16)) * 8;
-  const int px = (Y >> sh) * (W >> sh) + (X >> sh);
-  const float sc = dinv * sqrtf(__ldg(a.nsq[si][lvl + 1] + px) + 1e-30f);       // undo the per-level normalisation
-  uint4 v = __ldg(reinterpret_cast<const uint4*>(a.nhwc16[si][lvl] + (size_t)px * C + coff));
-  __half2* h2 = reinterpret_cast<__half2*>(&v);
+  // phase 1: all loads of the warp's pixels in flight; phase 2: scale and store
+  uint4 v[kMapPxPerWarp];
+  float t[kMapPxPerWarp], nl[kMapPxPerWarp], rgb[kMapPxPerWarp];
+  long long q[kMapPxPerWarp];
+  int si[kMapPxPerWarp];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 f = __half22float2(h2[i]);
-    h2[i] = __floats2half2_rn(f.x * sc, f.y * sc);
+  for (int u = 0; u < kMapPxPerWarp; ++u) {
+    long long qq = q0 + u;
+    const bool ok = qq < a.px0[2];
+    if (!ok) qq = 0;
+    si[u] = qq >= a.px0[1] ? 1 : 0;
+    qq -= a.px0[si[u]];
+    q[u] = ok ? qq : -1;
+    const int W = a.W[si[u]], H = a.H[si[u]], Wp = W + 2 * kMapPad;
+    const int yp = (int)(qq / Wp), xp = (int)(qq - (long long)yp * Wp);
+    const int Y = min(max(yp - kMapPad, 0), H - 1), X = min(max(xp - kMapPad, 0), W - 1);
+    float tt = 0.f;
+#pragma unroll
+    for (int l = 0; l < 4; ++l) tt += __ldg(a.nsq[si[u]][l] + (size_t)(Y >> l) * (W >> l) + (X >> l));
+    t[u] = tt;
+    const int px = (Y >> sh) * (W >> sh) + (X >> sh);
+    nl[u] = __ldg(a.nsq[si[u]][lvl + 1] + px);
+    v[u] = __ldg(reinterpret_cast<const uint4*>(a.nhwc16[si[u]][lvl] + (size_t)px * C + coff));
+    rgb[u] = lane < 3 ? __ldg(a.img[si[u]] + ((size_t)lane * H + Y) * W + X) : 0.f;
   }
-  reinterpret_cast<uint4*>(a.wmap[si] + (size_t)q * 256)[lane] = v;
-  if (lane < 3) {
-    const float r = __ldg(a.img[si] + ((size_t)lane * H + Y) * W + X) * dinv;
-    a.rgbn[si][(size_t)q * 4 + lane] = __float2half_rn(r);
-  } else if (lane == 3) {
-    a.rgbn[si][(size_t)q * 4 + 3] = __float2half_rn(0.f);
+#pragma unroll
+  for (int u = 0; u < kMapPxPerWarp; ++u) {
+    if (q[u] < 0) continue;
+    const float dinv = __fdiv_rn(kActScale, sqrtf(t[u] + 1e-6f));
+    const float sc = dinv * sqrtf(nl[u] + 1e-30f);       // undo the per-level normalisation
+    __half2* h2 = reinterpret_cast<__half2*>(&v[u]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h2[i]);
+      h2[i] = __floats2half2_rn(f.x * sc, f.y * sc);
+    }
+    reinterpret_cast<uint4*>(a.wmap[si[u]] + (size_t)q[u] * 256)[lane] = v[u];
+    if (lane < 4) a.rgbn[si[u]][(size_t)q[u] * 4 + lane] = __float2half_rn(rgb[u] * dinv);
   }
 }
 
@@ -168,7 +183,7 @@ int launch_window_map(const PairFeatures pf[2], cudaStream_t st) {
     tot += (long long)(pf[s].H + 2 * kMapPad) * (pf[s].W + 2 * kMapPad);
   }
   a.px0[2] = tot;
-  window_map_kernel<<<(unsigned)((tot + 7) / 8), 256, 0, st>>>(a);
+  window_map_kernel<<<(unsigned)((tot + 8 * kMapPxPerWarp - 1) / (8 * kMapPxPerWarp)), 256, 0, st>>>(a);
   P2P_LAUNCH_OK();
   return 0;
 }

@@ -89,6 +89,24 @@ def case_stages(net, name, pair_idx, H, W, ksize=2, gen=synthetic_pair):
     print(name, 'mutual', out['mutual_matches'].shape, 'fine', out['fine'].shape)
 
 
+def reference_tie_rows(net, corr4d, feat1, feat2, ksize, tie_eps=1e-6, margin_eps=2e-5):
+    """Candidate rows of the reference's own output that are ambiguous under fp32 rounding: the selected cell's 2^4
+    pooling window has a top-2 gap <= tie_eps, or the argmax of its corr4d row / column has a top-2 margin
+    <= margin_eps * max(corr4d).  Computed from the LIVE reference's tensors (same rule as tests/_tie_masks)."""
+    mm = corr4d[0, 0].reshape(corr4d.shape[2] * corr4d.shape[3], -1)
+    nA, nB = mm.shape
+    scale = mm.max().clamp_min(1e-30)
+    tA, tB = mm.topk(2, dim=0)[0], mm.topk(2, dim=1)[0]
+    fragile = torch.cat([(tA[0] - tA[1]) <= margin_eps * scale, (tB[:, 0] - tB[:, 1]) <= margin_eps * scale])
+    corr = net.combine(L2Normalize(feat1, dim=1), L2Normalize(feat2, dim=1))
+    k = ksize
+    sl = torch.cat([corr[:, :, i::k, j::k, a::k, b::k] for i in range(k) for j in range(k) for a in range(k) for b in range(k)], 1)
+    top2 = sl.topk(2, dim=1)[0]
+    tie = ((top2[:, 0] - top2[:, 1]) <= tie_eps)[0].reshape(nA, nB)
+    ia, ib = mm.argmax(0), mm.argmax(1)
+    return fragile | torch.cat([tie[ia, torch.arange(nB)], tie[torch.arange(nA), ib]])
+
+
 def case_train_sequence(net8, name, pair_idx, H, W, ptmax, np_seed, gen=synthetic_pair):
     """train_patch2pix.py:97-118 forward sequence under eval()/no_grad (ptmax, panc=8)."""
     im1, im2 = gen(pair_idx, H, W)
@@ -96,6 +114,9 @@ def case_train_sequence(net8, name, pair_idx, H, W, ptmax, np_seed, gen=syntheti
     with torch.no_grad():
         corr4d, delta4d, feats1, feats2 = net8.forward(im1, im2, ksize=2, return_feats=True)
         cm, sc = net8.cal_coarse_matches(corr4d, delta4d, ksize=2, upsample=net8.upsample, center=True)
+        out['cand_matches'] = np_(cm)
+        out['cand_scores'] = np_(sc)
+        out['cand_fp32_tie'] = np_(reference_tie_rows(net8, corr4d, feats1[-1], feats2[-1], 2))
         np.random.seed(np_seed)
         cm, sc = filter_coarse(cm, sc, 0.0, True, ptmax=ptmax)
         out['sampled'] = np_(cm[0])
