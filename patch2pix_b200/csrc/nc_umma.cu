@@ -15,8 +15,8 @@
 //             Epilogue: + bias, ReLU, re-scale, fp16 hi/lo split -> hidden[cell][64 fp16] =
 //             [net0 hi 16 | net0 lo 16 | net1 hi 16 | net1 lo 16] (one 128-byte line per cell).
 //   layer 2   16 -> 1 channels would be an N = 1 GEMM.  Instead, per hidden cell a' and per net, the 9 PARTIAL maps
-//             P_(ta,tb)[a'][b] = sum over the 9 B-taps and 16 channels are one GEMM with K = 9 x 16 = 144 (3 swizzle
-//             atoms), N = 9 (padded to 16); the im2col rows are pure 16-byte copies of hidden lines.
+//             P_(ta,tb)[a'][b] = sum over the 9 B-taps and 16 channels are one GEMM with K = 9 x 16 = 144, N = 9
+//             (padded to 16); one operand atom per B-tap whose rows are verbatim copies of 128-byte hidden lines.
 //   combine   out[a][b] = sum_net relu(b2 + sum_(ta,tb) P_(ta,tb)[a + (ta-1, tb-1)][b])  (fixed summation order:
 //             deterministic), fused with the row/column maxima of the MutualMatching that follows.
 //
@@ -25,10 +25,9 @@
 // stays below 1e-6 relative).  Activations are scaled by powers of two derived ON THE DEVICE from max|x| (and from
 // a weight-norm bound for the hidden tensor), so any input range is safe in fp16.
 //
-// CTA = 512 threads: warp 1 MMA issuer, warp 2 TMEM allocator, warps 4..7 epilogue (one TMEM lane quadrant each),
-// warps 8..15 im2col producers; persistent over 128-row tiles; ring of 4 (layer 1) / 3 (layer 2) operand stages
-// (the stage index always equals the atom index modulo the ring, so never-written chunks stay zero);
-// two TMEM accumulator slots so that the epilogue of tile i overlaps the MMAs of tile i+1.
+// Warp-specialised persistent kernels (MMA issuer, TMEM allocator, 4 epilogue warps = TMEM lane quadrants, producer
+// warps), mbarrier ring of operand stages, two TMEM accumulator slots so that the epilogue of tile i overlaps the MMAs
+// of tile i+1.
 #include <math.h>
 
 #include <vector>
@@ -95,7 +94,7 @@ __global__ void __launch_bounds__(384, 2) nc_l1_umma_kernel(const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* wsm = smem + kL1Stages * STAGE_BYTES;                          // [hi|lo][atom] weight images, 16 KB
-  float* xs = reinterpret_cast<float*>(wsm + 4 * WATOM);                  // [9][span]
+  float* xs = reinterpret_cast<float*>(wsm + 4 * WATOM);                  // [2 buffers][9][span]
   __shared__ __align__(8) uint64_t full_bar[kL1Stages];
   __shared__ __align__(8) uint64_t empty_bar[kL1Stages];
   __shared__ __align__(8) uint64_t tfull_bar[2];
@@ -163,28 +162,44 @@ __global__ void __launch_bounds__(384, 2) nc_l1_umma_kernel(const __grid_constan
     const int r = threadIdx.x - 256;
     float sx, sh;
     nc_scales(p, sx, sh);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    // stage the 9 A-neighbour segments [b0 - wB - 1, b0 + 128 + wB + 1) of a tile with cp.async (zero fill outside
+    // the volume), double-buffered: the copies of tile i+1 are in flight while tile i is built
+    auto issue = [&](int tile, int buf) {
       const int a = tile / TB, b0 = (tile - a * TB) << 7;
       const int ia = a / p.wA, ja = a - ia * p.wA;
-      // stage the 9 A-neighbour segments [b0 - wB - 1, b0 + 128 + wB + 1) (zero outside the volume), pre-scaled by sx
-      asm volatile("bar.sync 1, 128;" ::: "memory");          // everyone is done reading the previous tile's segments
+      float* dst = xs + (size_t)buf * 9 * span;
       for (int d = 0; d < 9; ++d) {
         const int i2 = ia + d / 3 - 1, j2 = ja + d % 3 - 1;
         const bool av = i2 >= 0 && i2 < p.hA && j2 >= 0 && j2 < p.wA;
         const float* src = p.x + (size_t)(av ? i2 * p.wA + j2 : 0) * p.nB;
         for (int j = r; j < span; j += 128) {
           const int b = b0 - p.wB - 1 + j;
-          xs[d * span + j] = (av && b >= 0 && b < p.nB) ? __ldg(src + b) * sx : 0.f;
+          const bool ok = av && b >= 0 && b < p.nB;
+          const unsigned sz = ok ? 4u : 0u;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst + d * span + j)), "l"(ok ? src + b : p.x), "r"(sz)
+                       : "memory");
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int it = 0, buf = 0;
+    if ((int)blockIdx.x < tiles) issue(blockIdx.x, 0);
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int next = tile + gridDim.x;
+      if (next < tiles) {
+        issue(next, buf ^ 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");          // every producer's copies of this tile have landed
+      const int a = tile / TB, b0 = (tile - a * TB) << 7;
       const int b = b0 + r;
       const bool rv = b < p.nB;
       const int k = rv ? b / p.wB : 0, l = rv ? b - k * p.wB : 0;
       // validity of the B-side taps: bits 0..2 rows (k-1, k, k+1), bits 3..5 columns (l-1, l, l+1)
       const unsigned m = rv ? ((k > 0 ? 1u : 0u) | 2u | (k + 1 < p.hB ? 4u : 0u) | (l > 0 ? 8u : 0u) | 16u | (l + 1 < p.wB ? 32u : 0u)) : 0u;
-      const float* xr = xs + r;
+      const float* xr = xs + (size_t)buf * 9 * span + r;
 #pragma unroll
       for (int atom = 0; atom < 2; ++atom, ++it) {
         const int s = it % kL1Stages;
@@ -200,7 +215,7 @@ __global__ void __launch_bounds__(384, 2) nc_l1_umma_kernel(const __grid_constan
             if (t < 81) {
               const int d = t / 9, tk = (t / 3) % 3, tl = t % 3;
               const unsigned need = (1u << tk) | (8u << tl);
-              f = ((m & need) == need) ? xr[d * span + tk * p.wB + tl] : 0.f;     // A-invalid segments hold zeros
+              f = ((m & need) == need) ? xr[d * span + tk * p.wB + tl] * sx : 0.f;     // A-invalid segments hold zeros
             }
             val[i] = f;
           }
@@ -212,6 +227,8 @@ __global__ void __launch_bounds__(384, 2) nc_l1_umma_kernel(const __grid_constan
         fence_proxy_async();
         mbar_arrive(&full_bar[s]);
       }
+      asm volatile("bar.sync 1, 128;" ::: "memory");          // all reads of this buffer done before it is refilled
+      buf ^= 1;
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
@@ -256,20 +273,20 @@ __global__ void __launch_bounds__(384, 2) nc_l1_umma_kernel(const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
-// layer 2.  Tile = 128 consecutive 4D cells, BOTH nets.  Producers: 8 lanes per tile row, lane = one 16-byte chunk
-// of the 128-byte hidden line [net0 hi0 hi1 lo0 lo1 | net1 hi0 hi1 lo0 lo1], so every warp load instruction reads four
-// complete lines; the chunk goes to the (net, hi|lo) operand tile of the tap's K range.
-// 512 threads (warp 1 MMA, 2 TMEM, 4..7 epilogue, 8..15 producers); 3 stages x 64 KB (stage == atom).
+// layer 2.  Tile = 128 consecutive 4D cells, both nets.  One operand atom per B-TAP: the atom row of a cell is the
+// complete 128-byte hidden line of its tap neighbour, K = [net][hi|lo][16 ch] -- so the producers are pure line copies
+// (8 lanes per line: fully coalesced loads, conflict-free swizzled stores) and the (net, hi|lo) factor of an MMA is
+// selected by the K16 slice of the descriptors: per tap and net  lo*hi + hi*lo + hi*hi  = 3 MMAs (M128 N16 K16).
+// 512 threads (warp 1 MMA, 2 TMEM, 4..7 epilogue, 8..15 producers); ring of 8 x 16 KB stages.
 // ------------------------------------------------------------------------------------------------
-constexpr int kL2Stages = 3;
+constexpr int kL2Stages = 8;
 
 __global__ void __launch_bounds__(512, 1) nc_l2_umma_kernel(const __grid_constant__ NcParams p) {
-  constexpr int STAGE_BYTES = 4 * kNcAtom;         // [net][hi|lo] x 16 KB
   constexpr int WATOM = 16 * 128;
   constexpr uint32_t IDESC = make_idesc_f16(128, 16);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* wsm = smem + kL2Stages * STAGE_BYTES;   // [net][hi|lo][atom] weight images, 24 KB
+  uint8_t* wsm = smem + kL2Stages * kNcAtom;       // [9 taps][16 rows][K = net | hi,lo | ch] weight images, 18 KB
   __shared__ __align__(8) uint64_t full_bar[kL2Stages];
   __shared__ __align__(8) uint64_t empty_bar[kL2Stages];
   __shared__ __align__(8) uint64_t tfull_bar[2];
@@ -279,8 +296,7 @@ __global__ void __launch_bounds__(512, 1) nc_l2_umma_kernel(const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles = p.tiles;
 
-  for (int i = threadIdx.x; i < kL2Stages * STAGE_BYTES / 16; i += 512) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = threadIdx.x; i < 12 * WATOM / 16; i += 512)
+  for (int i = threadIdx.x; i < 9 * WATOM / 16; i += 512)
     reinterpret_cast<uint4*>(wsm)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kL2Stages; ++i) {
@@ -307,22 +323,20 @@ __global__ void __launch_bounds__(512, 1) nc_l2_umma_kernel(const __grid_constan
         const int slot = tl & 1;
         mbar_wait(&tempty_bar[slot], ((uint32_t)(tl >> 1) & 1u) ^ 1u);
         tc_fence_after();
-#pragma unroll
-        for (int atom = 0; atom < 3; ++atom, ++it) {
+        for (int t = 0; t < 9; ++t, ++it) {
           const int s = it % kL2Stages;
           mbar_wait(&full_bar[s], (uint32_t)(it / kL2Stages) & 1u);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
-          const int nk = atom < 2 ? 4 : 1;           // atom 2 holds tap 8 only (one K16 slice)
+          const uint64_t a = make_sw128_desc(smem_u32(smem + (size_t)s * kNcAtom));
+          const uint64_t w = make_sw128_desc(smem_u32(wsm) + (uint32_t)(t * WATOM));
 #pragma unroll
           for (int net = 0; net < 2; ++net) {
             const uint32_t d_tmem = tmem_base + (uint32_t)(slot * 32 + net * 16);
-            const uint64_t a_hi = make_sw128_desc(sa + (net * 2) * kNcAtom), a_lo = make_sw128_desc(sa + (net * 2 + 1) * kNcAtom);
-            const uint32_t wb = smem_u32(wsm) + (uint32_t)((net * 6 + atom) * WATOM);
-            const uint64_t w_hi = make_sw128_desc(wb), w_lo = make_sw128_desc(wb + 3 * WATOM);
-            for (int kk = 0; kk < nk; ++kk) umma_f16(d_tmem, a_lo + 2 * kk, w_hi + 2 * kk, IDESC, (atom > 0 || kk > 0) ? 1u : 0u);
-            for (int kk = 0; kk < nk; ++kk) umma_f16(d_tmem, a_hi + 2 * kk, w_lo + 2 * kk, IDESC, 1u);
-            for (int kk = 0; kk < nk; ++kk) umma_f16(d_tmem, a_hi + 2 * kk, w_hi + 2 * kk, IDESC, 1u);
+            const uint64_t a_hi = a + 2 * (net * 2), a_lo = a + 2 * (net * 2 + 1);      // K16 slices of the line
+            const uint64_t w_hi = w + 2 * (net * 2), w_lo = w + 2 * (net * 2 + 1);
+            umma_f16(d_tmem, a_lo, w_hi, IDESC, t > 0 ? 1u : 0u);
+            umma_f16(d_tmem, a_hi, w_lo, IDESC, 1u);
+            umma_f16(d_tmem, a_hi, w_hi, IDESC, 1u);
           }
           umma_commit(&empty_bar[s]);
         }
@@ -330,11 +344,9 @@ __global__ void __launch_bounds__(512, 1) nc_l2_umma_kernel(const __grid_constan
       }
     }
   } else if (warp >= 8) {
-    // ===================== producers: 256 threads = 32 rows x 8 chunks per pass, 4 passes =====================
+    // ===================== producers: 256 threads = 32 rows x 8 chunks per pass, 4 passes per tap =====================
     const int ptid = threadIdx.x - 256;
     const int c = ptid & 7, r0 = ptid >> 3;
-    // destination of this lane's chunk: operand sub-tile (net, hi|lo) and the half (channels 0-7 / 8-15) inside a tap
-    const int sub = (c >> 2) * 2 + ((c >> 1) & 1), half = c & 1;
     int it = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       unsigned mask[4];
@@ -348,28 +360,31 @@ __global__ void __launch_bounds__(512, 1) nc_l2_umma_kernel(const __grid_constan
         mask[ps] = rv ? ((k > 0 ? 1u : 0u) | 2u | (k + 1 < p.hB ? 4u : 0u) | (l > 0 ? 8u : 0u) | 16u | (l + 1 < p.wB ? 32u : 0u)) : 0u;
         base[ps] = reinterpret_cast<const uint4*>(p.hidden + (rv ? v : 0) * 64) + c;
       }
+      auto load_tap = [&](int t, uint4* q) {
+        const int tk = t / 3, tl = t - tk * 3;
+        const unsigned need = (1u << tk) | (8u << tl);
+        const long long off = ((long long)(tk - 1) * p.wB + (tl - 1)) * 8;
 #pragma unroll
-      for (int atom = 0; atom < 3; ++atom, ++it) {
+        for (int ps = 0; ps < 4; ++ps) q[ps] = ((mask[ps] & need) == need) ? __ldg(base[ps] + off) : make_uint4(0, 0, 0, 0);
+      };
+      uint4 cur[4], nxt[4];
+      load_tap(0, cur);
+#pragma unroll 1
+      for (int t = 0; t < 9; ++t, ++it) {
+        if (t + 1 < 9) load_tap(t + 1, nxt);             // next tap's lines are in flight while this tap is stored
         const int s = it % kL2Stages;
         mbar_wait(&empty_bar[s], ((uint32_t)(it / kL2Stages) & 1u) ^ 1u);
-        uint8_t* st = smem + (size_t)s * STAGE_BYTES + sub * kNcAtom;
+        uint8_t* st = smem + (size_t)s * kNcAtom;
 #pragma unroll
         for (int ps = 0; ps < 4; ++ps) {
           const int row = ps * 32 + r0;
-          uint4 q[4];
-#pragma unroll
-          for (int j = 0; j < (atom < 2 ? 4 : 1); ++j) {
-            const int t = atom * 4 + j, tk = t / 3, tl = t % 3;
-            const unsigned need = (1u << tk) | (8u << tl);
-            q[j] = ((mask[ps] & need) == need) ? __ldg(base[ps] + ((long long)(tk - 1) * p.wB + (tl - 1)) * 8) : make_uint4(0, 0, 0, 0);
-          }
-#pragma unroll
-          for (int j = 0; j < (atom < 2 ? 4 : 1); ++j)
-            *reinterpret_cast<uint4*>(st + row * 128 + (((2 * j + half) ^ (row & 7)) << 4)) = q[j];
+          *reinterpret_cast<uint4*>(st + row * 128 + ((c ^ (row & 7)) << 4)) = cur[ps];
         }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[s]);
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) cur[ps] = nxt[ps];
       }
     }
   } else if (warp >= 4) {
@@ -523,17 +538,16 @@ int nc_umma_pack(const float* w1p, const float* b1p, const float* w2p, NcUmmaWei
       img1[(size_t)(0 * 2 + atom) * 32 * 64 + sw128_index(c, k)] = h;
       img1[(size_t)(1 * 2 + atom) * 32 * 64 + sw128_index(c, k)] = l;
     }
-  // layer 2: [net][hi|lo][atom 0..2][16 rows][64]; row = partial map (ta,tb) (9 used), k = (B tap - 4*atom) * 16 + channel
-  std::vector<__half> img2((size_t)2 * 2 * 3 * 16 * 64, __float2half(0.f));
+  // layer 2: [B tap 0..8][16 rows][64]; row = partial map (ta,tb) (9 used), k = net * 32 + (hi: 0 | lo: 16) + channel
+  std::vector<__half> img2((size_t)9 * 16 * 64, __float2half(0.f));
   for (int net = 0; net < 2; ++net)
     for (int d = 0; d < 9; ++d)
       for (int t = 0; t < 9; ++t)
         for (int ch = 0; ch < 16; ++ch) {
           const float v = w2p[(d * 9 + t) * 32 + net * 16 + ch] * s2;
           const __half h = __float2half_rn(v), l = __float2half_rn(v - __half2float(h));
-          const int atom = t >> 2, k = (t & 3) * 16 + ch;
-          img2[(size_t)((net * 2 + 0) * 3 + atom) * 16 * 64 + sw128_index(d, k)] = h;
-          img2[(size_t)((net * 2 + 1) * 3 + atom) * 16 * 64 + sw128_index(d, k)] = l;
+          img2[(size_t)t * 16 * 64 + sw128_index(d, net * 32 + ch)] = h;
+          img2[(size_t)t * 16 * 64 + sw128_index(d, net * 32 + 16 + ch)] = l;
         }
   const size_t b1 = img1.size() * 2, b2 = img2.size() * 2;
   if (W.blob == nullptr) {
@@ -570,8 +584,8 @@ int launch_neigh_consensus_umma(const float* x, int hA, int wA, int hB, int wB, 
   {
     p.wimg = W.img1;
     p.tiles = (int)t1;
-    const int smem = kL1Stages * 2 * kNcAtom + 2 * 2 * 32 * 128 + 9 * (128 + 2 * wB + 2) * 4 + 1024;
-    P2P_REQUIRE(smem <= 200 * 1024, "NeighConsensus layer 1: B grid too wide for the shared-memory staging (wB <= ~1400)");
+    const int smem = kL1Stages * 2 * kNcAtom + 2 * 2 * 32 * 128 + 2 * 9 * (128 + 2 * wB + 2) * 4 + 1024;
+    P2P_REQUIRE(smem <= 200 * 1024, "NeighConsensus layer 1: B grid too wide for the shared-memory staging (wB <= ~700)");
     auto k = nc_l1_umma_kernel;
     P2P_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int grid = p.tiles < 2 * num_sms ? p.tiles : 2 * num_sms;       // 2 CTAs per SM
@@ -581,7 +595,7 @@ int launch_neigh_consensus_umma(const float* x, int hA, int wA, int hB, int wB, 
   {
     p.wimg = W.img2;
     p.tiles = (int)vt;
-    const int smem = kL2Stages * 4 * kNcAtom + 2 * 2 * 3 * 16 * 128 + 1024;
+    const int smem = kL2Stages * kNcAtom + 9 * 16 * 128 + 1024;
     auto k = nc_l2_umma_kernel;
     P2P_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     k<<<p.tiles < num_sms ? p.tiles : num_sms, 512, smem, st>>>(p);

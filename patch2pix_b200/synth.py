@@ -121,10 +121,12 @@ def shifted_pair_offset(pair_idx):
     return dx, dy
 
 
-def synthetic_pair_shifted(pair_idx, height, width, noise=0.05):
+def synthetic_pair_shifted(pair_idx, height, width, noise=0.6):
     """Benchmark workload (round 2): two overlapping views of one texture whose offset is a multiple
     of 16 px (= one pooled correlation cell at ksize 2), so that coarse cells correspond one to one in
-    the overlap, plus independent noise on the second view (no exact feature equality).  With the
+    the overlap, plus strong independent noise on the second view (std 0.6 against a unit-variance texture:
+    with less noise the four true fine-level matches inside a 2^4 pooling window all have cosine
+    1 - O(1e-6) and ~10 % of the reference's own relocalisation deltas are fp32 coin flips).  With the
     'consensus' NC weights this gives ~1000 distinct mutual matches at 640x480 (vs 13-17 for
     `synthetic_pair`), i.e. filter_coarse(ptmax=400) samples 400 DISTINCT proposals.
     Returns im1, im2 as [1,3,H,W] fp32 on CPU."""
