@@ -118,42 +118,41 @@ struct WindowMapArgs {
   long long px0[3];     // first padded-pixel index of image 1; total
 };
 
-constexpr int kMapPxPerWarp = 4;
+constexpr int kMapPxPerWarp = 8;     // consecutive pixels of one padded row (W is a multiple of 8, so is W + 2 * pad)
 
 __global__ void __launch_bounds__(256) window_map_kernel(const __grid_constant__ WindowMapArgs a) {
   const int lane = threadIdx.x & 31;
-  const long long q0 = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * kMapPxPerWarp;
+  const int q0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * kMapPxPerWarp;
+  if (q0 >= (int)a.px0[2]) return;
+  const int si = q0 >= (int)a.px0[1] ? 1 : 0;
+  const int qb = q0 - (int)a.px0[si];
+  const int W = a.W[si], H = a.H[si], Wp = W + 2 * kMapPad;
+  const int yp = qb / Wp, xp0 = qb - yp * Wp;
+  const int Y = min(max(yp - kMapPad, 0), H - 1);
   const int lvl = lane < 8 ? 0 : (lane < 16 ? 1 : 2);
   const int sh = lvl + 1, C = lvl == 2 ? 128 : 64;
   const int coff = (lane < 16 ? (lane & 7) : (lane - 16)) * 8;
-  // phase 1: all loads of the warp's pixels in flight; phase 2: scale and store
+  const float* nsq0 = a.nsq[si][0] + (size_t)Y * W;
+  const float* nsq1 = a.nsq[si][1] + (size_t)(Y >> 1) * (W >> 1);
+  const float* nsq2 = a.nsq[si][2] + (size_t)(Y >> 2) * (W >> 2);
+  const float* nsq3 = a.nsq[si][3] + (size_t)(Y >> 3) * (W >> 3);
+  const float* nsql = lvl == 0 ? nsq1 : (lvl == 1 ? nsq2 : nsq3);
+  const __half* frow = a.nhwc16[si][lvl] + (size_t)(Y >> sh) * (W >> sh) * C + coff;
+  // phase 1: every load of the warp's 8 pixels in flight; phase 2: scale and store
   uint4 v[kMapPxPerWarp];
   float t[kMapPxPerWarp], nl[kMapPxPerWarp], rgb[kMapPxPerWarp];
-  long long q[kMapPxPerWarp];
-  int si[kMapPxPerWarp];
 #pragma unroll
   for (int u = 0; u < kMapPxPerWarp; ++u) {
-    long long qq = q0 + u;
-    const bool ok = qq < a.px0[2];
-    if (!ok) qq = 0;
-    si[u] = qq >= a.px0[1] ? 1 : 0;
-    qq -= a.px0[si[u]];
-    q[u] = ok ? qq : -1;
-    const int W = a.W[si[u]], H = a.H[si[u]], Wp = W + 2 * kMapPad;
-    const int yp = (int)(qq / Wp), xp = (int)(qq - (long long)yp * Wp);
-    const int Y = min(max(yp - kMapPad, 0), H - 1), X = min(max(xp - kMapPad, 0), W - 1);
-    float tt = 0.f;
-#pragma unroll
-    for (int l = 0; l < 4; ++l) tt += __ldg(a.nsq[si[u]][l] + (size_t)(Y >> l) * (W >> l) + (X >> l));
-    t[u] = tt;
-    const int px = (Y >> sh) * (W >> sh) + (X >> sh);
-    nl[u] = __ldg(a.nsq[si[u]][lvl + 1] + px);
-    v[u] = __ldg(reinterpret_cast<const uint4*>(a.nhwc16[si[u]][lvl] + (size_t)px * C + coff));
-    rgb[u] = lane < 3 ? __ldg(a.img[si[u]] + ((size_t)lane * H + Y) * W + X) : 0.f;
+    const int X = min(max(xp0 + u - kMapPad, 0), W - 1);
+    t[u] = ((__ldg(nsq0 + X) + __ldg(nsq1 + (X >> 1))) + __ldg(nsq2 + (X >> 2))) + __ldg(nsq3 + (X >> 3));
+    nl[u] = __ldg(nsql + (X >> sh));
+    v[u] = __ldg(reinterpret_cast<const uint4*>(frow + (size_t)(X >> sh) * C));
+    rgb[u] = lane < 3 ? __ldg(a.img[si] + ((size_t)lane * H + Y) * W + X) : 0.f;
   }
+  __half* wrow = a.wmap[si] + (size_t)qb * 256;
+  __half* rrow = a.rgbn[si] + (size_t)qb * 4;
 #pragma unroll
   for (int u = 0; u < kMapPxPerWarp; ++u) {
-    if (q[u] < 0) continue;
     const float dinv = __fdiv_rn(kActScale, sqrtf(t[u] + 1e-6f));
     const float sc = dinv * sqrtf(nl[u] + 1e-30f);       // undo the per-level normalisation
     __half2* h2 = reinterpret_cast<__half2*>(&v[u]);
@@ -162,8 +161,8 @@ __global__ void __launch_bounds__(256) window_map_kernel(const __grid_constant__
       const float2 f = __half22float2(h2[i]);
       h2[i] = __floats2half2_rn(f.x * sc, f.y * sc);
     }
-    reinterpret_cast<uint4*>(a.wmap[si[u]] + (size_t)q[u] * 256)[lane] = v[u];
-    if (lane < 4) a.rgbn[si[u]][(size_t)q[u] * 4 + lane] = __float2half_rn(rgb[u] * dinv);
+    reinterpret_cast<uint4*>(wrow + (size_t)u * 256)[lane] = v[u];
+    if (lane < 4) rrow[u * 4 + lane] = __float2half_rn(rgb[u] * dinv);
   }
 }
 
