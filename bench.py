@@ -98,16 +98,47 @@ def load_peaks():
     return {'hbm_gbs': 6650.0, 'tflops_burst': 1590.0, 'tflops_sustained': 1400.0, 'src': 'fallback'}
 
 
-class ClockSampler(threading.Thread):
-    """Samples SM clock / power / throttle reasons through NVML every 8 ms while the timed region runs
-    (the region can be ~0.1 s long: nvidia-smi's process start-up alone would miss it)."""
+_SAMPLER_SRC = r"""
+import sys, time
+import pynvml as N
+N.nvmlInit()
+h = N.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+reasons = getattr(N, 'nvmlDeviceGetCurrentClocksEventReasons', None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+print('ready', N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM), flush=True)
+sys.stdin.readline()                      # 'go'
+import select
+i, pw = 0, 0.0
+while not select.select([sys.stdin], [], [], 0.005)[0]:
+    if i % 8 == 0:
+        pw = N.nvmlDeviceGetPowerUsage(h) / 1e3
+    print(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), pw, int(reasons(h)), flush=False)
+    i += 1
+sys.stdout.flush()
+"""
+
+
+class ClockSampler:
+    """Samples SM clock / power / throttle reasons through NVML every ~5 ms while the timed region runs -- in a separate
+    PROCESS (a sampler thread in this interpreter contends for the GIL with the launch loop and shows up as launch gaps;
+    nvidia-smi's own start-up would miss a 0.5 s region)."""
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._halt, self.err = index, [], threading.Event(), None
-        self.sm_max = None
+        self.index, self.proc, self.sm_max, self.err = index, None, None, None
+        try:
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[index]) if vis and vis.split(',')[index].isdigit() else index
+            self.proc = subprocess.Popen([sys.executable, '-u', '-c', _SAMPLER_SRC, str(phys)], stdin=subprocess.PIPE,
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            line = self.proc.stdout.readline().split()
+            if len(line) == 2 and line[0] == 'ready':
+                self.sm_max = float(line[1])
+            else:
+                raise RuntimeError('sampler did not start')
+        except Exception as e:       # no sampler process: fall back to a thread in this interpreter (still real NVML samples)
+            self.err, self.proc = repr(e), None
+        self.thread = None
 
-    def run(self):
+    def _thread_loop(self):
         try:
             import pynvml as N
             N.nvmlInit()
@@ -116,29 +147,48 @@ class ClockSampler(threading.Thread):
             h = N.nvmlDeviceGetHandleByIndex(phys)
             self.sm_max = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
             reasons = getattr(N, 'nvmlDeviceGetCurrentClocksEventReasons', None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
-            i, pw = 0, 0.0
             while not self._halt.is_set():
-                if i % 8 == 0:                       # power changes slowly; keep the per-sample work (GIL time) small
-                    pw = N.nvmlDeviceGetPowerUsage(h) / 1e3
-                self.rows.append((float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), pw, int(reasons(h))))
-                i += 1
-                self._halt.wait(0.008)
-        except Exception as e:   # NVML missing: report it, never fake a sample
+                self._rows.append((float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), N.nvmlDeviceGetPowerUsage(h) / 1e3,
+                                   int(reasons(h))))
+                self._halt.wait(0.02)
+        except Exception as e:
             self.err = repr(e)
 
+    def start(self):
+        if self.proc:
+            self.proc.stdin.write('go\n')
+            self.proc.stdin.flush()
+        else:
+            self._rows, self._halt = [], threading.Event()
+            self.thread = threading.Thread(target=self._thread_loop, daemon=True)
+            self.thread.start()
+
     def finish(self):
-        self._halt.set()
-        self.join(timeout=6)
-        if not self.rows:
+        rows = []
+        if self.thread is not None:
+            self._halt.set()
+            self.thread.join(timeout=5)
+            rows = list(self._rows)
+        if self.proc:
+            try:
+                out, _ = self.proc.communicate('stop\n', timeout=10)
+                for ln in out.splitlines():
+                    p = ln.split()
+                    if len(p) == 3:
+                        rows.append((float(p[0]), float(p[1]), int(p[2])))
+            except Exception as e:
+                self.err = repr(e)
+                self.proc.kill()
+        if not rows:
             return {'sm_mhz': None, 'sm_max_mhz': self.sm_max, 'reasons': ['unavailable: ' + str(self.err)]}
         bits = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20, 'sw_power_cap': 0x4,
                 'hw_power_brake_slowdown': 0x80}
         allbits = 0
-        for r in self.rows:
+        for r in rows:
             allbits |= r[2]
-        return {'sm_mhz': statistics.median(r[0] for r in self.rows), 'sm_min_mhz': min(r[0] for r in self.rows),
-                'sm_max_mhz': self.sm_max, 'power_w_max': max(r[1] for r in self.rows), 'samples': len(self.rows),
-                'interval_ms': 8, 'source': 'nvml', 'reasons': [n for n, b in bits.items() if allbits & b]}
+        return {'sm_mhz': statistics.median(r[0] for r in rows), 'sm_min_mhz': min(r[0] for r in rows),
+                'sm_max_mhz': self.sm_max, 'power_w_max': max(r[1] for r in rows), 'samples': len(rows),
+                'interval_ms': 5 if self.proc else 20, 'source': 'nvml (separate process)' if self.proc else 'nvml (thread)', 'reasons': [n for n, b in bits.items() if allbits & b]}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -359,7 +409,7 @@ def run_ours(args):
         barrier()
         if sampler:
             sampler.start()
-            time.sleep(0.02)
+            time.sleep(0.01)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn(steps)
@@ -438,17 +488,21 @@ def run_ours(args):
         # the fp32-backbone variant is measured beside it (parity: tests/test_gpu_parity.py::test_backbone_graph_tf32_path)
         e2e_ms = {}
         host_outs = [torch.empty(n_patches, 5).pin_memory() for _ in range(2)]
-        for mode in (['fp32'] if args.backbone_fp32 else ['tf32', 'fp32']):
-            if strong and mode == 'fp32' and not args.backbone_fp32:
+        for mode in (['fp32'] if args.backbone_fp32 else ['tf32', 'fp16', 'fp32']):
+            if strong and mode != 'tf32' and not args.backbone_fp32:
                 continue
-            torch.backends.cudnn.allow_tf32 = mode == 'tf32'
+            torch.backends.cudnn.allow_tf32 = mode != 'fp32'
             torch.backends.cudnn.benchmark = True
-            net.enable_backbone_graphs(H, W, instances=2)
+            net.enable_backbone_graphs(H, W, instances=2, fast=mode == 'fp16')
             e2e_loop(0, max(min(Wm, 3), 1), host_outs)
 
             def e2e_region(steps):
                 e2e_loop(Wm, min(steps, n_mine), host_outs)
             e2e_ms[mode] = timed(e2e_region, K)
+            if mode == 'tf32' and not strong:           # the backbone share of the end-to-end step (H2D + graph replay alone)
+                nb = min(K, 30)
+                e2e_ms['backbone_only'] = timed(lambda steps: [net.extract_pair(*pinned[slots[i % len(slots)]], slot=i)
+                                                               for i in range(steps)], nb) / nb
         torch.backends.cudnn.allow_tf32 = False
 
     if rank == 0:
@@ -516,6 +570,10 @@ def run_ours(args):
                        + ('fp32' if head == 'fp32' else 'TF32 convs, PyTorch default') + ') -> hot path -> D2H matches+scores'}
         if 'fp32' in e2e_ms and head != 'fp32':
             e2e['fp32_backbone_value'] = pairs / (e2e_ms['fp32'] / 1e3)
+        if 'fp16' in e2e_ms:
+            e2e['fp16_channels_last_backbone_value'] = pairs / (e2e_ms['fp16'] / 1e3)
+        if 'backbone_only' in e2e_ms:
+            e2e['backbone_h2d_ms_per_pair'] = e2e_ms['backbone_only']
         line = {
             'metric': 'image-pairs/sec', 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': K, 'warmup': Wm,
             'ms_per_step': ms_hot / K, 'higher_is_better': True, 'scaling': 'strong' if strong else 'weak', 'vs_baseline': None,

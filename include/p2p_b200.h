@@ -113,6 +113,12 @@ P2P_API int p2p_coarse(p2p_handle_t h, const float* feat1, const float* feat2, i
                int ksize, float* corr4d_out, uint8_t* delta_code_out, float* pooled_out, float* ncn_out,
                void* stream);
 
+/* Same, for a channels-last fp16 layer-3 map: feat1 [h1][w1][c], feat2 [h2][w2][c] (what an fp16 / channels_last
+ * backbone emits; the L2-normalise + K-major re-layout pass then needs no transpose).  Identical arithmetic from there on. */
+P2P_API int p2p_coarse_nhwc16(p2p_handle_t h, const void* feat1_nhwc16, const void* feat2_nhwc16, int c, int h1, int w1, int h2,
+               int w2, int ksize, float* corr4d_out, uint8_t* delta_code_out, float* pooled_out, float* ncn_out,
+               void* stream);
+
 /* maxpool4d's four int64 delta tensors (max_i,max_j,max_k,max_l) from the packed code. */
 P2P_API int p2p_delta_unpack(p2p_handle_t h, const uint8_t* code, long long n, int ksize, int64_t* di, int64_t* dj,
                      int64_t* dk, int64_t* dl, void* stream);
@@ -160,6 +166,9 @@ P2P_API int p2p_select_anchor(p2p_handle_t h, const int64_t* rows, const float* 
  * copies and norm maps); matches_in [n,4] int64 (is_float = 0) or fp32 (is_float = 1);
  * matches_out fp32 [n,4]; probs_out fp32 [n]. */
 P2P_API int p2p_refine_prepare(p2p_handle_t h, const float* const* feats1, const float* const* feats2, int H1, int W1,
+                       int H2, int W2, void* stream);
+/* Same, with levels 1..3 as channels-last fp16 maps [h][w][C] (level 0, the image, stays [3,H,W] fp32). */
+P2P_API int p2p_refine_prepare_nhwc16(p2p_handle_t h, const void* const* feats1, const void* const* feats2, int H1, int W1,
                        int H2, int W2, void* stream);
 P2P_API int p2p_refine(p2p_handle_t h, int which, const void* matches_in, int is_float, int n, float* matches_out,
                float* probs_out, void* stream);

@@ -37,6 +37,7 @@ _SIGNATURES = {
     'p2p_get_option': (_I, [_P, C.c_char_p, C.POINTER(_I)]),
     'p2p_launch_count': (_I, [_P, C.POINTER(_LL)]),
     'p2p_coarse': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    'p2p_coarse_nhwc16': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     'p2p_delta_unpack': (_I, [_P, _P, _LL, _I, _P, _P, _P, _P, _P]),
     'p2p_delta_pack': (_I, [_P, _P, _P, _P, _P, _LL, _I, _P, _P]),
     'p2p_mutual_matching': (_I, [_P, _P, _I, _I, _P, _P]),
@@ -45,6 +46,7 @@ _SIGNATURES = {
     'p2p_unique_rows': (_I, [_P, _P, _I, _I, _P, _F, _P, _P, _P]),
     'p2p_select_anchor': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     'p2p_refine_prepare': (_I, [_P, C.POINTER(_P), C.POINTER(_P), _I, _I, _I, _I, _P]),
+    'p2p_refine_prepare_nhwc16': (_I, [_P, C.POINTER(_P), C.POINTER(_P), _I, _I, _I, _I, _P]),
     'p2p_refine': (_I, [_P, _I, _P, _I, _I, _P, _P, _P]),
     'p2p_finalize_matches': (_I, [_P, _P, _P, _P, _I, _F, C.POINTER(C.c_double), _P, _P]),
     'p2p_preprocess_image': (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P]),

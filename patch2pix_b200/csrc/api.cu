@@ -575,9 +575,9 @@ static int corr_umma(p2p_handle_s* h, const __half* a_hi, const __half* a_lo, co
   return launch_umma_gemm(p, EPI_PLAIN, h->opt_corr_passes, sms(h), st);
 }
 
-int p2p_coarse(p2p_handle_t h, const float* feat1, const float* feat2, int c, int h1, int w1, int h2, int w2,
-               int ksize, float* corr4d_out, uint8_t* delta_code_out, float* pooled_out, float* ncn_out,
-               void* stream) {
+static int coarse_impl(p2p_handle_t h, const float* feat1, const float* feat2, int fmt, int c, int h1, int w1, int h2, int w2,
+                       int ksize, float* corr4d_out, uint8_t* delta_code_out, float* pooled_out, float* ncn_out,
+                       void* stream) {
   P2P_ENTER(h);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   P2P_REQUIRE(h->nc_set, "p2p_set_ncn_weights has not been called");
@@ -594,6 +594,7 @@ int p2p_coarse(p2p_handle_t h, const float* feat1, const float* feat2, int c, in
   const size_t V = (size_t)nA * nB;
   const bool tc = h->opt_corr_passes > 0;
   if (tc) P2P_REQUIRE(c % 64 == 0 && c / 64 <= kMaxKSteps, "tensor-core correlation needs C % 64 == 0");
+  P2P_REQUIRE(fmt == 0 || tc, "channels-last fp16 features need the tensor-core correlation (corr_passes 1 or 3)");
   const int n1pad = (int)align_up(n1, 128), n2pad = (int)align_up(n2, 256);
   size_t need = 4 * V * 4 + nc_umma_scratch_bytes(V) + (size_t)(nA + nB) * 8 + (1 << 16);
   need += tc ? (size_t)(n1pad + n2pad) * c * 4 : (size_t)(n1 + n2) * c * 4;
@@ -617,9 +618,13 @@ int p2p_coarse(p2p_handle_t h, const float* feat1, const float* feat2, int c, in
     const bool lo = h->opt_corr_passes == 3;
     {
       ProfScope ps(h, P2P_PROF_L2NORM, st);
-      if ((rc = launch_l2norm_perm_kmajor_pair(feat1, feat2, a_hi, lo ? a_lo : nullptr, b_hi, lo ? b_lo : nullptr, c, h1, w1, h2,
-                                               w2, ksize, st)))
-        return rc;
+      if (fmt == 1)
+        rc = launch_l2norm_perm_kmajor_pair_nhwc16(reinterpret_cast<const __half*>(feat1), reinterpret_cast<const __half*>(feat2),
+                                                   a_hi, lo ? a_lo : nullptr, b_hi, lo ? b_lo : nullptr, c, h1, w1, h2, w2, ksize, st);
+      else
+        rc = launch_l2norm_perm_kmajor_pair(feat1, feat2, a_hi, lo ? a_lo : nullptr, b_hi, lo ? b_lo : nullptr, c, h1, w1, h2,
+                                            w2, ksize, st);
+      if (rc) return rc;
     }
     ProfScope ps(h, P2P_PROF_CORR, st);
     if ((rc = corr_umma(h, a_hi, a_lo, b_hi, b_lo, c, n1, n2, n1pad, n2pad, ksize, pooled, delta_code_out, st)))
@@ -664,6 +669,19 @@ int p2p_coarse(p2p_handle_t h, const float* feat1, const float* feat2, int c, in
   ProfScope ps(h, P2P_PROF_MUTUAL, st);
   if ((rc = launch_mutual_matching(nc, nA, nB, rowmax, colmax, corr4d_out, nullptr, st))) return rc;
   return 0;
+}
+
+int p2p_coarse(p2p_handle_t h, const float* feat1, const float* feat2, int c, int h1, int w1, int h2, int w2,
+               int ksize, float* corr4d_out, uint8_t* delta_code_out, float* pooled_out, float* ncn_out,
+               void* stream) {
+  return coarse_impl(h, feat1, feat2, 0, c, h1, w1, h2, w2, ksize, corr4d_out, delta_code_out, pooled_out, ncn_out, stream);
+}
+
+int p2p_coarse_nhwc16(p2p_handle_t h, const void* feat1_nhwc16, const void* feat2_nhwc16, int c, int h1, int w1, int h2, int w2,
+                      int ksize, float* corr4d_out, uint8_t* delta_code_out, float* pooled_out, float* ncn_out,
+                      void* stream) {
+  return coarse_impl(h, reinterpret_cast<const float*>(feat1_nhwc16), reinterpret_cast<const float*>(feat2_nhwc16), 1, c, h1, w1,
+                     h2, w2, ksize, corr4d_out, delta_code_out, pooled_out, ncn_out, stream);
 }
 
 int p2p_delta_unpack(p2p_handle_t h, const uint8_t* code, long long n, int ksize, int64_t* di, int64_t* dj,
@@ -758,8 +776,8 @@ int p2p_select_anchor(p2p_handle_t h, const int64_t* rows, const float* scores, 
 // -------------------------------------------------------------------------------------------------
 // refine
 // -------------------------------------------------------------------------------------------------
-int p2p_refine_prepare(p2p_handle_t h, const float* const* feats1, const float* const* feats2, int H1, int W1,
-                       int H2, int W2, void* stream) {
+static int refine_prepare_impl(p2p_handle_t h, const float* const* feats1, const float* const* feats2, int fmt, int H1, int W1,
+                               int H2, int W2, void* stream) {
   P2P_ENTER(h);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   P2P_REQUIRE(feats1 && feats2, "null feature list");
@@ -801,11 +819,22 @@ int p2p_refine_prepare(p2p_handle_t h, const float* const* feats1, const float* 
   }
   {
     ProfScope ps(h, P2P_PROF_PREP, st);
-    if ((rc = launch_feature_prep_pair(feats1, feats2, Hs, Ws, h->pf, st))) return rc;
+    if ((rc = launch_feature_prep_pair(feats1, feats2, Hs, Ws, h->pf, fmt, st))) return rc;
     if (want_map && (rc = launch_window_map(h->pf, st))) return rc;
   }
   h->prepared = true;
   return 0;
+}
+
+int p2p_refine_prepare(p2p_handle_t h, const float* const* feats1, const float* const* feats2, int H1, int W1,
+                       int H2, int W2, void* stream) {
+  return refine_prepare_impl(h, feats1, feats2, 0, H1, W1, H2, W2, stream);
+}
+
+int p2p_refine_prepare_nhwc16(p2p_handle_t h, const void* const* feats1, const void* const* feats2, int H1, int W1,
+                              int H2, int W2, void* stream) {
+  return refine_prepare_impl(h, reinterpret_cast<const float* const*>(feats1), reinterpret_cast<const float* const*>(feats2), 1,
+                             H1, W1, H2, W2, stream);
 }
 
 namespace {

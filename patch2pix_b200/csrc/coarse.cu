@@ -208,6 +208,74 @@ int launch_l2norm_perm_kmajor_pair(const float* in1, const float* in2, __half* h
   return 0;
 }
 
+// Same, for a channels-last fp16 layer-3 map [n][C] (the fp16 / channels_last backbone of the end-to-end path):
+// the input is already K-major, so this is a row-wise normalise + hi/lo split; one warp per output position.
+template <int KS>
+__global__ void __launch_bounds__(256) l2norm_perm_kmajor_nhwc16_kernel(const __grid_constant__ L2NormArgs a, int C) {
+  const int im = blockIdx.y;
+  const int h = a.h[im], w = a.w[im], n = h * w;
+  const int lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (q >= n) return;
+  int pos;
+  if (KS == 2) {
+    const int wp = w >> 1;
+    const int cell = q >> 2, m = q & 3;
+    const int pi = cell / wp, pj = cell - pi * wp;
+    pos = (2 * pi + (m >> 1)) * w + 2 * pj + (m & 1);
+  } else {
+    pos = q;
+  }
+  const __half* in = reinterpret_cast<const __half*>(a.in[im]) + (size_t)pos * C;
+  float s = 0.f;
+  for (int c = lane * 8; c < C; c += 256) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + c));
+    const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h2[i]);
+      s = fmaf(f.x, f.x, s);
+      s = fmaf(f.y, f.y, s);
+    }
+  }
+  s = warp_sum(s);
+  const float d = sqrtf(s + 1e-6f);
+  __half* hi = a.hi[im] + (size_t)q * C;
+  __half* lo = a.lo[im] != nullptr ? a.lo[im] + (size_t)q * C : nullptr;
+  for (int c = lane * 8; c < C; c += 256) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + c));
+    const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+    __align__(16) __half2 oh[4];
+    __align__(16) __half2 ol[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h2[i]);
+      const float v0 = __fdiv_rn(f.x, d) * kActScale, v1 = __fdiv_rn(f.y, d) * kActScale;
+      oh[i] = __floats2half2_rn(v0, v1);
+      const float2 g = __half22float2(oh[i]);
+      ol[i] = __floats2half2_rn(v0 - g.x, v1 - g.y);
+    }
+    *reinterpret_cast<uint4*>(hi + c) = *reinterpret_cast<const uint4*>(oh);
+    if (lo != nullptr) *reinterpret_cast<uint4*>(lo + c) = *reinterpret_cast<const uint4*>(ol);
+  }
+}
+
+int launch_l2norm_perm_kmajor_pair_nhwc16(const __half* in1, const __half* in2, __half* hi1, __half* lo1, __half* hi2, __half* lo2,
+                                          int C, int h1, int w1, int h2, int w2, int ksize, cudaStream_t st) {
+  P2P_REQUIRE(C % 8 == 0, "l2norm (channels-last fp16): channel count must be a multiple of 8");
+  L2NormArgs a;
+  a.in[0] = reinterpret_cast<const float*>(in1); a.in[1] = reinterpret_cast<const float*>(in2);
+  a.hi[0] = hi1; a.hi[1] = hi2;
+  a.lo[0] = lo1; a.lo[1] = lo2;
+  a.h[0] = h1; a.w[0] = w1; a.h[1] = h2; a.w[1] = w2;
+  const int nmax = h1 * w1 > h2 * w2 ? h1 * w1 : h2 * w2;
+  dim3 grid(cdiv(nmax, 8), 2);
+  if (ksize == 2) l2norm_perm_kmajor_nhwc16_kernel<2><<<grid, 256, 0, st>>>(a, C);
+  else l2norm_perm_kmajor_nhwc16_kernel<1><<<grid, 256, 0, st>>>(a, C);
+  P2P_LAUNCH_OK();
+  return 0;
+}
+
 __global__ void split_rows_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo,
                                   size_t n, float scale) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -9,6 +9,8 @@ int launch_l2norm_perm(const float* in, float* out, int C, int h, int w, int ksi
 // K-major fp16 hi/lo variant for the tensor-core correlation: out[q][c] = split(kActScale * f/|f|)
 int launch_l2norm_perm_kmajor_pair(const float* in1, const float* in2, __half* hi1, __half* lo1, __half* hi2, __half* lo2,
                                    int C, int h1, int w1, int h2, int w2, int ksize, cudaStream_t st);
+int launch_l2norm_perm_kmajor_pair_nhwc16(const __half* in1, const __half* in2, __half* hi1, __half* lo1, __half* hi2, __half* lo2,
+                                          int C, int h1, int w1, int h2, int w2, int ksize, cudaStream_t st);
 int launch_split_rows(const float* in, __half* hi, __half* lo, size_t n, float scale, cudaStream_t st);
 int launch_delta_pack(const long long* di, const long long* dj, const long long* dk, const long long* dl, size_t n,
                       int ks, uint8_t* code, cudaStream_t st);
@@ -81,7 +83,7 @@ constexpr int kMapPad = 16;
 int launch_window_map(const PairFeatures pf[2], cudaStream_t st);
 
 int launch_feature_prep_pair(const float* const feats1[4], const float* const feats2[4], const int H[2], const int W[2],
-                             PairFeatures out[2], cudaStream_t st);
+                             PairFeatures out[2], int fmt, cudaStream_t st);
 // rowmap/d_count (optional, device): process only rows rowmap[0..*d_count) (patch slot b <- row rowmap[b]).
 int launch_patch_gather(const PairFeatures& f1, const PairFeatures& f2, const void* matches, int is_float, int N,
                         __half* p_hi, __half* p_lo, __half* rgb_hi, __half* rgb_lo, const int* rowmap,

@@ -20,7 +20,8 @@ namespace p2p {
 // One launch for both images and all four levels: segment = (image, level); level 0 (rgb, C = 3) only needs its
 // squared-norm map, levels 1..3 additionally get channels-last fp32 / level-normalised fp16 copies.
 struct PrepSegment {
-  const float* in;     // [C][npx]
+  const float* in;     // [C][npx] fp32, or (fmt 1) [npx][C] fp16
+  int fmt;             // 0: NCHW fp32 (reference layout); 1: channels-last fp16 (fp16 / channels_last backbone)
   float* out;          // [npx][C] (nullptr for level 0)
   __half* out16;       // [npx][C], every pixel divided by its own norm (nullptr for level 0)
   float* nsq;          // [npx]
@@ -43,6 +44,37 @@ __global__ void __launch_bounds__(256) feature_prep_kernel(const __grid_constant
   const int C = g.C, npx = g.npx;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int px0 = ((int)blockIdx.x - g.block0) * 32;
+  if (g.fmt == 1) {
+    // channels-last fp16 input: one warp per pixel (4 pixels per warp and block pass), lane = C/32 channels
+    const __half* in16 = reinterpret_cast<const __half*>(g.in);
+    const int per = C >> 5;                 // 2 (C = 64) or 4 (C = 128) halves per lane
+    for (int pp = wid; pp < 32; pp += 8) {
+      const int px = px0 + pp;
+      if (px >= npx) break;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (per == 2) {
+        const float2 f = __half22float2(__ldg(reinterpret_cast<const __half2*>(in16 + (size_t)px * C) + lane));
+        v[0] = f.x; v[1] = f.y;
+      } else {
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(in16 + (size_t)px * C) + lane);
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+        v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
+      }
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s = fmaf(v[i], v[i], s);
+      s = warp_sum(s);
+      if (lane == 0) g.nsq[px] = s;
+      const float ri = rsqrtf(s + 1e-30f);
+      float* o = g.out + (size_t)px * C + lane * per;
+      __half* o16 = g.out16 + (size_t)px * C + lane * per;
+      for (int i = 0; i < per; ++i) {
+        o[i] = v[i];
+        o16[i] = __float2half_rn(v[i] * ri);
+      }
+    }
+    return;
+  }
   const int px = px0 + lane;
   float s = 0.f;
   for (int c = wid; c < C; c += 8) {
@@ -72,7 +104,7 @@ __global__ void __launch_bounds__(256) feature_prep_kernel(const __grid_constant
 }
 
 int launch_feature_prep_pair(const float* const feats1[4], const float* const feats2[4], const int H[2], const int W[2],
-                             PairFeatures out[2], cudaStream_t st) {
+                             PairFeatures out[2], int fmt, cudaStream_t st) {
   PrepArgs a;
   memset(&a, 0, sizeof(a));
   const int chans[4] = {3, 64, 64, 128};
@@ -86,6 +118,7 @@ int launch_feature_prep_pair(const float* const feats1[4], const float* const fe
       PrepSegment& g = a.seg[a.nseg++];
       const int ds = 1 << l;
       g.in = f[l];
+      g.fmt = l > 0 ? fmt : 0;              // the image (level 0) is always NCHW fp32
       g.C = chans[l];
       g.npx = (H[s] / ds) * (W[s] / ds);
       g.nsq = out[s].nsq[l];

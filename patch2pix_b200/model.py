@@ -36,6 +36,17 @@ def _check_cuda_f32(t, name):
     return t.contiguous()
 
 
+def _feat_format(t, name):
+    """0: contiguous NCHW fp32 (the reference's layout); 1: channels-last fp16 (the fast backbone of the end-to-end path)."""
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError(f'{name} must be a CUDA tensor (no CPU fallback)')
+    if t.dtype == torch.float32:
+        return 0
+    if t.dtype == torch.float16 and t.dim() >= 3 and t.permute(*range(t.dim() - 3), -2, -1, -3).is_contiguous():
+        return 1
+    raise RuntimeError(f'{name} must be float32 NCHW or channels-last float16')
+
+
 class _UniqueTicket:
     """unique_rows in flight: ids buffer on the device, counters on their way to pinned host memory.
     Every ticket owns its pinned counter buffer (PyTorch's caching host allocator recycles it, stream-aware,
@@ -318,6 +329,7 @@ class Patch2PixB200(nn.Module):
     def load_state_dict(self, state_dict, strict=True, **kw):
         r = super().load_state_dict(state_dict, strict=strict, **kw)
         self._packed = False
+        object.__setattr__(self, '_extract_half', None)
         return r
 
     def train(self, mode=True):
@@ -360,8 +372,12 @@ class Patch2PixB200(nn.Module):
     # -- coarse --------------------------------------------------------------------------------
     def _coarse_raw(self, feat1, feat2, ksize, return_stages=False):
         h = self._ready()
-        feat1 = _check_cuda_f32(feat1, 'feat1')
-        feat2 = _check_cuda_f32(feat2, 'feat2')
+        fmt = _feat_format(feat1, 'feat1')
+        if _feat_format(feat2, 'feat2') != fmt:
+            raise RuntimeError('feat1 and feat2 must share dtype / memory format')
+        if fmt == 0:
+            feat1, feat2 = feat1.contiguous(), feat2.contiguous()
+        entry = h.lib.p2p_coarse if fmt == 0 else h.lib.p2p_coarse_nhwc16
         b, c, h1, w1 = feat1.shape
         _, _, h2, w2 = feat2.shape
         hA, wA, hB, wB = h1 // ksize, w1 // ksize, h2 // ksize, w2 // ksize
@@ -372,7 +388,7 @@ class Patch2PixB200(nn.Module):
         ncn = torch.empty_like(corr4d) if return_stages else None
         with torch.cuda.device(dev):
             for i in range(b):
-                _lib.check(h.lib.p2p_coarse(h.h, _lib.ptr(feat1[i]), _lib.ptr(feat2[i]), c, h1, w1, h2, w2, ksize,
+                _lib.check(entry(h.h, _lib.ptr(feat1[i]), _lib.ptr(feat2[i]), c, h1, w1, h2, w2, ksize,
                                             _lib.ptr(corr4d[i]), _lib.ptr(code[i]) if code is not None else None,
                                             _lib.ptr(pooled[i]) if pooled is not None else None,
                                             _lib.ptr(ncn[i]) if ncn is not None else None, h.stream()))
@@ -423,8 +439,17 @@ class Patch2PixB200(nn.Module):
 
     def _prepare_pair(self, feats1, feats2, ibatch):
         h = self._handle
-        lv1 = [_check_cuda_f32(feats1[l][ibatch], f'feats1[{l}]') for l in range(4)]
-        lv2 = [_check_cuda_f32(feats2[l][ibatch], f'feats2[{l}]') for l in range(4)]
+        fmt = _feat_format(feats1[1], 'feats1[1]')
+        lvs = []
+        for feats, nm in ((feats1, 'feats1'), (feats2, 'feats2')):
+            lv = [_check_cuda_f32(feats[0][ibatch], f'{nm}[0]')]
+            for l in range(1, 4):
+                if _feat_format(feats[l], f'{nm}[{l}]') != fmt:
+                    raise RuntimeError('all pyramid levels must share dtype / memory format')
+                t = feats[l][ibatch]
+                lv.append(t.contiguous() if fmt == 0 else t)     # a channels-last fp16 item is dense as [h][w][C]
+            lvs.append(lv)
+        lv1, lv2 = lvs
         _, H1, W1 = lv1[0].shape
         _, H2, W2 = lv2[0].shape
         for lv, H, W in ((lv1, H1, W1), (lv2, H2, W2)):
@@ -433,7 +458,8 @@ class Patch2PixB200(nn.Module):
                 raise RuntimeError(f'feature pyramid shapes {[tuple(t.shape) for t in lv]} do not match {exp}')
         a1 = (C.c_void_p * 4)(*[t.data_ptr() for t in lv1])
         a2 = (C.c_void_p * 4)(*[t.data_ptr() for t in lv2])
-        _lib.check(h.lib.p2p_refine_prepare(h.h, a1, a2, H1, W1, H2, W2, h.stream()))
+        entry = h.lib.p2p_refine_prepare if fmt == 0 else h.lib.p2p_refine_prepare_nhwc16
+        _lib.check(entry(h.h, a1, a2, H1, W1, H2, W2, h.stream()))
         return lv1, lv2   # keep alive until the refine kernels have been enqueued
 
     def forward_fine_match(self, feats1, feats2, coarse_matches, psize=16, ptype='center', regressor=None,
@@ -593,10 +619,28 @@ class Patch2PixB200(nn.Module):
         b = im1.shape[0]
         return [f[:b] for f in feats], [f[b:] for f in feats]
 
-    def enable_backbone_graphs(self, height, width, instances=2):
-        """Capture the (launch-bound) backbone for a fixed image size into CUDA graphs."""
+    def _extract16(self):
+        """fp16 / channels_last copy of the backbone (same weights): cuDNN's tensor-core NHWC kernels, and pyramids born
+        in the layouts the path wants (levels 1..4 channels-last fp16; the K-major re-layout and the NCHW->NHWC prep
+        transposes disappear).  fp16 carries the same 10-bit mantissa as the TF32 convolutions PyTorch runs by default."""
+        net = getattr(self, '_extract_half', None)
+        if net is None:
+            import copy
+            net = copy.deepcopy(self.extract).half().to(memory_format=torch.channels_last).eval()
+            object.__setattr__(self, '_extract_half', net)      # not a registered sub-module: state_dict stays the reference's
+        return net
+
+    def _forward_all_fast(self, x32):
+        """x32 [b,3,H,W] fp32 -> [x32, fp16 channels-last levels 1..4]."""
+        feats = self._extract16().forward_all(x32.to(dtype=torch.float16, memory_format=torch.channels_last), [], early_feat=True)
+        return [x32] + feats[1:]
+
+    def enable_backbone_graphs(self, height, width, instances=2, fast=False):
+        """Capture the (launch-bound) backbone for a fixed image size into CUDA graphs.  fast=True: the fp16 /
+        channels_last backbone (levels 1..4 come out channels-last fp16, consumed directly by the C ABI's *_nhwc16 entries)."""
         shape = (1, 3, height, width)
         insts = []
+        fwd = self._forward_all_fast if fast else (lambda x: self.extract.forward_all(x, [], early_feat=True))
         with torch.no_grad(), torch.cuda.device(self.device):
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -604,10 +648,10 @@ class Patch2PixB200(nn.Module):
                 for _ in range(instances):
                     inp = torch.zeros(2, 3, height, width, device=self.device)
                     for _ in range(3):
-                        self.extract.forward_all(inp, [], early_feat=True)
+                        fwd(inp)
                     graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(graph, stream=side):
-                        out = self.extract.forward_all(inp, [], early_feat=True)
+                        out = fwd(inp)
                     insts.append({'inp': inp, 'graph': graph, 'out': out, 'pending': 0})
             torch.cuda.current_stream().wait_stream(side)
             for inst in insts:

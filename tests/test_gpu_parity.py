@@ -396,7 +396,7 @@ def _tie_masks(o_corr, c1, c2, ksize, tie_eps=1e-6, margin_eps=2e-5):
     return fragile
 
 
-def _e2e(net, sd, pair_idx, H, W, ptmax, panc, np_seed=7, shifted=False):
+def _e2e(net, sd, pair_idx, H, W, ptmax, panc, np_seed=7, shifted=False, feats=None):
     """Whole hot path against the oracle.  Stage 1 (coarse): the candidate lists must agree on every row that is not an
     fp32 tie of the reference itself (`_tie_masks`; such rows are counted and reported).  Stage 2 (everything
     downstream: unique/mutual filter, ptmax sampling, anchors, mid, fine) starts from the REFERENCE's candidate list on
@@ -404,7 +404,7 @@ def _e2e(net, sd, pair_idx, H, W, ptmax, panc, np_seed=7, shifted=False):
     production entry (match_from_feats) must in addition reproduce the staged result bit for bit."""
     from oracle import p2p_oracle as O
     from patch2pix_b200.model import filter_coarse
-    f1, f2, c1, c2 = _feats(net, pair_idx, H, W, shifted)
+    f1, f2, c1, c2 = feats if feats is not None else _feats(net, pair_idx, H, W, shifted)
     with torch.no_grad():
         o_corr, o_delta = O.forward_coarse_match(c1[-1], c2[-1], sd, 2)
         o_m, o_s = O.cal_coarse_matches(o_corr, o_delta, 2, upsample=O.UPSAMPLE, center=True)
@@ -994,3 +994,42 @@ def test_estimate_matches_from_files(tmp_path, consensus_sd):
     # nothing passes -> everything is kept
     m3, s3, _ = estimate_matches(net, ts[0], ts[1], scs[0], scs[1], io_thres=2.0)
     assert len(m3) == n_all and len(s3) == n_all
+
+
+def test_backbone_fp16_channels_last_path(consensus_sd):
+    """The fp16 / channels_last backbone of the end-to-end path: pyramids come out channels-last fp16 and are consumed
+    directly (p2p_coarse_nhwc16 / p2p_refine_prepare_nhwc16).  The hot path on THOSE features equals the oracle on the
+    same values (up-cast to fp32 NCHW): proposals exact up to reference ties, every row within tolerance; and equals
+    our own NCHW-fp32 entry points fed the same values (same arithmetic behind a different load)."""
+    from patch2pix_b200.model import Patch2PixB200
+    from patch2pix_b200.synth import synthetic_pair_shifted
+    cfg = _cfg(8)
+    cfg.weights_dict = consensus_sd
+    net = Patch2PixB200(cfg)
+    H, W = 240, 320
+    im1, im2 = synthetic_pair_shifted(6, H, W)
+    with torch.no_grad():
+        net.enable_backbone_graphs(H, W, instances=2, fast=True)
+        f1, f2 = net.extract_pair(im1.pin_memory(), im2.pin_memory())
+        torch.cuda.synchronize()
+        assert f1[1].dtype == torch.float16 and f1[0].dtype == torch.float32
+        u1 = [t.float().contiguous() for t in f1]
+        u2 = [t.float().contiguous() for t in f2]
+        c1, c2 = [t.cpu() for t in u1], [t.cpu() for t in u2]
+        o, g, coarse = _e2e(net, consensus_sd, 6, H, W, 100, 8, np_seed=3, feats=(f1, f2, c1, c2))
+        rep = dict(_e2e_report(o, g), **coarse)
+        # the same values through the NCHW fp32 entry points
+        np.random.seed(3)
+        a = net.match_from_feats(f1, f2, 2, ptmax=100, return_all=True)
+        np.random.seed(3)
+        b = net.match_from_feats(u1, u2, 2, ptmax=100, return_all=True)
+        torch.cuda.synchronize()
+        assert torch.equal(a[4][0], b[4][0])
+        rep['nhwc16_vs_nchw32_entry_max_px'] = (a[0][0] - b[0][0]).abs().max().item()
+        assert rep['nhwc16_vs_nchw32_entry_max_px'] < 0.05
+        # deviation of the fp16 backbone from the fp32 one (reported; the backbone is not part of the path)
+        ref = net.extract.forward_all(torch.cat([im1, im2]).cuda(), [], True)
+        rep['fp16_vs_fp32_backbone_rel_dev'] = max(((x[:1].float() - y[:1]).abs().max() / y.abs().max()).item() for x, y in zip(f1[1:], ref[1:]))
+        _report('backbone_fp16_channels_last', rep)
+        _assert_e2e(rep)
+        assert rep['fp16_vs_fp32_backbone_rel_dev'] < 3e-2, rep
