@@ -64,6 +64,7 @@ def parse():
     ap.add_argument('--pairs', type=int, default=0,
                     help='strong-scaling mode (BASELINE configs[4]): this many pairs in total, sharded over the ranks; '
                          'rank 0 re-computes a sample of the other ranks\' pairs and checks bit-equality')
+    ap.add_argument('--depth', type=int, default=3, help='pairs in flight per GPU (coarse stages enqueued ahead of the host sync)')
     ap.add_argument('--legacy-workload', action='store_true', help="round-1 generator (13-17 mutual matches per pair)")
     ap.add_argument('--cpu-sample-patches', type=int, default=200)
     return ap.parse_args()
@@ -367,15 +368,21 @@ def run_ours(args):
         if keep is not None:
             keep.append(cm[0])
 
+    depth = max(1, args.depth)
+
     def hot_loop(first, steps, record, keep=None):
-        prev = None
+        # `depth` pairs in flight: the coarse stages of the next pairs are already queued when the host waits for the
+        # mutual-match count of the oldest one, so the GPU always has more than a coarse stage of work ahead of the host
+        from collections import deque
+        q = deque()
         for j in range(steps):
-            tk = hot_submit(first + j)
-            if prev is not None:
-                hot_finish(prev[0], prev[1], keep)
-            prev = (tk, j if record else None)
-        if prev is not None:
-            hot_finish(prev[0], prev[1], keep)
+            q.append((hot_submit(first + j), j if record else None))
+            if len(q) >= depth:
+                tk, slot = q.popleft()
+                hot_finish(tk, slot, keep)
+        while q:
+            tk, slot = q.popleft()
+            hot_finish(tk, slot, keep)
 
     def e2e_submit(i):
         a, b = pinned[slots[i]]
@@ -390,14 +397,16 @@ def run_ours(args):
         host_out[:, 4].copy_(fine_p[0], non_blocking=True)
 
     def e2e_loop(first, steps, host_outs):
-        prev = None
+        from collections import deque
+        q = deque()
         for j in range(steps):
-            tk = e2e_submit(first + j)
-            if prev is not None:
-                e2e_finish(prev, host_outs[(j - 1) % len(host_outs)])
-            prev = tk
-        if prev is not None:
-            e2e_finish(prev, host_outs[(steps - 1) % len(host_outs)])
+            q.append((e2e_submit(first + j), j))
+            if len(q) >= depth:
+                tk, jj = q.popleft()
+                e2e_finish(tk, host_outs[jj % len(host_outs)])
+        while q:
+            tk, jj = q.popleft()
+            e2e_finish(tk, host_outs[jj % len(host_outs)])
         torch.cuda.current_stream().synchronize()
 
     def barrier():
@@ -487,13 +496,13 @@ def run_ours(args):
         # backbone in PyTorch's default cuDNN mode (TF32 convolutions allowed, as the reference would run on a GPU);
         # the fp32-backbone variant is measured beside it (parity: tests/test_gpu_parity.py::test_backbone_graph_tf32_path)
         e2e_ms = {}
-        host_outs = [torch.empty(n_patches, 5).pin_memory() for _ in range(2)]
+        host_outs = [torch.empty(n_patches, 5).pin_memory() for _ in range(depth + 1)]
         for mode in (['fp32'] if args.backbone_fp32 else ['tf32', 'fp16', 'fp32']):
             if strong and mode != 'tf32' and not args.backbone_fp32:
                 continue
             torch.backends.cudnn.allow_tf32 = mode != 'fp32'
             torch.backends.cudnn.benchmark = True
-            net.enable_backbone_graphs(H, W, instances=2, fast=mode == 'fp16')
+            net.enable_backbone_graphs(H, W, instances=depth + 1, fast=mode == 'fp16')
             e2e_loop(0, max(min(Wm, 3), 1), host_outs)
 
             def e2e_region(steps):
@@ -587,7 +596,7 @@ def run_ours(args):
                        'total_pairs': pairs, 'distinct_proposals_first_pairs': distinct,
                        'l2': f'{len(imgs)} distinct pairs cycled per rank; per-step working set (~3 GB of scratch written and '
                              f're-read) >> 126 MB L2',
-                       'pipelining': 'two pairs in flight per GPU (coarse of pair i is enqueued before the host sync of pair i-1)',
+                       'pipelining': f'{depth} pairs in flight per GPU (the coarse stages of the next pairs are enqueued before the host sync of the oldest)',
                        'options': opts},
             'e2e': e2e, 'gpu_launches': launches, 'roofline': roofline, 'kernels': kern, 'clocks': clocks,
             'cpu_baseline': cpu, 'refine_only': refine_only, 'cross_rank_check': cross,

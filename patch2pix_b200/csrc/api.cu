@@ -14,6 +14,29 @@ static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 long long g_launch_count = 0;
 
+int ensure_dyn_smem(const void* kernel, int bytes) {
+  struct Key { const void* k; int dev; };
+  static thread_local std::vector<std::pair<Key, int>> granted;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (auto& g : granted)
+    if (g.first.k == kernel && g.first.dev == dev) {
+      if (g.second >= bytes) return 0;
+      if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) {
+        set_last_error(std::string("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: ") + cudaGetErrorString(cudaGetLastError()));
+        return -2;
+      }
+      g.second = bytes;
+      return 0;
+    }
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) {
+    set_last_error(std::string("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: ") + cudaGetErrorString(cudaGetLastError()));
+    return -2;
+  }
+  granted.push_back({Key{kernel, dev}, bytes});
+  return 0;
+}
+
 int Arena::reserve(size_t bytes) {
   off = 0;
   if (bytes <= cap) return 0;

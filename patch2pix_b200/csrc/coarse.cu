@@ -198,10 +198,10 @@ int launch_l2norm_perm_kmajor_pair(const float* in1, const float* in2, __half* h
   dim3 grid(cdiv(nmax, 32), 2);
   const size_t smem = sizeof(float) * C * 33;
   if (ksize == 2) {
-    P2P_CUDA_OK(cudaFuncSetAttribute(l2norm_perm_kmajor_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    P2P_ENSURE_SMEM(l2norm_perm_kmajor_kernel<2>, smem);
     l2norm_perm_kmajor_kernel<2><<<grid, 256, smem, st>>>(a, C);
   } else {
-    P2P_CUDA_OK(cudaFuncSetAttribute(l2norm_perm_kmajor_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    P2P_ENSURE_SMEM(l2norm_perm_kmajor_kernel<1>, smem);
     l2norm_perm_kmajor_kernel<1><<<grid, 256, smem, st>>>(a, C);
   }
   P2P_LAUNCH_OK();
@@ -691,12 +691,12 @@ int launch_neigh_consensus(const float* x, int hA, int wA, int hB, int wB, const
     const size_t smem = sizeof(float) * (81 * 32 + 9 * 10 * (wB + 4));
     if (block.x * block.y <= 160) {   // small B grids: cap registers so that 4 blocks share an SM
       auto k = nc_layer1_kernel<160, 4>;
-      P2P_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      P2P_ENSURE_SMEM(k, smem);
       P2P_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       k<<<grid, block, smem, st>>>(x, hA, wA, hB, wB, w1p, b1p, hidden);
     } else {
       auto k = nc_layer1_kernel<512, 1>;
-      P2P_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      P2P_ENSURE_SMEM(k, smem);
       P2P_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       k<<<grid, block, smem, st>>>(x, hA, wA, hB, wB, w1p, b1p, hidden);
     }
@@ -726,11 +726,11 @@ int launch_neigh_consensus(const float* x, int hA, int wA, int hB, int wB, const
     }
     const int grid = hA * cdiv(wA, JB);
     if (wB % 4 == 0) {
-      P2P_CUDA_OK(cudaFuncSetAttribute(nc_layer2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      P2P_ENSURE_SMEM(nc_layer2_kernel<true>, smem);
       P2P_CUDA_OK(cudaFuncSetAttribute(nc_layer2_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       nc_layer2_kernel<true><<<grid, block, smem, st>>>(hidden, hA, wA, hB, wB, JB, w2p, b2, out);
     } else {
-      P2P_CUDA_OK(cudaFuncSetAttribute(nc_layer2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      P2P_ENSURE_SMEM(nc_layer2_kernel<false>, smem);
       P2P_CUDA_OK(cudaFuncSetAttribute(nc_layer2_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
       nc_layer2_kernel<false><<<grid, block, smem, st>>>(hidden, hA, wA, hB, wB, JB, w2p, b2, out);
     }
@@ -965,7 +965,7 @@ int launch_unique_rows(const long long* rows, int n, int mutual, const float* sc
     unique_rows_kernel<<<1, 1024, 0, st>>>(rows, n, P, mutual, scores, thres, ids_out, count_out, gscratch);
   } else {
     const size_t smem = (size_t)P * 12;
-    P2P_CUDA_OK(cudaFuncSetAttribute(unique_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    P2P_ENSURE_SMEM(unique_rows_kernel, smem);
     unique_rows_kernel<<<1, 1024, smem, st>>>(rows, n, P, mutual, scores, thres, ids_out, count_out, nullptr);
   }
   P2P_LAUNCH_OK();

@@ -38,6 +38,15 @@ extern long long g_launch_count;  // kernels enqueued by this library (bench.py'
     P2P_CUDA_OK(cudaGetLastError());   \
   } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) only when this kernel on this device has not been granted at least
+// `bytes` yet (the attribute is sticky; setting it on every launch costs a driver call per kernel per pair).
+int ensure_dyn_smem(const void* kernel, int bytes);
+#define P2P_ENSURE_SMEM(kern, bytes)                                            \
+  do {                                                                          \
+    int _rc = ::p2p::ensure_dyn_smem(reinterpret_cast<const void*>(kern), (int)(bytes)); \
+    if (_rc) return _rc;                                                        \
+  } while (0)
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -30,6 +30,7 @@
 // of tile i+1.
 #include <math.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "kernels.h"
@@ -79,15 +80,30 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
   lo = *reinterpret_cast<uint4*>(l);
 }
 
+// operands that are bounded by construction (|x * sx| < 4096): no saturation needed
+__device__ __forceinline__ void split8_bounded(const float* v, uint4& hi, uint4& lo) {
+  __half2 h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    const float2 f = __half22float2(h[i]);
+    l[i] = __floats2half2_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+  }
+  hi = *reinterpret_cast<uint4*>(h);
+  lo = *reinterpret_cast<uint4*>(l);
+}
+
 // ------------------------------------------------------------------------------------------------
 // layer 1.  Tile = (A cell a, 128 consecutive B cells).  The 9 A-neighbours' B segments (with a one-row halo) are
-// staged in shared memory with coalesced loads; four producer warps (one tile row per thread) then build the 81-tap
-// im2col row from shared memory, scale, split to fp16 hi/lo and store the swizzled operand chunks.
-// 384 threads (warp 1 MMA, 2 TMEM, 4..7 epilogue, 8..11 producers), 2 CTAs per SM (2 x 32 KB operand stages).
+// staged in shared memory with cp.async (double-buffered); sixteen producer warps (four threads per tile row, each a
+// quarter of the 11 tap chunks) then build the 81-tap im2col row from shared memory, scale, split to fp16 hi/lo and
+// store the swizzled operand chunks -- the kernel is bound by this scalar work, hence the wide producer group.
+// 768 threads (warp 1 MMA, 2 TMEM, 4..7 epilogue, 8..23 producers), 1 CTA per SM, 4 x 32 KB operand stages.
 // ------------------------------------------------------------------------------------------------
-constexpr int kL1Stages = 2;
+constexpr int kL1Stages = 4;
+constexpr int kL1Threads = 768, kL1Producers = 512;
 
-__global__ void __launch_bounds__(384, 2) nc_l1_umma_kernel(const __grid_constant__ NcParams p) {
+__global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_constant__ NcParams p) {
   constexpr int STAGE_BYTES = 2 * kNcAtom;         // A_hi + A_lo of one atom
   constexpr int WATOM = 32 * 128;
   constexpr uint32_t IDESC = make_idesc_f16(128, 32);
@@ -106,12 +122,12 @@ __global__ void __launch_bounds__(384, 2) nc_l1_umma_kernel(const __grid_constan
   const int TB = (p.nB + 127) >> 7;
   const int span = 128 + 2 * p.wB + 2;
 
-  for (int i = threadIdx.x; i < kL1Stages * STAGE_BYTES / 16; i += 384) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = threadIdx.x; i < 4 * WATOM / 16; i += 384)
+  for (int i = threadIdx.x; i < kL1Stages * STAGE_BYTES / 16; i += kL1Threads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < 4 * WATOM / 16; i += kL1Threads)
     reinterpret_cast<uint4*>(wsm)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kL1Stages; ++i) {
-      mbar_init(&full_bar[i], 128);
+      mbar_init(&full_bar[i], kL1Producers);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -158,8 +174,10 @@ __global__ void __launch_bounds__(384, 2) nc_l1_umma_kernel(const __grid_constan
       }
     }
   } else if (warp >= 8) {
-    // ===================== producers: 128 threads, one tile row each =====================
-    const int r = threadIdx.x - 256;
+    // ===================== producers: 512 threads = 128 tile rows x 4 chunk quarters =====================
+    const int ptid = threadIdx.x - 256;
+    const int r = ptid & 127;
+    const int qt = ptid >> 7;          // warp-uniform: chunks qt and qt + 4 of atom 0, chunk qt of atom 1 (qt < 3)
     float sx, sh;
     nc_scales(p, sx, sh);
     // stage the 9 A-neighbour segments [b0 - wB - 1, b0 + 128 + wB + 1) of a tile with cp.async (zero fill outside
@@ -168,17 +186,14 @@ __global__ void __launch_bounds__(384, 2) nc_l1_umma_kernel(const __grid_constan
       const int a = tile / TB, b0 = (tile - a * TB) << 7;
       const int ia = a / p.wA, ja = a - ia * p.wA;
       float* dst = xs + (size_t)buf * 9 * span;
-      for (int d = 0; d < 9; ++d) {
+      for (int idx = ptid; idx < 9 * span; idx += kL1Producers) {
+        const int d = idx / span, j = idx - d * span;
         const int i2 = ia + d / 3 - 1, j2 = ja + d % 3 - 1;
-        const bool av = i2 >= 0 && i2 < p.hA && j2 >= 0 && j2 < p.wA;
-        const float* src = p.x + (size_t)(av ? i2 * p.wA + j2 : 0) * p.nB;
-        for (int j = r; j < span; j += 128) {
-          const int b = b0 - p.wB - 1 + j;
-          const bool ok = av && b >= 0 && b < p.nB;
-          const unsigned sz = ok ? 4u : 0u;
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst + d * span + j)), "l"(ok ? src + b : p.x), "r"(sz)
-                       : "memory");
-        }
+        const int b = b0 - p.wB - 1 + j;
+        const bool ok = i2 >= 0 && i2 < p.hA && j2 >= 0 && j2 < p.wA && b >= 0 && b < p.nB;
+        const float* src = ok ? p.x + (size_t)(i2 * p.wA + j2) * p.nB + b : p.x;
+        const unsigned sz = ok ? 4u : 0u;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst + idx)), "l"(src), "r"(sz) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -192,7 +207,7 @@ __global__ void __launch_bounds__(384, 2) nc_l1_umma_kernel(const __grid_constan
       } else {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");          // every producer's copies of this tile have landed
+      asm volatile("bar.sync 1, 512;" ::: "memory");          // every producer's copies of this tile have landed
       const int a = tile / TB, b0 = (tile - a * TB) << 7;
       const int b = b0 + r;
       const bool rv = b < p.nB;
@@ -200,34 +215,56 @@ __global__ void __launch_bounds__(384, 2) nc_l1_umma_kernel(const __grid_constan
       // validity of the B-side taps: bits 0..2 rows (k-1, k, k+1), bits 3..5 columns (l-1, l, l+1)
       const unsigned m = rv ? ((k > 0 ? 1u : 0u) | 2u | (k + 1 < p.hB ? 4u : 0u) | (l > 0 ? 8u : 0u) | 16u | (l + 1 < p.wB ? 32u : 0u)) : 0u;
       const float* xr = xs + (size_t)buf * 9 * span + r;
+      auto chunk = [&](auto ATOM, auto CH, uint8_t* st) {
+        constexpr int atom = decltype(ATOM)::value, c = decltype(CH)::value;
+        float val[8];
 #pragma unroll
-      for (int atom = 0; atom < 2; ++atom, ++it) {
-        const int s = it % kL1Stages;
-        mbar_wait(&empty_bar[s], ((uint32_t)(it / kL1Stages) & 1u) ^ 1u);
-        uint8_t* st = smem + (size_t)s * STAGE_BYTES + r * 128;
-#pragma unroll
-        for (int c = 0; c < (atom == 0 ? 8 : 3); ++c) {          // chunks of 8 taps; atom 1 holds taps 64..80 (+ zeros)
-          float val[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int t = (atom * 8 + c) * 8 + i;                // compile-time after unrolling
-            float f = 0.f;
-            if (t < 81) {
-              const int d = t / 9, tk = (t / 3) % 3, tl = t % 3;
-              const unsigned need = (1u << tk) | (8u << tl);
-              f = ((m & need) == need) ? xr[d * span + tk * p.wB + tl] * sx : 0.f;     // A-invalid segments hold zeros
-            }
-            val[i] = f;
+        for (int i = 0; i < 8; ++i) {
+          constexpr int dummy = 0;
+          const int t = (atom * 8 + c) * 8 + i;                  // compile-time
+          float f = 0.f;
+          if (t < 81) {
+            const int d = t / 9, tk = (t / 3) % 3, tl = t % 3;
+            const unsigned need = (1u << tk) | (8u << tl);
+            f = ((m & need) == need) ? xr[d * span + tk * p.wB + tl] * sx : 0.f;     // A-invalid segments hold zeros
           }
-          uint4 hi, lo;
-          split8(val, hi, lo);
-          *reinterpret_cast<uint4*>(st + ((c ^ (r & 7)) << 4)) = hi;
-          *reinterpret_cast<uint4*>(st + kNcAtom + ((c ^ (r & 7)) << 4)) = lo;
+          (void)dummy;
+          val[i] = f;
         }
-        fence_proxy_async();
-        mbar_arrive(&full_bar[s]);
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");          // all reads of this buffer done before it is refilled
+        uint4 hi, lo;
+        split8_bounded(val, hi, lo);
+        *reinterpret_cast<uint4*>(st + ((c ^ (r & 7)) << 4)) = hi;
+        *reinterpret_cast<uint4*>(st + kNcAtom + ((c ^ (r & 7)) << 4)) = lo;
+      };
+      auto build = [&](auto QT) {
+        constexpr int Q = decltype(QT)::value;
+        {   // atom 0: chunks Q and Q + 4
+          const int s = it % kL1Stages;
+          mbar_wait(&empty_bar[s], ((uint32_t)(it / kL1Stages) & 1u) ^ 1u);
+          uint8_t* st = smem + (size_t)s * STAGE_BYTES + r * 128;
+          chunk(std::integral_constant<int, 0>{}, std::integral_constant<int, Q>{}, st);
+          chunk(std::integral_constant<int, 0>{}, std::integral_constant<int, Q + 4>{}, st);
+          fence_proxy_async();
+          mbar_arrive(&full_bar[s]);
+          ++it;
+        }
+        {   // atom 1: chunk Q (taps 64 + 8Q ..; Q = 3 has nothing to write, chunks 3..7 stay zero)
+          const int s = it % kL1Stages;
+          mbar_wait(&empty_bar[s], ((uint32_t)(it / kL1Stages) & 1u) ^ 1u);
+          if (Q < 3) {
+            uint8_t* st = smem + (size_t)s * STAGE_BYTES + r * 128;
+            chunk(std::integral_constant<int, 1>{}, std::integral_constant<int, (Q < 3 ? Q : 0)>{}, st);
+            fence_proxy_async();
+          }
+          mbar_arrive(&full_bar[s]);
+          ++it;
+        }
+      };
+      if (qt == 0) build(std::integral_constant<int, 0>{});
+      else if (qt == 1) build(std::integral_constant<int, 1>{});
+      else if (qt == 2) build(std::integral_constant<int, 2>{});
+      else build(std::integral_constant<int, 3>{});
+      asm volatile("bar.sync 1, 512;" ::: "memory");          // all reads of this buffer done before it is refilled
       buf ^= 1;
     }
   } else if (warp >= 4) {
@@ -367,24 +404,25 @@ __global__ void __launch_bounds__(512, 1) nc_l2_umma_kernel(const __grid_constan
 #pragma unroll
         for (int ps = 0; ps < 4; ++ps) q[ps] = ((mask[ps] & need) == need) ? __ldg(base[ps] + off) : make_uint4(0, 0, 0, 0);
       };
-      uint4 cur[4], nxt[4];
-      load_tap(0, cur);
-#pragma unroll 1
+      // three taps' lines in flight per thread (the loads are latency-bound: 8 of 9 lines hit L1, one comes from L2/HBM)
+      uint4 q[3][4];
+      load_tap(0, q[0]);
+      load_tap(1, q[1]);
+      load_tap(2, q[2]);
+#pragma unroll
       for (int t = 0; t < 9; ++t, ++it) {
-        if (t + 1 < 9) load_tap(t + 1, nxt);             // next tap's lines are in flight while this tap is stored
         const int s = it % kL2Stages;
         mbar_wait(&empty_bar[s], ((uint32_t)(it / kL2Stages) & 1u) ^ 1u);
         uint8_t* st = smem + (size_t)s * kNcAtom;
 #pragma unroll
         for (int ps = 0; ps < 4; ++ps) {
           const int row = ps * 32 + r0;
-          *reinterpret_cast<uint4*>(st + row * 128 + ((c ^ (row & 7)) << 4)) = cur[ps];
+          *reinterpret_cast<uint4*>(st + row * 128 + ((c ^ (row & 7)) << 4)) = q[t % 3][ps];
         }
+        if (t + 3 < 9) load_tap(t + 3, q[t % 3]);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[s]);
-#pragma unroll
-        for (int ps = 0; ps < 4; ++ps) cur[ps] = nxt[ps];
       }
     }
   } else if (warp >= 4) {
@@ -587,9 +625,9 @@ int launch_neigh_consensus_umma(const float* x, int hA, int wA, int hB, int wB, 
     const int smem = kL1Stages * 2 * kNcAtom + 2 * 2 * 32 * 128 + 2 * 9 * (128 + 2 * wB + 2) * 4 + 1024;
     P2P_REQUIRE(smem <= 200 * 1024, "NeighConsensus layer 1: B grid too wide for the shared-memory staging (wB <= ~700)");
     auto k = nc_l1_umma_kernel;
-    P2P_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const int grid = p.tiles < 2 * num_sms ? p.tiles : 2 * num_sms;       // 2 CTAs per SM
-    k<<<grid, 384, smem, st>>>(p);
+    P2P_ENSURE_SMEM(k, smem);
+    const int grid = p.tiles < num_sms ? p.tiles : num_sms;
+    k<<<grid, kL1Threads, smem, st>>>(p);
     P2P_LAUNCH_OK();
   }
   {
@@ -597,7 +635,7 @@ int launch_neigh_consensus_umma(const float* x, int hA, int wA, int hB, int wB, 
     p.tiles = (int)vt;
     const int smem = kL2Stages * kNcAtom + 9 * 16 * 128 + 1024;
     auto k = nc_l2_umma_kernel;
-    P2P_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    P2P_ENSURE_SMEM(k, smem);
     k<<<p.tiles < num_sms ? p.tiles : num_sms, 512, smem, st>>>(p);
     P2P_LAUNCH_OK();
   }

@@ -1100,7 +1100,7 @@ static int launch_one(const UmmaGemmParams& p, int grid, cudaStream_t st) {
   constexpr int NOP = (PASSES == 3) ? 2 : 1;
   const int smem = STAGES * NOP * (kATile + (PAIR ? kBTile / 2 : kBTile)) + 1024;
   auto kern = umma_gemm_kernel<PASSES, SEGMENTED, EPI, FUSED, PAIR>;
-  P2P_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  P2P_ENSURE_SMEM(kern, smem);
   if (PAIR) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
@@ -1153,7 +1153,7 @@ int launch_umma_gemm(const UmmaGemmParams& p, int epi, int passes, int num_sms, 
     if (p.pair) {
       const int smem = kF2PairStages * kF2PairStageBytes + 3072 * 8 + 1024;
       auto kern = umma_conv1_fused_kernel<true>;
-      P2P_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      P2P_ENSURE_SMEM(kern, smem);
       const int ptiles = (p.m_tiles + 1) / 2;
       const int max_clusters = num_sms >= 2 ? num_sms / 2 : 1;
       const int clusters = ptiles < max_clusters ? ptiles : max_clusters;
@@ -1175,7 +1175,7 @@ int launch_umma_gemm(const UmmaGemmParams& p, int epi, int passes, int num_sms, 
     }
     const int smem = kF2Stages * kF2StageBytes + 3072 * 8 + 1024;
     auto kern = umma_conv1_fused_kernel<false>;
-    P2P_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    P2P_ENSURE_SMEM(kern, smem);
     const int g2 = p.m_tiles < num_sms ? p.m_tiles : num_sms;
     kern<<<g2, 512, smem, st>>>(p);
     P2P_LAUNCH_OK();
@@ -1196,7 +1196,7 @@ int launch_conv1_tma(const Conv1TmaParams& p, int num_sms, cudaStream_t st) {
   P2P_REQUIRE(p.nsteps > 0 && p.m_tiles > 0, "conv1 (window-map TMA): empty problem");
   const int smem = kC1Stages * kC1StageBytes + 1024;
   auto kern = umma_conv1_tma_kernel;
-  P2P_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  P2P_ENSURE_SMEM(kern, smem);
   const int ptiles = (p.m_tiles + 1) / 2;
   const int max_clusters = num_sms >= 2 ? num_sms / 2 : 1;
   const int clusters = ptiles < max_clusters ? ptiles : max_clusters;

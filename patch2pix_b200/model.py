@@ -47,10 +47,33 @@ def _feat_format(t, name):
     raise RuntimeError(f'{name} must be float32 NCHW or channels-last float16')
 
 
+class _PinnedPool:
+    """Recycled pinned int32 staging buffers.  A per-step `torch.empty(pin_memory=True)` can fall through PyTorch's
+    caching host allocator to cudaHostAlloc (hundreds of microseconds, serialising) whenever the cached block is still
+    marked in use; here a buffer returns to the pool with the event after which it may be rewritten."""
+
+    def __init__(self):
+        self._free = {}
+
+    def get(self, n):
+        lst = self._free.setdefault(n, [])
+        for i, (t, ev) in enumerate(lst):
+            if ev is None or ev.query():
+                lst.pop(i)
+                return t
+        return torch.empty(n, dtype=torch.int32).pin_memory()
+
+    def put(self, t, ev=None):
+        self._free.setdefault(t.numel(), []).append((t, ev))
+
+
+_pinned = _PinnedPool()
+
+
 class _UniqueTicket:
     """unique_rows in flight: ids buffer on the device, counters on their way to pinned host memory.
-    Every ticket owns its pinned counter buffer (PyTorch's caching host allocator recycles it, stream-aware,
-    once the ticket is dropped), so any number of tickets can be outstanding."""
+    Every ticket owns its pinned counter buffer (taken from / returned to a pool), so any number of tickets can be
+    outstanding."""
 
     def __init__(self, ids, cnt_host, event, thres):
         self.ids, self.cnt_host, self.event, self.thres = ids, cnt_host, event, thres
@@ -61,6 +84,8 @@ class _UniqueTicket:
         if self.n is None:
             self.event.synchronize()
             self.n, bad, self.n_pass_selected, self.n_pass_all = self.cnt_host.tolist()
+            _pinned.put(self.cnt_host)           # the copy has completed: the buffer may be reused at once
+            self.cnt_host = None
             if bad:
                 raise RuntimeError('filter_coarse: match coordinates must lie in [0, 65535]')
         return self.n
@@ -77,7 +102,7 @@ def unique_rows_submit(rows, mutual=True, handle=None, scores=None, thres=0.0):
     h = handle or _lib.default_handle(rows.device)
     ids = torch.empty(max(n, 1), dtype=torch.int32, device=rows.device)
     cnt = torch.empty(4, dtype=torch.int32, device=rows.device)
-    cnt_host = torch.empty(4, dtype=torch.int32, pin_memory=True)
+    cnt_host = _pinned.get(4)
     if scores is not None:
         scores = _check_cuda_f32(scores.flatten(), 'scores')
     with torch.cuda.device(rows.device):
@@ -133,9 +158,12 @@ def _filter_coarse_core(coarse_matches, match_scores, ncn_thres, mutual, ptmax, 
                 iids = np.arange(n_rows)
                 np.random.shuffle(iids)
                 iids = np.tile(iids, (ptmax // n_rows + 1))[:ptmax]
-                stage = torch.empty(ptmax, dtype=torch.int32, pin_memory=True)
+                stage = _pinned.get(int(ptmax))
                 stage.numpy()[:] = iids
                 sel, m = stage.to(imatches.device, non_blocking=True), int(ptmax)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(imatches.device))
+                _pinned.put(stage, ev)           # reusable once the host-to-device copy has executed
             if ids is None and sel is None and panc == 1:
                 om, osc, an = imatches, iscores, None       # nothing filtered: the input passes unchanged
             else:
