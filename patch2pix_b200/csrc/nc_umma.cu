@@ -52,6 +52,7 @@ struct NcParams {
   float wsum1, b1max;          // max_c sum_taps |w1|, max |b1|: bound of the hidden activations
   float inv_sw1, inv_sw2;      // 1 / (power-of-two weight scales)
   int tiles;
+  int l1_bufs;                 // layer-1 staging buffers: 2 (copies of tile i+1 overlap tile i) or 1 (wide B grids)
 };
 
 // Power-of-two activation scales: max|x| * sx and (hidden bound) * sh land in [2048, 4096).
@@ -94,14 +95,25 @@ __device__ __forceinline__ void split8_bounded(const float* v, uint4& hi, uint4&
 }
 
 // ------------------------------------------------------------------------------------------------
-// layer 1.  Tile = (A cell a, 128 consecutive B cells).  The 9 A-neighbours' B segments (with a one-row halo) are
-// staged in shared memory with cp.async (double-buffered); sixteen producer warps (four threads per tile row, each a
-// quarter of the 11 tap chunks) then build the 81-tap im2col row from shared memory, scale, split to fp16 hi/lo and
-// store the swizzled operand chunks -- the kernel is bound by this scalar work, hence the wide producer group.
+// layer 1.  Tile = (A cell a, 128 consecutive B cells).  The 9 A-neighbours' B rows touched by the tile are staged in
+// shared memory with cp.async as a zero-PADDED 2-D block (one extra row above/below, one extra column left/right,
+// zero outside the volume; double-buffered: tile i+1 is in flight while tile i is built), so a tap is a plain
+// `ld.shared [row base + tk*pitch + tl]` with no validity logic.  Sixteen producer warps (four threads per tile row,
+// each a quarter of the 11 tap chunks) scale, split to fp16 hi/lo and store the swizzled operand chunks.
+// The three products of the hi/lo split (lo*hi, hi*lo, hi*hi) accumulate in three SEPARATE TMEM blocks -- three
+// independent MMA chains instead of one 18-deep dependent chain of tiny (N = 32) MMAs -- and are summed by the epilogue.
 // 768 threads (warp 1 MMA, 2 TMEM, 4..7 epilogue, 8..23 producers), 1 CTA per SM, 4 x 32 KB operand stages.
 // ------------------------------------------------------------------------------------------------
 constexpr int kL1Stages = 4;
 constexpr int kL1Threads = 768, kL1Producers = 512;
+
+__host__ __device__ inline int nc_l1_rows(int wB) { return 127 / wB + 4; }      // B rows a tile can touch, + halo
+
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
 
 __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_constant__ NcParams p) {
   constexpr int STAGE_BYTES = 2 * kNcAtom;         // A_hi + A_lo of one atom
@@ -110,7 +122,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* wsm = smem + kL1Stages * STAGE_BYTES;                          // [hi|lo][atom] weight images, 16 KB
-  float* xs = reinterpret_cast<float*>(wsm + 4 * WATOM);                  // [2 buffers][9][span]
+  float* xs = reinterpret_cast<float*>(wsm + 4 * WATOM);                  // [2 buffers][9][rows][pitch]
   __shared__ __align__(8) uint64_t full_bar[kL1Stages];
   __shared__ __align__(8) uint64_t empty_bar[kL1Stages];
   __shared__ __align__(8) uint64_t tfull_bar[2];
@@ -120,7 +132,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles = p.tiles;
   const int TB = (p.nB + 127) >> 7;
-  const int span = 128 + 2 * p.wB + 2;
+  const int PW = p.wB + 2, NR = nc_l1_rows(p.wB), DS = NR * PW;           // pitch, rows, floats per A-neighbour block
 
   for (int i = threadIdx.x; i < kL1Stages * STAGE_BYTES / 16; i += kL1Threads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   for (int i = threadIdx.x; i < 4 * WATOM / 16; i += kL1Threads)
@@ -136,7 +148,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(&tmem_base_smem, 64);
+  if (warp == 2) tmem_alloc(&tmem_base_smem, 256);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -150,8 +162,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
         const int slot = tl & 1;
         mbar_wait(&tempty_bar[slot], ((uint32_t)(tl >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(slot * 32);
-        uint32_t acc = 0u;
+        const uint32_t d0 = tmem_base + (uint32_t)(slot * 96);            // three 32-column blocks: lo*hi, hi*lo, hi*hi
 #pragma unroll
         for (int atom = 0; atom < 2; ++atom, ++it) {
           const int s = it % kL1Stages;
@@ -163,11 +174,11 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
           const uint64_t w_hi = make_sw128_desc(wb), w_lo = make_sw128_desc(wb + 2 * WATOM);
           const int nk = atom == 0 ? 4 : 2;           // taps 64..80 live in the first two K16 slices of atom 1
           for (int kk = 0; kk < nk; ++kk) {
-            umma_f16(d_tmem, a_lo + 2 * kk, w_hi + 2 * kk, IDESC, acc);
-            acc = 1u;
+            const uint32_t acc = (atom > 0 || kk > 0) ? 1u : 0u;
+            umma_f16(d0, a_lo + 2 * kk, w_hi + 2 * kk, IDESC, acc);
+            umma_f16(d0 + 32, a_hi + 2 * kk, w_lo + 2 * kk, IDESC, acc);
+            umma_f16(d0 + 64, a_hi + 2 * kk, w_hi + 2 * kk, IDESC, acc);
           }
-          for (int kk = 0; kk < nk; ++kk) umma_f16(d_tmem, a_hi + 2 * kk, w_lo + 2 * kk, IDESC, 1u);
-          for (int kk = 0; kk < nk; ++kk) umma_f16(d_tmem, a_hi + 2 * kk, w_hi + 2 * kk, IDESC, 1u);
           umma_commit(&empty_bar[s]);
         }
         umma_commit(&tfull_bar[slot]);
@@ -180,28 +191,32 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
     const int qt = ptid >> 7;          // warp-uniform: chunks qt and qt + 4 of atom 0, chunk qt of atom 1 (qt < 3)
     float sx, sh;
     nc_scales(p, sx, sh);
-    // stage the 9 A-neighbour segments [b0 - wB - 1, b0 + 128 + wB + 1) of a tile with cp.async (zero fill outside
-    // the volume), double-buffered: the copies of tile i+1 are in flight while tile i is built
     auto issue = [&](int tile, int buf) {
       const int a = tile / TB, b0 = (tile - a * TB) << 7;
       const int ia = a / p.wA, ja = a - ia * p.wA;
-      float* dst = xs + (size_t)buf * 9 * span;
-      for (int idx = ptid; idx < 9 * span; idx += kL1Producers) {
-        const int d = idx / span, j = idx - d * span;
+      const int kr0 = b0 / p.wB - 1;                          // B row of block row 0
+      float* dst = xs + (size_t)buf * 9 * DS;
+      for (int idx = ptid; idx < 9 * DS; idx += kL1Producers) {
+        const int d = idx / DS, rem = idx - d * DS;
+        const int rr = rem / PW, cc = rem - rr * PW;
         const int i2 = ia + d / 3 - 1, j2 = ja + d % 3 - 1;
-        const int b = b0 - p.wB - 1 + j;
-        const bool ok = i2 >= 0 && i2 < p.hA && j2 >= 0 && j2 < p.wA && b >= 0 && b < p.nB;
-        const float* src = ok ? p.x + (size_t)(i2 * p.wA + j2) * p.nB + b : p.x;
+        const int k = kr0 + rr, l = cc - 1;
+        const bool ok = i2 >= 0 && i2 < p.hA && j2 >= 0 && j2 < p.wA && k >= 0 && k < p.hB && l >= 0 && l < p.wB;
+        const float* src = ok ? p.x + (size_t)(i2 * p.wA + j2) * p.nB + k * p.wB + l : p.x;
         const unsigned sz = ok ? 4u : 0u;
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst + idx)), "l"(src), "r"(sz) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     int it = 0, buf = 0;
-    if ((int)blockIdx.x < tiles) issue(blockIdx.x, 0);
+    const bool dbuf = p.l1_bufs == 2;
+    if (dbuf && (int)blockIdx.x < tiles) issue(blockIdx.x, 0);
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       const int next = tile + gridDim.x;
-      if (next < tiles) {
+      if (!dbuf) {
+        issue(tile, 0);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      } else if (next < tiles) {
         issue(next, buf ^ 1);
         asm volatile("cp.async.wait_group 1;" ::: "memory");
       } else {
@@ -211,24 +226,23 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
       const int a = tile / TB, b0 = (tile - a * TB) << 7;
       const int b = b0 + r;
       const bool rv = b < p.nB;
-      const int k = rv ? b / p.wB : 0, l = rv ? b - k * p.wB : 0;
-      // validity of the B-side taps: bits 0..2 rows (k-1, k, k+1), bits 3..5 columns (l-1, l, l+1)
-      const unsigned m = rv ? ((k > 0 ? 1u : 0u) | 2u | (k + 1 < p.hB ? 4u : 0u) | (l > 0 ? 8u : 0u) | 16u | (l + 1 < p.wB ? 32u : 0u)) : 0u;
-      const float* xr = xs + (size_t)buf * 9 * span + r;
+      const int k = rv ? b / p.wB : b0 / p.wB, l = rv ? b - k * p.wB : 0;
+      const float sxr = rv ? sx : 0.f;                         // rows past the end of the B grid produce zeros
+      // shared address of block element (row k - 1, column l - 1) of A-neighbour 0: tap (d, tk, tl) is at
+      // + d * DS + tk * PW + tl floats
+      const uint32_t base = smem_u32(xs + (size_t)buf * 9 * DS) + (uint32_t)(((k - (b0 / p.wB - 1) - 1) * PW + l) * 4);
+      const uint32_t otk1 = (uint32_t)(PW * 4), otk2 = (uint32_t)(2 * PW * 4), ods = (uint32_t)(DS * 4);
       auto chunk = [&](auto ATOM, auto CH, uint8_t* st) {
         constexpr int atom = decltype(ATOM)::value, c = decltype(CH)::value;
         float val[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          constexpr int dummy = 0;
           const int t = (atom * 8 + c) * 8 + i;                  // compile-time
           float f = 0.f;
           if (t < 81) {
             const int d = t / 9, tk = (t / 3) % 3, tl = t % 3;
-            const unsigned need = (1u << tk) | (8u << tl);
-            f = ((m & need) == need) ? xr[d * span + tk * p.wB + tl] * sx : 0.f;     // A-invalid segments hold zeros
+            f = lds_f32(base + (uint32_t)d * ods + (tk == 0 ? 0u : (tk == 1 ? otk1 : otk2)) + (uint32_t)(tl * 4)) * sxr;
           }
-          (void)dummy;
           val[i] = f;
         }
         uint4 hi, lo;
@@ -265,7 +279,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
       else if (qt == 2) build(std::integral_constant<int, 2>{});
       else build(std::integral_constant<int, 3>{});
       asm volatile("bar.sync 1, 512;" ::: "memory");          // all reads of this buffer done before it is refilled
-      buf ^= 1;
+      if (dbuf) buf ^= 1;
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
@@ -279,11 +293,18 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
       const int slot = tl & 1;
       mbar_wait(&tfull_bar[slot], (uint32_t)(tl >> 1) & 1u);
       tc_fence_after();
-      float acc[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 32), acc);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 96);
+      float acc[32], t1[32];
+      tmem_ld32(taddr, acc);                       // lo*hi
+      tmem_ld32(taddr + 32, t1);                   // hi*lo
+#pragma unroll
+      for (int c = 0; c < 32; ++c) acc[c] += t1[c];
+      tmem_ld32(taddr + 64, t1);                   // hi*hi
+#pragma unroll
+      for (int c = 0; c < 32; ++c) acc[c] += t1[c];
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[slot]);     // accumulator is in registers: the slot can be refilled
+      if (lane == 0) mbar_arrive(&tempty_bar[slot]);     // accumulators are in registers: the slot can be refilled
       const int a = tile / TB, b = ((tile - a * TB) << 7) + row;
       if (b < p.nB) {
         const long long v = (long long)a * p.nB + b;
@@ -293,7 +314,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
           float hval[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) hval[c] = fmaxf(fmaf(acc[g * 8 + c], inv, __ldg(p.b1p + g * 8 + c)), 0.f) * sh;
-          split8(hval, o[(g >> 1) * 4 + (g & 1)], o[(g >> 1) * 4 + 2 + (g & 1)]);   // [net][hi0 hi1 lo0 lo1]
+          split8_bounded(hval, o[(g >> 1) * 4 + (g & 1)], o[(g >> 1) * 4 + 2 + (g & 1)]);   // [net][hi0 hi1 lo0 lo1]
         }
         uint4* dst = reinterpret_cast<uint4*>(p.hidden + v * 64);
 #pragma unroll
@@ -305,7 +326,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 64);
+    tmem_dealloc(tmem_base, 256);
   }
 }
 
@@ -346,7 +367,7 @@ __global__ void __launch_bounds__(512, 1) nc_l2_umma_kernel(const __grid_constan
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(&tmem_base_smem, 64);
+  if (warp == 2) tmem_alloc(&tmem_base_smem, 256);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -368,12 +389,15 @@ __global__ void __launch_bounds__(512, 1) nc_l2_umma_kernel(const __grid_constan
           const uint64_t w = make_sw128_desc(smem_u32(wsm) + (uint32_t)(t * WATOM));
 #pragma unroll
           for (int net = 0; net < 2; ++net) {
-            const uint32_t d_tmem = tmem_base + (uint32_t)(slot * 32 + net * 16);
+            // six independent accumulator chains per tile (net x product), 16 columns each, summed by the epilogue:
+            // a single chain of 27 dependent N = 16 MMAs is bound by the MMA latency, not by the tensor pipe
+            const uint32_t d_tmem = tmem_base + (uint32_t)(slot * 96 + net * 48);
             const uint64_t a_hi = a + 2 * (net * 2), a_lo = a + 2 * (net * 2 + 1);      // K16 slices of the line
             const uint64_t w_hi = w + 2 * (net * 2), w_lo = w + 2 * (net * 2 + 1);
-            umma_f16(d_tmem, a_lo, w_hi, IDESC, t > 0 ? 1u : 0u);
-            umma_f16(d_tmem, a_hi, w_lo, IDESC, 1u);
-            umma_f16(d_tmem, a_hi, w_hi, IDESC, 1u);
+            const uint32_t acc = t > 0 ? 1u : 0u;
+            umma_f16(d_tmem, a_lo, w_hi, IDESC, acc);
+            umma_f16(d_tmem + 16, a_hi, w_lo, IDESC, acc);
+            umma_f16(d_tmem + 32, a_hi, w_hi, IDESC, acc);
           }
           umma_commit(&empty_bar[s]);
         }
@@ -437,8 +461,19 @@ __global__ void __launch_bounds__(512, 1) nc_l2_umma_kernel(const __grid_constan
       const int slot = tl & 1;
       mbar_wait(&tfull_bar[slot], (uint32_t)(tl >> 1) & 1u);
       tc_fence_after();
-      float acc[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 32), acc);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 96);
+      float acc[2][16];
+#pragma unroll
+      for (int net = 0; net < 2; ++net) {
+        float t1[16];
+        tmem_ld16(taddr + net * 48, acc[net]);               // lo*hi
+        tmem_ld16(taddr + net * 48 + 16, t1);                // hi*lo
+#pragma unroll
+        for (int d = 0; d < 16; ++d) acc[net][d] += t1[d];
+        tmem_ld16(taddr + net * 48 + 32, t1);                // hi*hi
+#pragma unroll
+        for (int d = 0; d < 16; ++d) acc[net][d] += t1[d];
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[slot]);
@@ -447,7 +482,7 @@ __global__ void __launch_bounds__(512, 1) nc_l2_umma_kernel(const __grid_constan
 #pragma unroll
         for (int net = 0; net < 2; ++net)
 #pragma unroll
-          for (int d = 0; d < 9; ++d) p.partial[(size_t)(net * 9 + d) * p.V + v] = acc[net * 16 + d] * inv;
+          for (int d = 0; d < 9; ++d) p.partial[(size_t)(net * 9 + d) * p.V + v] = acc[net][d] * inv;
       }
     }
   }
@@ -455,7 +490,7 @@ __global__ void __launch_bounds__(512, 1) nc_l2_umma_kernel(const __grid_constan
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 64);
+    tmem_dealloc(tmem_base, 256);
   }
 }
 
@@ -481,12 +516,14 @@ int launch_absmax(const float* x, size_t n, unsigned int* out, cudaStream_t st) 
 // ------------------------------------------------------------------------------------------------
 // combine: out[a][b] = sum_net relu(b2 + sum_(ta,tb) P[net][ta*3+tb][a + (ta-1, tb-1)][b]), fused with the
 // row / column maxima of the MutualMatching that follows (rowmax[a] = max_b, colmax[b] = max_a).
-// Block = 8 A cells; the 9 neighbour offsets are block-uniform.
+// Block = kCombineRows A cells; the 9 neighbour offsets are block-uniform.
 // ------------------------------------------------------------------------------------------------
+constexpr int kCombineRows = 2;      // A cells per block: nA / 2 blocks keep every SM busy with several blocks
+
 __global__ void __launch_bounds__(256) nc_combine_kernel(const float* __restrict__ P, int hA, int wA, int nB, float b2,
                                                         float* __restrict__ out, float* __restrict__ rowmax,
                                                         unsigned int* __restrict__ colmax) {
-  constexpr int R = 8;
+  constexpr int R = kCombineRows;
   __shared__ float red[8][R];
   const int nA = hA * wA;
   const size_t V = (size_t)nA * nB;
@@ -496,7 +533,7 @@ __global__ void __launch_bounds__(256) nc_combine_kernel(const float* __restrict
   for (int r = 0; r < R; ++r) rm[r] = -INFINITY;
   for (int col = threadIdx.x; col < nB; col += 256) {
     float cm = -INFINITY;
-#pragma unroll 2
+#pragma unroll
     for (int r = 0; r < R; ++r) {
       const int a = r0 + r;
       if (a >= nA) continue;
@@ -622,8 +659,11 @@ int launch_neigh_consensus_umma(const float* x, int hA, int wA, int hB, int wB, 
   {
     p.wimg = W.img1;
     p.tiles = (int)t1;
-    const int smem = kL1Stages * 2 * kNcAtom + 2 * 2 * 32 * 128 + 2 * 9 * (128 + 2 * wB + 2) * 4 + 1024;
-    P2P_REQUIRE(smem <= 200 * 1024, "NeighConsensus layer 1: B grid too wide for the shared-memory staging (wB <= ~700)");
+    const int seg = 9 * nc_l1_rows(wB) * (wB + 2) * 4;
+    const int fixed = kL1Stages * 2 * kNcAtom + 2 * 2 * 32 * 128 + 1024;
+    p.l1_bufs = fixed + 2 * seg <= 220 * 1024 ? 2 : 1;
+    const int smem = fixed + p.l1_bufs * seg;
+    P2P_REQUIRE(smem <= 220 * 1024, "NeighConsensus layer 1: B grid too wide for the shared-memory staging (wB <= ~500)");
     auto k = nc_l1_umma_kernel;
     P2P_ENSURE_SMEM(k, smem);
     const int grid = p.tiles < num_sms ? p.tiles : num_sms;
@@ -640,7 +680,7 @@ int launch_neigh_consensus_umma(const float* x, int hA, int wA, int hB, int wB, 
     P2P_LAUNCH_OK();
   }
   if (colmax != nullptr) P2P_CUDA_OK(cudaMemsetAsync(colmax, 0, sizeof(unsigned int) * p.nB, st));
-  nc_combine_kernel<<<cdiv(p.nA, 8), 256, 0, st>>>(partial, hA, wA, p.nB, b2, out, rowmax, colmax);
+  nc_combine_kernel<<<cdiv(p.nA, kCombineRows), 256, 0, st>>>(partial, hA, wA, p.nB, b2, out, rowmax, colmax);
   P2P_LAUNCH_OK();
   return 0;
 }

@@ -437,8 +437,12 @@ def _e2e(net, sd, pair_idx, H, W, ptmax, panc, np_seed=7, shifted=False, feats=N
             np.random.seed(np_seed)
             g = net.match_from_feats(f1, f2, 2, 0.0, True, ptmax, return_all=True)
             torch.cuda.synchronize()
-            assert torch.equal(g[4][0], cm[0]) and torch.equal(g[0][0].reshape(-1, 4), fine[0].reshape(-1, 4)) \
-                and torch.equal(g[1][0].reshape(-1), finep[0].reshape(-1)), 'fused entry differs from the staged path'
+            assert torch.equal(g[4][0], cm[0]), 'fused entry: anchors differ from the staged path'
+            dfine = (g[0][0].reshape(-1, 4) - fine[0].reshape(-1, 4)).abs()
+            assert torch.equal(g[0][0].reshape(-1, 4), fine[0].reshape(-1, 4)), \
+                ('fused entry differs from the staged path', dfine.max().item(), int((dfine > 0).any(1).sum()),
+                 (g[3][0].reshape(-1) - midp[0].reshape(-1)).abs().max().item(), (g[2][0].reshape(-1, 4) - mid[0].reshape(-1, 4)).abs().max().item())
+            assert torch.equal(g[1][0].reshape(-1), finep[0].reshape(-1))
     o = (o_fine, o_finep, o_mid, o_midp, o_cm)
     g = (fine, finep, mid, midp, cm)
     return o, g, coarse
