@@ -46,7 +46,7 @@ def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=100)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--height', type=int, default=H_DEF)
     ap.add_argument('--width', type=int, default=W_DEF)
@@ -358,19 +358,23 @@ def run_ours(args):
         f1, f2 = feats[slots[i]]
         return (i, net.submit_coarse(f1, f2, 2, True))
 
-    def hot_finish(tk, out_slot=None, keep=None):
+    step_events = [torch.cuda.Event(enable_timing=True) for _ in range(max(K, 1))]   # created before the timed region
+
+    def hot_finish(tk, out_slot=None, keep=None, stamp=False):
         i, ticket = tk
         np.random.seed(mine[i] % (2 ** 31))               # the reference's global numpy RNG, seeded per pair
         fine, fine_p, cm = net.finish_match(ticket, 0.0, args.ptmax)
         if out_slot is not None:
             results[out_slot, :, :4] = fine[0]
             results[out_slot, :, 4] = fine_p[0]
+            if stamp:
+                step_events[out_slot].record()
         if keep is not None:
             keep.append(cm[0])
 
     depth = max(1, args.depth)
 
-    def hot_loop(first, steps, record, keep=None):
+    def hot_loop(first, steps, record, keep=None, stamp=False):
         # `depth` pairs in flight: the coarse stages of the next pairs are already queued when the host waits for the
         # mutual-match count of the oldest one, so the GPU always has more than a coarse stage of work ahead of the host
         from collections import deque
@@ -379,10 +383,10 @@ def run_ours(args):
             q.append((hot_submit(first + j), j if record else None))
             if len(q) >= depth:
                 tk, slot = q.popleft()
-                hot_finish(tk, slot, keep)
+                hot_finish(tk, slot, keep, stamp)
         while q:
             tk, slot = q.popleft()
-            hot_finish(tk, slot, keep)
+            hot_finish(tk, slot, keep, stamp)
 
     def e2e_submit(i):
         a, b = pinned[slots[i]]
@@ -435,19 +439,25 @@ def run_ours(args):
         # ---- hot path, features resident in HBM -------------------------------------------------
         hot_loop(0, Wm, False)
         sharder.gather_results(results)                  # warm-up of the collective (NCCL sets up channels lazily)
-        net.set_option('profile', 1)
-        net._handle.profile_read()
-        net._handle.get_option('band_calls_rows_total')  # reset the running band totals
         l0 = net._handle.launch_count()
         sampler = ClockSampler(local) if rank == 0 else None
         anchors_seen = []
 
         def hot_region(steps):
-            hot_loop(Wm, min(steps, n_mine), True, anchors_seen if rank == 0 else None)
+            hot_loop(Wm, min(steps, n_mine), True, anchors_seen if rank == 0 else None, stamp=True)
             sharder.gather_results(results)              # NCCL gather of the matches (inside the timed region)
         ms_hot = timed(hot_region, K, sampler)
         launches = net._handle.launch_count() - l0
         clocks = sampler.finish() if sampler else None
+        nst = min(K, n_mine)
+        step_ms = sorted(step_events[j].elapsed_time(step_events[j + 1]) for j in range(nst - 1))
+        # ---- per-kernel breakdown: a SEPARATE, untimed-for-the-headline pass with an event pair around every launch
+        # group (the event bookkeeping of the profiler stays out of the headline number) ----
+        Kp = max(min(K, n_mine, 20), 1)
+        net.set_option('profile', 1)
+        net._handle.profile_read()
+        net._handle.get_option('band_calls_rows_total')  # reset the running band totals
+        ms_prof = timed(lambda steps: hot_loop(Wm, steps, False), Kp)
         prof = net._handle.profile_read()
         net.set_option('profile', 0)
         band_rows_total = net._handle.get_option('band_rows_total')
@@ -554,10 +564,12 @@ def run_ours(args):
                         'frac_vs_burst': ach / peaks['tflops_burst'], 'frac_vs_sustained': ach / peaks['tflops_sustained'],
                         'tensor_passes': kern[dom]['tensor_passes'],
                         'issued_frac': kern[dom]['issued_tflops'] / peak,
-                        'share_of_step': kern[dom]['ms_per_launch'] * kern[dom]['launches'] / ms_hot,
-                        'all_umma_gemm_share_of_step': gemm_ms / ms_hot,
-                        'kernel_event_sum_ms_per_step': ksum / max(K, 1),
-                        'gap_ms_per_step': (ms_hot - ksum) / max(K, 1) if world == 1 else None,
+                        'share_of_step': kern[dom]['ms_per_launch'] * kern[dom]['launches'] / Kp / (ms_hot / K),
+                        'all_umma_gemm_share_of_step': gemm_ms / Kp / (ms_hot / K),
+                        'kernel_event_sum_ms_per_step': ksum / Kp,
+                        'gap_ms_per_step': ms_hot / K - ksum / Kp if world == 1 else None,
+                        'breakdown_pass': f'{Kp} steps with an event pair around every launch group, run after the timed '
+                                          f'region ({ms_prof / Kp:.3f} ms/step with the event bookkeeping)',
                         'band_rows_fraction': band_rows_total / mid_rows_total if (banded and mid_rows_total) else None}
         cpu = None
         if world == 1 and not args.no_cpu_baseline and not strong:
@@ -594,6 +606,8 @@ def run_ours(args):
                        'hot_path': 'correlation .. fine matches, features resident in HBM',
                        'sequence': 'train_patch2pix.py:97-118 under eval/no_grad', 'pairs_per_step': world,
                        'total_pairs': pairs, 'distinct_proposals_first_pairs': distinct,
+                       'step_ms_quantiles': ({'p10': step_ms[len(step_ms) // 10], 'p50': step_ms[len(step_ms) // 2],
+                                              'p90': step_ms[(len(step_ms) * 9) // 10], 'max': step_ms[-1]} if step_ms else None),
                        'l2': f'{len(imgs)} distinct pairs cycled per rank; per-step working set (~3 GB of scratch written and '
                              f're-read) >> 126 MB L2',
                        'pipelining': f'{depth} pairs in flight per GPU (the coarse stages of the next pairs are enqueued before the host sync of the oldest)',

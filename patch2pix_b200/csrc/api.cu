@@ -100,6 +100,7 @@ struct p2p_handle_s {
   float *nc_w1p = nullptr, *nc_b1p = nullptr, *nc_w2p = nullptr;
   float nc_b2 = 0.f;
   NcUmmaWeights ncw;            // tensor-core NC operand images
+  int opt_nc_l2_mode = 0;       // NC layer 2 block layout: 0 auto, 1 one haloed block per tile, 2 one block per column tap
   int opt_nc_impl = 1;          // 1: NeighConsensus on the tensor cores (nc_umma.cu); 0: fp32 CUDA-core kernels (shape-capped)
   Regressor reg[2];
   Arena coarse, refine, feat, misc, uniq, pre;
@@ -483,6 +484,7 @@ static int* option_slot(p2p_handle_t h, const char* key) {
   if (!strcmp(key, "fc_impl")) return &h->opt_fc_impl;
   if (!strcmp(key, "gemm_pair")) return &h->opt_gemm_pair;
   if (!strcmp(key, "nc_impl")) return &h->opt_nc_impl;
+  if (!strcmp(key, "nc_l2_mode")) return &h->opt_nc_l2_mode;
   return nullptr;
 }
 
@@ -619,7 +621,7 @@ static int coarse_impl(p2p_handle_t h, const float* feat1, const float* feat2, i
   if (tc) P2P_REQUIRE(c % 64 == 0 && c / 64 <= kMaxKSteps, "tensor-core correlation needs C % 64 == 0");
   P2P_REQUIRE(fmt == 0 || tc, "channels-last fp16 features need the tensor-core correlation (corr_passes 1 or 3)");
   const int n1pad = (int)align_up(n1, 128), n2pad = (int)align_up(n2, 256);
-  size_t need = 4 * V * 4 + nc_umma_scratch_bytes(V) + (size_t)(nA + nB) * 8 + (1 << 16);
+  size_t need = 4 * V * 4 + nc_umma_scratch_bytes(V) + nc_umma_xp_bytes(hA, wA, hB, wB) + (size_t)(nA + nB) * 8 + (1 << 16);
   need += tc ? (size_t)(n1pad + n2pad) * c * 4 : (size_t)(n1 + n2) * c * 4;
   int rc = h->coarse.reserve(need);
   if (rc) return rc;
@@ -629,6 +631,7 @@ static int coarse_impl(p2p_handle_t h, const float* feat1, const float* feat2, i
   float* nc = ncn_out ? ncn_out : (float*)A.take(V * 4);
   float* hidden = (float*)A.take(V * 128);               // fp32 [nA][32][nB] (nc_impl 0) or fp16 hi/lo [V][64] (nc_impl 1)
   float* partial = (float*)A.take(18 * V * 4);
+  uint32_t* xp = (uint32_t*)A.take(nc_umma_xp_bytes(hA, wA, hB, wB));
   float* rowmax = (float*)A.take((size_t)nA * 4);
   unsigned int* colmax = (unsigned int*)A.take((size_t)nB * 4 + 16);
   unsigned int* xmax = colmax != nullptr ? colmax + nB : nullptr;
@@ -664,7 +667,7 @@ static int coarse_impl(p2p_handle_t h, const float* feat1, const float* feat2, i
     ProfScope ps(h, P2P_PROF_CORR, st);
     if ((rc = launch_corr_pool_simt(fa, fb, c, n1, n2, ksize, pooled, delta_code_out, st))) return rc;
   }
-  P2P_REQUIRE(partial != nullptr && xmax != nullptr, "scratch carve failed");
+  P2P_REQUIRE(partial != nullptr && xmax != nullptr && xp != nullptr, "scratch carve failed");
   if (h->opt_nc_impl == 1) {
     {
       ProfScope ps(h, P2P_PROF_MUTUAL, st);
@@ -673,8 +676,8 @@ static int coarse_impl(p2p_handle_t h, const float* feat1, const float* feat2, i
     {
       // layer 1, layer 2 (tensor cores) and the combine pass, which also yields the maxima of the second MutualMatching
       ProfScope ps(h, P2P_PROF_NC, st);
-      if ((rc = launch_neigh_consensus_umma(m1, hA, wA, hB, wB, h->ncw, h->nc_b1p, h->nc_b2, xmax, (__half*)hidden, partial,
-                                            nc, rowmax, colmax, sms(h), st)))
+      if ((rc = launch_neigh_consensus_umma(m1, hA, wA, hB, wB, h->ncw, h->nc_b1p, h->nc_b2, xmax, xp, (__half*)hidden, partial,
+                                            nc, rowmax, colmax, h->opt_nc_l2_mode, sms(h), st)))
         return rc;
     }
     ProfScope ps(h, P2P_PROF_MUTUAL, st);
@@ -740,17 +743,18 @@ int p2p_neigh_consensus(p2p_handle_t h, const float* in, int hA, int wA, int hB,
   P2P_REQUIRE(h->nc_set, "p2p_set_ncn_weights has not been called");
   P2P_REQUIRE(in && out && hA > 0 && wA > 0 && hB > 0 && wB > 0, "bad argument");
   const size_t V = (size_t)hA * wA * hB * wB;
-  int rc = h->misc.reserve(nc_umma_scratch_bytes(V) + 8192);
+  int rc = h->misc.reserve(nc_umma_scratch_bytes(V) + nc_umma_xp_bytes(hA, wA, hB, wB) + 8192);
   if (rc) return rc;
   float* hidden = (float*)h->misc.take(V * 128);
   float* partial = (float*)h->misc.take(18 * V * 4);
+  uint32_t* xp = (uint32_t*)h->misc.take(nc_umma_xp_bytes(hA, wA, hB, wB));
   unsigned int* xmax = (unsigned int*)h->misc.take(16);
-  P2P_REQUIRE(hidden && partial && xmax, "scratch carve failed");
+  P2P_REQUIRE(hidden && partial && xmax && xp, "scratch carve failed");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (h->opt_nc_impl == 1) {
     if ((rc = launch_absmax(in, V, xmax, st))) return rc;
-    return launch_neigh_consensus_umma(in, hA, wA, hB, wB, h->ncw, h->nc_b1p, h->nc_b2, xmax, (__half*)hidden, partial, out,
-                                       nullptr, nullptr, sms(h), st);
+    return launch_neigh_consensus_umma(in, hA, wA, hB, wB, h->ncw, h->nc_b1p, h->nc_b2, xmax, xp, (__half*)hidden, partial, out,
+                                       nullptr, nullptr, h->opt_nc_l2_mode, sms(h), st);
   }
   return launch_neigh_consensus(in, hA, wA, hB, wB, h->nc_w1p, h->nc_b1p, h->nc_w2p, h->nc_b2, hidden, out, st);
 }

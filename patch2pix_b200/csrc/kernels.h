@@ -44,10 +44,11 @@ struct NcUmmaWeights {
 };
 int nc_umma_pack(const float* w1p, const float* b1p, const float* w2p, NcUmmaWeights& W);
 size_t nc_umma_scratch_bytes(size_t V);
+size_t nc_umma_xp_bytes(int hA, int wA, int hB, int wB);
 int launch_absmax(const float* x, size_t n, unsigned int* out, cudaStream_t st);
 int launch_neigh_consensus_umma(const float* x, int hA, int wA, int hB, int wB, const NcUmmaWeights& W, const float* b1p,
-                                float b2, const unsigned int* xmax, __half* hidden, float* partial, float* out,
-                                float* rowmax, unsigned int* colmax, int num_sms, cudaStream_t st);
+                                float b2, const unsigned int* xmax, uint32_t* xp, __half* hidden, float* partial,
+                                float* out, float* rowmax, unsigned int* colmax, int l2_mode, int num_sms, cudaStream_t st);
 
 // ---- preprocess.cu: PIL-exact bicubic resize + ToTensor + Normalize (utils/datasets/preprocess.py:32-60) ----
 struct PreprocessCoefs {

@@ -7,33 +7,39 @@
 // conv(x) + conv(x^T)^T equals two independent nets on the SAME input, the second with tap axes (a,b) <-> (d,e)
 // swapped (api.cu packs both: w1p / w2p [81 taps][32 = 16 ch of net 0 | 16 ch of net 1]).
 //
-// Both layers are skinny GEMMs whose A operand is an im2col matrix that producer warps build directly in shared
-// memory in the 128B-swizzled K-major layout tcgen05.mma consumes; nothing but x, the hidden tensor and the
-// partial maps touches HBM and no FMA-pipe inner loop is left:
+// Both layers are skinny GEMMs on tcgen05; nothing but x, the hidden tensor and the partial maps touches HBM and no
+// FMA-pipe inner loop is left:
 //
-//   layer 1   rows = 128 consecutive 4D cells, K = 81 taps (padded to 128), N = 32 channels (both nets).
+//   pad/split x -> xp: zero-haloed copy of x, every element already scaled and split into an fp16 (hi, lo) pair packed
+//             in one 32-bit word, so layer 1 needs neither bounds logic nor conversions.
+//   layer 1   rows = 128 consecutive B cells of one A cell, K = 81 taps (padded to 128), N = 32 channels (both nets).
+//             Producer warps build the im2col operand in shared memory (ld.shared + prmt + st.shared only) from the
+//             tile's 9 neighbour blocks, which one thread stages with bulk copies (cp.async.bulk).
 //             Epilogue: + bias, ReLU, re-scale, fp16 hi/lo split -> hidden[cell][64 fp16] =
 //             [net0 hi 16 | net0 lo 16 | net1 hi 16 | net1 lo 16] (one 128-byte line per cell).
 //   layer 2   16 -> 1 channels would be an N = 1 GEMM.  Instead, per hidden cell a' and per net, the 9 PARTIAL maps
 //             P_(ta,tb)[a'][b] = sum over the 9 B-taps and 16 channels are one GEMM with K = 9 x 16 = 144, N = 9
-//             (padded to 16); one operand atom per B-tap whose rows are verbatim copies of 128-byte hidden lines.
+//             (padded to 16).  The A operand of a B-tap is the tile's block of hidden lines SHIFTED by the tap offset:
+//             the block (with its zero halo, courtesy of TMA out-of-bounds fill) is loaded ONCE per tile and every tap
+//             only moves the start address of the shared-memory descriptor -- there are no producer warps at all.
 //   combine   out[a][b] = sum_net relu(b2 + sum_(ta,tb) P_(ta,tb)[a + (ta-1, tb-1)][b])  (fixed summation order:
 //             deterministic), fused with the row/column maxima of the MutualMatching that follows.
 //
-// Precision: fp16 hi/lo operand pairs, three MMAs per product (lo*hi + hi*lo + hi*hi, fp32 accumulate in TMEM):
-// products good to ~2^-22, i.e. fp32-grade (chains are 18 / 27 MMAs long, so the accumulator's round-toward-zero
-// stays below 1e-6 relative).  Activations are scaled by powers of two derived ON THE DEVICE from max|x| (and from
-// a weight-norm bound for the hidden tensor), so any input range is safe in fp16.
+// Precision: fp16 hi/lo operand pairs, three products per term (lo*hi + hi*lo + hi*hi, fp32 accumulate in TMEM, each
+// product kind in its own accumulator so the chains are short and independent): products good to ~2^-22, i.e.
+// fp32-grade.  Activations are scaled by powers of two derived ON THE DEVICE from max|x| (and from a weight-norm bound
+// for the hidden tensor), so any input range is safe in fp16.
 //
-// Warp-specialised persistent kernels (MMA issuer, TMEM allocator, 4 epilogue warps = TMEM lane quadrants, producer
-// warps), mbarrier ring of operand stages, two TMEM accumulator slots so that the epilogue of tile i overlaps the MMAs
-// of tile i+1.
+// Warp-specialised persistent kernels (loader thread, MMA issuer, TMEM allocator, 4 epilogue warps = TMEM lane
+// quadrants, producer warps in layer 1), mbarrier rings, two TMEM accumulator slots so that the epilogue of tile i
+// overlaps the MMAs of tile i+1.
 #include <math.h>
 
 #include <type_traits>
 #include <vector>
 
 #include "kernels.h"
+#include "umma_gemm.h"
 #include "umma_ptx.cuh"
 
 namespace p2p {
@@ -45,6 +51,7 @@ struct NcParams {
   long long V;                 // nA * nB cells
   const float* x;              // [V] input (after the first MutualMatching)
   const unsigned int* xmax;    // device: float bits of max |x|
+  uint32_t* xp;                // [(hA+2)(wA+2)][hB+2][WP] zero-haloed (hi | lo << 16) fp16 pairs of x * sx
   __half* hidden;              // [V][64]
   float* partial;              // [2 nets][9][V]
   const __half* wimg;          // weight operand image, laid out exactly as in shared memory
@@ -52,7 +59,12 @@ struct NcParams {
   float wsum1, b1max;          // max_c sum_taps |w1|, max |b1|: bound of the hidden activations
   float inv_sw1, inv_sw2;      // 1 / (power-of-two weight scales)
   int tiles;
+  int WP;                      // padded row pitch of xp (multiple of 4 words)
   int l1_bufs;                 // layer-1 staging buffers: 2 (copies of tile i+1 overlap tile i) or 1 (wide B grids)
+  // layer 2 tiling: tile = R rows x TW columns of one A cell's B grid, enumerated with pitch P lines
+  int TW, R, P, KB, LB;        // KB x LB tiles per A cell
+  int copies;                  // 1: one haloed block per tile (pitch TW + 2); 3: one block per column tap (pitch TW)
+  int ring, unit_bytes;        // ring of block buffers in shared memory
 };
 
 // Power-of-two activation scales: max|x| * sx and (hidden bound) * sh land in [2048, 4096).
@@ -68,20 +80,7 @@ __device__ __forceinline__ void nc_scales(const NcParams& p, float& sx, float& s
   sh = ldexpf(1.f, min(12 - e, 60));
 }
 
-__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
-  __half2 h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float a = fminf(fmaxf(v[2 * i], -65504.f), 65504.f), b = fminf(fmaxf(v[2 * i + 1], -65504.f), 65504.f);
-    h[i] = __floats2half2_rn(a, b);
-    const float2 f = __half22float2(h[i]);
-    l[i] = __floats2half2_rn(a - f.x, b - f.y);
-  }
-  hi = *reinterpret_cast<uint4*>(h);
-  lo = *reinterpret_cast<uint4*>(l);
-}
-
-// operands that are bounded by construction (|x * sx| < 4096): no saturation needed
+// operands that are bounded by construction (|v| < 4096): no saturation needed
 __device__ __forceinline__ void split8_bounded(const float* v, uint4& hi, uint4& lo) {
   __half2 h[4], l[4];
 #pragma unroll
@@ -94,26 +93,57 @@ __device__ __forceinline__ void split8_bounded(const float* v, uint4& hi, uint4&
   lo = *reinterpret_cast<uint4*>(l);
 }
 
-// ------------------------------------------------------------------------------------------------
-// layer 1.  Tile = (A cell a, 128 consecutive B cells).  The 9 A-neighbours' B rows touched by the tile are staged in
-// shared memory with cp.async as a zero-PADDED 2-D block (one extra row above/below, one extra column left/right,
-// zero outside the volume; double-buffered: tile i+1 is in flight while tile i is built), so a tap is a plain
-// `ld.shared [row base + tk*pitch + tl]` with no validity logic.  Sixteen producer warps (four threads per tile row,
-// each a quarter of the 11 tap chunks) scale, split to fp16 hi/lo and store the swizzled operand chunks.
-// The three products of the hi/lo split (lo*hi, hi*lo, hi*hi) accumulate in three SEPARATE TMEM blocks -- three
-// independent MMA chains instead of one 18-deep dependent chain of tiny (N = 32) MMAs -- and are summed by the epilogue.
-// 768 threads (warp 1 MMA, 2 TMEM, 4..7 epilogue, 8..23 producers), 1 CTA per SM, 4 x 32 KB operand stages.
-// ------------------------------------------------------------------------------------------------
-constexpr int kL1Stages = 4;
-constexpr int kL1Threads = 768, kL1Producers = 512;
+// exact n / d for 0 <= n < 2^22 with inv = 1.f / d (the quotient of n + 0.5 is at least 0.5 / d away from an integer)
+__device__ __forceinline__ int fast_div(int n, float inv) { return __float2int_rz(((float)n + 0.5f) * inv); }
 
-__host__ __device__ inline int nc_l1_rows(int wB) { return 127 / wB + 4; }      // B rows a tile can touch, + halo
-
-__device__ __forceinline__ float lds_f32(uint32_t addr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// pad / split: x [nA][hB][wB] fp32 -> xp [(hA+2)(wA+2)][hB+2][WP] words (fp16 hi | fp16 lo << 16) of x * sx, zero halo.
+// One block per padded A cell.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nc_pad_split_kernel(const __grid_constant__ NcParams p) {
+  const int pa = blockIdx.x;
+  const int pi = pa / (p.wA + 2), pj = pa - pi * (p.wA + 2);
+  const bool inside = pi >= 1 && pi <= p.hA && pj >= 1 && pj <= p.wA;
+  float sx, sh;
+  nc_scales(p, sx, sh);
+  const int n = (p.hB + 2) * p.WP;
+  uint32_t* dst = p.xp + (size_t)pa * n;
+  const float* src = inside ? p.x + (size_t)((pi - 1) * p.wA + (pj - 1)) * p.nB : p.x;
+  const float inv = 1.f / (float)p.WP;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int kp = fast_div(i, inv), lp = i - kp * p.WP;
+    uint32_t w = 0;
+    if (inside && kp >= 1 && kp <= p.hB && lp >= 1 && lp <= p.wB) {
+      const float v = src[(kp - 1) * p.wB + (lp - 1)] * sx;
+      const __half h = __float2half_rn(v), l = __float2half_rn(v - __half2float(h));
+      w = (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16);
+    }
+    dst[i] = w;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// layer 1.  Tile = (A cell a, 128 consecutive B cells).  The B rows of the 9 A-neighbours the tile touches are staged
+// from xp with 9 bulk copies by one thread (double-buffered: tile i+1 is in flight while tile i is built), so a tap is
+// a plain `ld.shared [row base + tk*pitch + tl]` with no validity logic.  Sixteen producer warps (four threads per
+// tile row, each a quarter of the 11 tap chunks) pack the (hi, lo) words into the swizzled operand chunks.
+// The three products of the hi/lo split (lo*hi, hi*lo, hi*hi) accumulate in three SEPARATE TMEM blocks -- three
+// independent MMA chains instead of one 18-deep dependent chain of tiny (N = 32) MMAs -- and are summed by the epilogue.
+// 768 threads (warp 1 MMA, 2 TMEM, 3 loader, 4..7 epilogue, 8..23 producers), 1 CTA per SM, 4 x 32 KB operand stages.
+// ------------------------------------------------------------------------------------------------
+constexpr int kL1Stages = 4;
+constexpr int kL1Threads = 768, kL1ProducerWarps = 16;
+
+__host__ __device__ inline int nc_l1_rows(int wB) { return 127 / wB + 4; }      // padded B rows a tile can touch
 
 __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_constant__ NcParams p) {
   constexpr int STAGE_BYTES = 2 * kNcAtom;         // A_hi + A_lo of one atom
@@ -122,29 +152,36 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* wsm = smem + kL1Stages * STAGE_BYTES;                          // [hi|lo][atom] weight images, 16 KB
-  float* xs = reinterpret_cast<float*>(wsm + 4 * WATOM);                  // [2 buffers][9][rows][pitch]
+  uint8_t* xs = wsm + 4 * WATOM;                                          // [bufs][9][rows][pitch] words
   __shared__ __align__(8) uint64_t full_bar[kL1Stages];
   __shared__ __align__(8) uint64_t empty_bar[kL1Stages];
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ __align__(8) uint64_t xfull_bar[2];
+  __shared__ __align__(8) uint64_t xempty_bar[2];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles = p.tiles;
   const int TB = (p.nB + 127) >> 7;
-  const int PW = p.wB + 2, NR = nc_l1_rows(p.wB), DS = NR * PW;           // pitch, rows, floats per A-neighbour block
+  const int NR = nc_l1_rows(p.wB);
+  const uint32_t NRB = (uint32_t)(NR * p.WP * 4);                         // bytes of one neighbour block
+  const float inv_tb = 1.f / (float)TB, inv_wb = 1.f / (float)p.wB;
+  const int nbuf = p.l1_bufs;
 
   for (int i = threadIdx.x; i < kL1Stages * STAGE_BYTES / 16; i += kL1Threads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   for (int i = threadIdx.x; i < 4 * WATOM / 16; i += kL1Threads)
     reinterpret_cast<uint4*>(wsm)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kL1Stages; ++i) {
-      mbar_init(&full_bar[i], kL1Producers);
+      mbar_init(&full_bar[i], kL1ProducerWarps);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);
+      mbar_init(&xfull_bar[i], 1);
+      mbar_init(&xempty_bar[i], kL1ProducerWarps);
     }
     fence_barrier_init();
   }
@@ -184,93 +221,87 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
         umma_commit(&tfull_bar[slot]);
       }
     }
+  } else if (warp == 3) {
+    // ===================== loader: 9 bulk copies per tile =====================
+    if (lane == 0) {
+      int tl = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
+        const int buf = tl % nbuf;
+        mbar_wait(&xempty_bar[buf], ((uint32_t)(tl / nbuf) & 1u) ^ 1u);
+        const int a = fast_div(tile, inv_tb), b0 = (tile - a * TB) << 7;
+        const int ia = a / p.wA, ja = a - ia * p.wA;
+        const int k0 = fast_div(b0, inv_wb);                          // padded row k0 = unpadded row k0 - 1
+        mbar_expect_tx(&xfull_bar[buf], 9u * NRB);
+        uint8_t* dst = xs + (size_t)buf * 9 * NRB;
+#pragma unroll
+        for (int d = 0; d < 9; ++d) {
+          const int pa = (ia + d / 3) * (p.wA + 2) + ja + d % 3;
+          bulk_load(&xfull_bar[buf], dst + (size_t)d * NRB, p.xp + ((size_t)pa * (p.hB + 2) + k0) * p.WP, NRB);
+        }
+      }
+    }
   } else if (warp >= 8) {
     // ===================== producers: 512 threads = 128 tile rows x 4 chunk quarters =====================
     const int ptid = threadIdx.x - 256;
     const int r = ptid & 127;
     const int qt = ptid >> 7;          // warp-uniform: chunks qt and qt + 4 of atom 0, chunk qt of atom 1 (qt < 3)
-    float sx, sh;
-    nc_scales(p, sx, sh);
-    auto issue = [&](int tile, int buf) {
-      const int a = tile / TB, b0 = (tile - a * TB) << 7;
-      const int ia = a / p.wA, ja = a - ia * p.wA;
-      const int kr0 = b0 / p.wB - 1;                          // B row of block row 0
-      float* dst = xs + (size_t)buf * 9 * DS;
-      for (int idx = ptid; idx < 9 * DS; idx += kL1Producers) {
-        const int d = idx / DS, rem = idx - d * DS;
-        const int rr = rem / PW, cc = rem - rr * PW;
-        const int i2 = ia + d / 3 - 1, j2 = ja + d % 3 - 1;
-        const int k = kr0 + rr, l = cc - 1;
-        const bool ok = i2 >= 0 && i2 < p.hA && j2 >= 0 && j2 < p.wA && k >= 0 && k < p.hB && l >= 0 && l < p.wB;
-        const float* src = ok ? p.x + (size_t)(i2 * p.wA + j2) * p.nB + k * p.wB + l : p.x;
-        const unsigned sz = ok ? 4u : 0u;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst + idx)), "l"(src), "r"(sz) : "memory");
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    int it = 0, buf = 0;
-    const bool dbuf = p.l1_bufs == 2;
-    if (dbuf && (int)blockIdx.x < tiles) issue(blockIdx.x, 0);
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      const int next = tile + gridDim.x;
-      if (!dbuf) {
-        issue(tile, 0);
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-      } else if (next < tiles) {
-        issue(next, buf ^ 1);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-      } else {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-      }
-      asm volatile("bar.sync 1, 512;" ::: "memory");          // every producer's copies of this tile have landed
-      const int a = tile / TB, b0 = (tile - a * TB) << 7;
+    const uint32_t sw = (uint32_t)(r & 7);
+    const uint32_t otk = (uint32_t)(p.WP * 4);
+    int it = 0, tl = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
+      const int buf = tl % nbuf;
+      const int a = fast_div(tile, inv_tb), b0 = (tile - a * TB) << 7;
       const int b = b0 + r;
-      const bool rv = b < p.nB;
-      const int k = rv ? b / p.wB : b0 / p.wB, l = rv ? b - k * p.wB : 0;
-      const float sxr = rv ? sx : 0.f;                         // rows past the end of the B grid produce zeros
-      // shared address of block element (row k - 1, column l - 1) of A-neighbour 0: tap (d, tk, tl) is at
-      // + d * DS + tk * PW + tl floats
-      const uint32_t base = smem_u32(xs + (size_t)buf * 9 * DS) + (uint32_t)(((k - (b0 / p.wB - 1) - 1) * PW + l) * 4);
-      const uint32_t otk1 = (uint32_t)(PW * 4), otk2 = (uint32_t)(2 * PW * 4), ods = (uint32_t)(DS * 4);
-      auto chunk = [&](auto ATOM, auto CH, uint8_t* st) {
+      const bool rv = b < p.nB;                                // rows past the end of the B grid are not built: their
+      const int k = fast_div(b, inv_wb), l = b - k * p.wB;     // operand rows keep stale data and the epilogue skips them
+      const int k0 = fast_div(b0, inv_wb);
+      // shared address of the (tk, tl) = (0, 0) tap of A-neighbour 0: tap (d, tk, tl) is at + d*NRB + tk*otk + tl*4
+      const uint32_t base = smem_u32(xs) + (uint32_t)buf * 9u * NRB + (uint32_t)(((k - k0) * p.WP + l) * 4);
+      mbar_wait(&xfull_bar[buf], (uint32_t)(tl / nbuf) & 1u);
+      auto chunk = [&](auto ATOM, auto CH, uint32_t st) {
         constexpr int atom = decltype(ATOM)::value, c = decltype(CH)::value;
-        float val[8];
+        uint32_t w[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int t = (atom * 8 + c) * 8 + i;                  // compile-time
-          float f = 0.f;
+          constexpr int t0 = (atom * 8 + c) * 8;
+          const int t = t0 + i;                                  // compile-time after unrolling
+          w[i] = 0u;
           if (t < 81) {
-            const int d = t / 9, tk = (t / 3) % 3, tl = t % 3;
-            f = lds_f32(base + (uint32_t)d * ods + (tk == 0 ? 0u : (tk == 1 ? otk1 : otk2)) + (uint32_t)(tl * 4)) * sxr;
+            const int d = t / 9, tk = (t / 3) % 3, tl2 = t % 3;
+            w[i] = lds_u32(base + (uint32_t)d * NRB + (uint32_t)tk * otk + (uint32_t)(tl2 * 4));
           }
-          val[i] = f;
         }
-        uint4 hi, lo;
-        split8_bounded(val, hi, lo);
-        *reinterpret_cast<uint4*>(st + ((c ^ (r & 7)) << 4)) = hi;
-        *reinterpret_cast<uint4*>(st + kNcAtom + ((c ^ (r & 7)) << 4)) = lo;
+        const uint32_t o = st + ((((uint32_t)c) ^ sw) << 4);
+        sts_v4(o, __byte_perm(w[0], w[1], 0x5410), __byte_perm(w[2], w[3], 0x5410), __byte_perm(w[4], w[5], 0x5410),
+               __byte_perm(w[6], w[7], 0x5410));
+        sts_v4(o + kNcAtom, __byte_perm(w[0], w[1], 0x7632), __byte_perm(w[2], w[3], 0x7632),
+               __byte_perm(w[4], w[5], 0x7632), __byte_perm(w[6], w[7], 0x7632));
       };
       auto build = [&](auto QT) {
         constexpr int Q = decltype(QT)::value;
         {   // atom 0: chunks Q and Q + 4
           const int s = it % kL1Stages;
           mbar_wait(&empty_bar[s], ((uint32_t)(it / kL1Stages) & 1u) ^ 1u);
-          uint8_t* st = smem + (size_t)s * STAGE_BYTES + r * 128;
-          chunk(std::integral_constant<int, 0>{}, std::integral_constant<int, Q>{}, st);
-          chunk(std::integral_constant<int, 0>{}, std::integral_constant<int, Q + 4>{}, st);
+          const uint32_t st = smem_u32(smem) + (uint32_t)(s * STAGE_BYTES + r * 128);
+          if (rv) {
+            chunk(std::integral_constant<int, 0>{}, std::integral_constant<int, Q>{}, st);
+            chunk(std::integral_constant<int, 0>{}, std::integral_constant<int, Q + 4>{}, st);
+          }
           fence_proxy_async();
-          mbar_arrive(&full_bar[s]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_bar[s]);
           ++it;
         }
         {   // atom 1: chunk Q (taps 64 + 8Q ..; Q = 3 has nothing to write, chunks 3..7 stay zero)
           const int s = it % kL1Stages;
           mbar_wait(&empty_bar[s], ((uint32_t)(it / kL1Stages) & 1u) ^ 1u);
           if (Q < 3) {
-            uint8_t* st = smem + (size_t)s * STAGE_BYTES + r * 128;
-            chunk(std::integral_constant<int, 1>{}, std::integral_constant<int, (Q < 3 ? Q : 0)>{}, st);
+            const uint32_t st = smem_u32(smem) + (uint32_t)(s * STAGE_BYTES + r * 128);
+            if (rv) chunk(std::integral_constant<int, 1>{}, std::integral_constant<int, (Q < 3 ? Q : 0)>{}, st);
             fence_proxy_async();
           }
-          mbar_arrive(&full_bar[s]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_bar[s]);
           ++it;
         }
       };
@@ -278,8 +309,8 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
       else if (qt == 1) build(std::integral_constant<int, 1>{});
       else if (qt == 2) build(std::integral_constant<int, 2>{});
       else build(std::integral_constant<int, 3>{});
-      asm volatile("bar.sync 1, 512;" ::: "memory");          // all reads of this buffer done before it is refilled
-      if (dbuf) buf ^= 1;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&xempty_bar[buf]);            // this warp's reads of the staging buffer are done
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
@@ -305,7 +336,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[slot]);     // accumulators are in registers: the slot can be refilled
-      const int a = tile / TB, b = ((tile - a * TB) << 7) + row;
+      const int a = fast_div(tile, inv_tb), b = ((tile - a * TB) << 7) + row;
       if (b < p.nB) {
         const long long v = (long long)a * p.nB + b;
         uint4 o[8];
@@ -331,34 +362,49 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
 }
 
 // ------------------------------------------------------------------------------------------------
-// layer 2.  Tile = 128 consecutive 4D cells, both nets.  One operand atom per B-TAP: the atom row of a cell is the
-// complete 128-byte hidden line of its tap neighbour, K = [net][hi|lo][16 ch] -- so the producers are pure line copies
-// (8 lanes per line: fully coalesced loads, conflict-free swizzled stores) and the (net, hi|lo) factor of an MMA is
-// selected by the K16 slice of the descriptors: per tap and net  lo*hi + hi*lo + hi*hi  = 3 MMAs (M128 N16 K16).
-// 512 threads (warp 1 MMA, 2 TMEM, 4..7 epilogue, 8..15 producers); ring of 8 x 16 KB stages.
+// layer 2.  Tile = R rows x TW columns of the B grid of one hidden cell a', both nets, enumerated as MMA rows
+// m = kk * P + ll (pitch P lines).  A tensor-map load brings the tile's block of 128-byte hidden lines -- rows
+// k0-1 .. k0+R, zero-filled outside the grid -- into shared memory in the 128B-swizzled layout tcgen05 reads, and the
+// A operand of B-tap (tk, tl) is simply that block starting (tk * P + tl) lines further on:
+//   copies = 1   the block carries its column halo (box TW + 2 wide, P = TW + 2): one load per tile; the two MMA rows
+//                per tile row that fall on the halo are junk and skipped by the epilogue.  Tap starts are 128-byte
+//                granular, so the descriptors carry the swizzle phase ("base offset" = address bits 7..9).
+//   copies = 3   one block per column tap tl, loaded with the column origin shifted by tl - 1 (P = TW): no junk rows
+//                and, when TW % 8 == 0, every tap start is 1024-byte aligned; costs 3 loads per tile.
+// Per tap and net: a_hi x [w_hi | w_lo] (one N = 32 MMA gives hi*hi and hi*lo) and a_lo x w_hi (N = 16): four
+// independent accumulator chains per tile, summed by the epilogue.
+// 256 threads (warp 1 MMA, 2 TMEM, 3 loader, 4..7 epilogue); ring of block buffers.
 // ------------------------------------------------------------------------------------------------
-constexpr int kL2Stages = 8;
+constexpr int kL2MaxRing = 8;
+constexpr int kL2WTap = 32 * 128;     // weight image per B-tap: rows 0..15 w_hi (9 used), 16..31 w_lo; K16 slice = net
 
-__global__ void __launch_bounds__(512, 1) nc_l2_umma_kernel(const __grid_constant__ NcParams p) {
-  constexpr int WATOM = 16 * 128;
-  constexpr uint32_t IDESC = make_idesc_f16(128, 16);
+__device__ __forceinline__ uint64_t sw128_desc_any(uint32_t saddr) {     // start need not be 1024-byte aligned
+  return make_sw128_desc(saddr) | ((uint64_t)((saddr >> 7) & 7u) << 49);
+}
+
+__global__ void __launch_bounds__(256, 1) nc_l2_umma_kernel(const __grid_constant__ NcParams p,
+                                                            const __grid_constant__ CUtensorMap hmap) {
+  constexpr uint32_t IDESC32 = make_idesc_f16(128, 32), IDESC16 = make_idesc_f16(128, 16);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* wsm = smem + kL2Stages * kNcAtom;       // [9 taps][16 rows][K = net | hi,lo | ch] weight images, 18 KB
-  __shared__ __align__(8) uint64_t full_bar[kL2Stages];
-  __shared__ __align__(8) uint64_t empty_bar[kL2Stages];
+  uint8_t* wsm = smem + (size_t)p.ring * p.unit_bytes;      // [9 taps][32 rows][64] weight images, 36 KB
+  __shared__ __align__(8) uint64_t full_bar[kL2MaxRing];
+  __shared__ __align__(8) uint64_t empty_bar[kL2MaxRing];
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles = p.tiles;
+  const int tiles = p.tiles, ring = p.ring, copies = p.copies;
+  const int per_a = p.KB * p.LB;
+  const float inv_pa = 1.f / (float)per_a, inv_lb = 1.f / (float)p.LB;
 
-  for (int i = threadIdx.x; i < 9 * WATOM / 16; i += 512)
+  for (int i = threadIdx.x; i < ring * p.unit_bytes / 16; i += 256) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < 9 * kL2WTap / 16; i += 256)
     reinterpret_cast<uint4*>(wsm)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kL2Stages; ++i) {
-      mbar_init(&full_bar[i], 8);                  // one arrival per producer warp
+    for (int i = 0; i < kL2MaxRing; ++i) {
+      mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -368,91 +414,72 @@ __global__ void __launch_bounds__(512, 1) nc_l2_umma_kernel(const __grid_constan
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, 256);
+  if (warp == 3 && lane == 0) tma_prefetch_desc(&hmap);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
-  if (warp == 1) {
+  if (warp == 3) {
+    // ===================== loader =====================
     if (lane == 0) {
-      int it = 0, tl = 0;
+      const uint32_t box_bytes = (uint32_t)((p.TW + (copies == 1 ? 2 : 0)) * (p.R + 2) * 128);
+      int u = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int a = fast_div(tile, inv_pa), rem = tile - a * per_a;
+        const int kb = fast_div(rem, inv_lb), lb = rem - kb * p.LB;
+        const int k0 = kb * p.R, l0 = lb * p.TW;
+        for (int c = 0; c < copies; ++c, ++u) {
+          const int s = u % ring;
+          mbar_wait(&empty_bar[s], ((uint32_t)(u / ring) & 1u) ^ 1u);
+          mbar_expect_tx(&full_bar[s], box_bytes);
+          tma_load_4d(&hmap, &full_bar[s], smem + (size_t)s * p.unit_bytes, 0, l0 - 1 + c, k0 - 1, a);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int u = 0, tl = 0;
+      const uint32_t wbase = smem_u32(wsm);
+      const uint32_t tk_stride = (uint32_t)(p.P * 128);
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
         const int slot = tl & 1;
         mbar_wait(&tempty_bar[slot], ((uint32_t)(tl >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        for (int t = 0; t < 9; ++t, ++it) {
-          const int s = it % kL2Stages;
-          mbar_wait(&full_bar[s], (uint32_t)(it / kL2Stages) & 1u);
+        const uint32_t d_slot = tmem_base + (uint32_t)(slot * 96);
+        for (int c = 0; c < copies; ++c, ++u) {
+          const int s = u % ring;
+          mbar_wait(&full_bar[s], (uint32_t)(u / ring) & 1u);
           tc_fence_after();
-          const uint64_t a = make_sw128_desc(smem_u32(smem + (size_t)s * kNcAtom));
-          const uint64_t w = make_sw128_desc(smem_u32(wsm) + (uint32_t)(t * WATOM));
+          const uint32_t blk = smem_u32(smem + (size_t)s * p.unit_bytes);
+          const int ntl = copies == 1 ? 3 : 1;
+          for (int j = 0; j < ntl; ++j) {                  // taps in (tl outer, tk inner) order for either mode
+            const int tlx = copies == 1 ? j : c;
 #pragma unroll
-          for (int net = 0; net < 2; ++net) {
-            // six independent accumulator chains per tile (net x product), 16 columns each, summed by the epilogue:
-            // a single chain of 27 dependent N = 16 MMAs is bound by the MMA latency, not by the tensor pipe
-            const uint32_t d_tmem = tmem_base + (uint32_t)(slot * 96 + net * 48);
-            const uint64_t a_hi = a + 2 * (net * 2), a_lo = a + 2 * (net * 2 + 1);      // K16 slices of the line
-            const uint64_t w_hi = w + 2 * (net * 2), w_lo = w + 2 * (net * 2 + 1);
-            const uint32_t acc = t > 0 ? 1u : 0u;
-            umma_f16(d_tmem, a_lo, w_hi, IDESC, acc);
-            umma_f16(d_tmem + 16, a_hi, w_lo, IDESC, acc);
-            umma_f16(d_tmem + 32, a_hi, w_hi, IDESC, acc);
+            for (int tk = 0; tk < 3; ++tk) {
+              const uint32_t astart = blk + (uint32_t)tk * tk_stride + (copies == 1 ? (uint32_t)(tlx * 128) : 0u);
+              const uint64_t adesc = sw128_desc_any(astart);
+              const uint64_t wdesc = make_sw128_desc(wbase + (uint32_t)((tk * 3 + tlx) * kL2WTap));
+              const uint32_t acc = (tlx > 0 || tk > 0) ? 1u : 0u;
+#pragma unroll
+              for (int net = 0; net < 2; ++net) {
+                const uint32_t d = d_slot + (uint32_t)(net * 48);
+                umma_f16(d, adesc + 2 * (net * 2), wdesc + 2 * net, IDESC32, acc);            // hi*hi | hi*lo
+                umma_f16(d + 32, adesc + 2 * (net * 2 + 1), wdesc + 2 * net, IDESC16, acc);   // lo*hi
+              }
+            }
           }
           umma_commit(&empty_bar[s]);
         }
         umma_commit(&tfull_bar[slot]);
       }
     }
-  } else if (warp >= 8) {
-    // ===================== producers: 256 threads = 32 rows x 8 chunks per pass, 4 passes per tap =====================
-    const int ptid = threadIdx.x - 256;
-    const int c = ptid & 7, r0 = ptid >> 3;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      unsigned mask[4];
-      const uint4* base[4];
-#pragma unroll
-      for (int ps = 0; ps < 4; ++ps) {
-        const long long v = (long long)tile * 128 + ps * 32 + r0;
-        const bool rv = v < p.V;
-        const int b = rv ? (int)(v % p.nB) : 0;
-        const int k = b / p.wB, l = b - k * p.wB;
-        mask[ps] = rv ? ((k > 0 ? 1u : 0u) | 2u | (k + 1 < p.hB ? 4u : 0u) | (l > 0 ? 8u : 0u) | 16u | (l + 1 < p.wB ? 32u : 0u)) : 0u;
-        base[ps] = reinterpret_cast<const uint4*>(p.hidden + (rv ? v : 0) * 64) + c;
-      }
-      auto load_tap = [&](int t, uint4* q) {
-        const int tk = t / 3, tl = t - tk * 3;
-        const unsigned need = (1u << tk) | (8u << tl);
-        const long long off = ((long long)(tk - 1) * p.wB + (tl - 1)) * 8;
-#pragma unroll
-        for (int ps = 0; ps < 4; ++ps) q[ps] = ((mask[ps] & need) == need) ? __ldg(base[ps] + off) : make_uint4(0, 0, 0, 0);
-      };
-      // three taps' lines in flight per thread (the loads are latency-bound: 8 of 9 lines hit L1, one comes from L2/HBM)
-      uint4 q[3][4];
-      load_tap(0, q[0]);
-      load_tap(1, q[1]);
-      load_tap(2, q[2]);
-#pragma unroll
-      for (int t = 0; t < 9; ++t, ++it) {
-        const int s = it % kL2Stages;
-        mbar_wait(&empty_bar[s], ((uint32_t)(it / kL2Stages) & 1u) ^ 1u);
-        uint8_t* st = smem + (size_t)s * kNcAtom;
-#pragma unroll
-        for (int ps = 0; ps < 4; ++ps) {
-          const int row = ps * 32 + r0;
-          *reinterpret_cast<uint4*>(st + row * 128 + ((c ^ (row & 7)) << 4)) = q[t % 3][ps];
-        }
-        if (t + 3 < 9) load_tap(t + 3, q[t % 3]);
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_bar[s]);
-      }
-    }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;
-    const int row = q * 32 + lane;
+    const int m = q * 32 + lane;
+    const int kk = m / p.P, ll = m - kk * p.P;
     float sx, sh;
     nc_scales(p, sx, sh);
     const float inv = p.inv_sw2 / sh;
@@ -462,23 +489,23 @@ __global__ void __launch_bounds__(512, 1) nc_l2_umma_kernel(const __grid_constan
       mbar_wait(&tfull_bar[slot], (uint32_t)(tl >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 96);
-      float acc[2][16];
+      float acc[2][9];
 #pragma unroll
       for (int net = 0; net < 2; ++net) {
-        float t1[16];
-        tmem_ld16(taddr + net * 48, acc[net]);               // lo*hi
-        tmem_ld16(taddr + net * 48 + 16, t1);                // hi*lo
+        float da[32], db[16];
+        tmem_ld32(taddr + net * 48, da);                     // [0,16) hi*hi, [16,32) hi*lo
+        tmem_ld16(taddr + net * 48 + 32, db);                // lo*hi
 #pragma unroll
-        for (int d = 0; d < 16; ++d) acc[net][d] += t1[d];
-        tmem_ld16(taddr + net * 48 + 32, t1);                // hi*hi
-#pragma unroll
-        for (int d = 0; d < 16; ++d) acc[net][d] += t1[d];
+        for (int d = 0; d < 9; ++d) acc[net][d] = (db[d] + da[16 + d]) + da[d];
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[slot]);
-      const long long v = (long long)tile * 128 + row;
-      if (v < p.V) {
+      const int a = fast_div(tile, inv_pa), rem = tile - a * per_a;
+      const int kb = fast_div(rem, inv_lb), lb = rem - kb * p.LB;
+      const int k = kb * p.R + kk, l = lb * p.TW + ll;
+      if (kk < p.R && ll < p.TW && k < p.hB && l < p.wB) {
+        const size_t v = (size_t)a * p.nB + (size_t)k * p.wB + l;
 #pragma unroll
         for (int net = 0; net < 2; ++net)
 #pragma unroll
@@ -613,16 +640,17 @@ int nc_umma_pack(const float* w1p, const float* b1p, const float* w2p, NcUmmaWei
       img1[(size_t)(0 * 2 + atom) * 32 * 64 + sw128_index(c, k)] = h;
       img1[(size_t)(1 * 2 + atom) * 32 * 64 + sw128_index(c, k)] = l;
     }
-  // layer 2: [B tap 0..8][16 rows][64]; row = partial map (ta,tb) (9 used), k = net * 32 + (hi: 0 | lo: 16) + channel
-  std::vector<__half> img2((size_t)9 * 16 * 64, __float2half(0.f));
+  // layer 2: [B tap 0..8][32 rows][64]; rows 0..15 = hi, 16..31 = lo parts of partial map (ta,tb) (9 used each),
+  // k = net * 16 + channel (K16 slice = net)
+  std::vector<__half> img2((size_t)9 * 32 * 64, __float2half(0.f));
   for (int net = 0; net < 2; ++net)
     for (int d = 0; d < 9; ++d)
       for (int t = 0; t < 9; ++t)
         for (int ch = 0; ch < 16; ++ch) {
           const float v = w2p[(d * 9 + t) * 32 + net * 16 + ch] * s2;
           const __half h = __float2half_rn(v), l = __float2half_rn(v - __half2float(h));
-          img2[(size_t)t * 16 * 64 + sw128_index(d, net * 32 + ch)] = h;
-          img2[(size_t)t * 16 * 64 + sw128_index(d, net * 32 + 16 + ch)] = l;
+          img2[(size_t)t * 32 * 64 + sw128_index(d, net * 16 + ch)] = h;
+          img2[(size_t)t * 32 * 64 + sw128_index(16 + d, net * 16 + ch)] = l;
         }
   const size_t b1 = img1.size() * 2, b2 = img2.size() * 2;
   if (W.blob == nullptr) {
@@ -641,25 +669,58 @@ int nc_umma_pack(const float* w1p, const float* b1p, const float* w2p, NcUmmaWei
 
 size_t nc_umma_scratch_bytes(size_t V) { return V * 128 + 18 * V * 4 + 4096; }
 
+static int nc_pitch(int wB) { return (wB + 2 + 3) & ~3; }
+size_t nc_umma_xp_bytes(int hA, int wA, int hB, int wB) {
+  return ((size_t)(hA + 2) * (wA + 2) * (hB + 2) + nc_l1_rows(wB)) * nc_pitch(wB) * 4 + 256;
+}
+
+// Layer-2 tiling: the (TW, R) with the fewest tiles; mode 0 compares both block layouts (ties: one haloed block).
+static void nc_l2_geometry(int hB, int wB, int mode, NcParams& p) {
+  long long best = -1;
+  for (int copies = 1; copies <= 3; copies += 2) {
+    if ((mode == 1 && copies != 1) || (mode == 2 && copies != 3)) continue;
+    for (int tw = wB < 128 ? wB : 128; tw >= 1; --tw) {
+      if (copies == 3 && wB >= 8 && tw % 8 != 0 && tw != wB) continue;   // keep tap starts 1024-byte aligned when possible
+      const int P = tw + (copies == 1 ? 2 : 0);
+      if (P > 128 && copies == 1 && tw > 126) continue;
+      const int R = (128 - tw) / P + 1;
+      const long long n = (long long)cdiv(wB, tw) * cdiv(hB, R);
+      if (best < 0 || n < best) {
+        best = n;
+        p.copies = copies; p.TW = tw; p.R = R; p.P = P;
+      }
+    }
+  }
+  p.KB = cdiv(hB, p.R);
+  p.LB = cdiv(wB, p.TW);
+  const int lines_box = (p.R + 2) * p.P, lines_read = 128 + 2 * p.P + 2;
+  p.unit_bytes = (int)align_up((size_t)(lines_box > lines_read ? lines_box : lines_read) * 128, 1024);
+  p.ring = (int)((200 * 1024 - 9 * kL2WTap) / p.unit_bytes);
+  if (p.ring > kL2MaxRing) p.ring = kL2MaxRing;
+}
+
 // x [hA*wA][hB*wB] -> out (NeighConsensus output); rowmax / colmax (optional) receive the maxima MutualMatching needs.
 // xmax: device word holding the float bits of max |x| (launch_absmax or the fused mutual_apply pass).
+// xp: scratch of nc_umma_xp_bytes().  l2_mode: 0 auto, 1 one haloed block per tile, 2 one block per column tap.
 int launch_neigh_consensus_umma(const float* x, int hA, int wA, int hB, int wB, const NcUmmaWeights& W, const float* b1p,
-                                float b2, const unsigned int* xmax, __half* hidden, float* partial, float* out,
-                                float* rowmax, unsigned int* colmax, int num_sms, cudaStream_t st) {
+                                float b2, const unsigned int* xmax, uint32_t* xp, __half* hidden, float* partial,
+                                float* out, float* rowmax, unsigned int* colmax, int l2_mode, int num_sms, cudaStream_t st) {
   NcParams p;
   memset(&p, 0, sizeof(p));
   p.hA = hA; p.wA = wA; p.hB = hB; p.wB = wB;
   p.nA = hA * wA; p.nB = hB * wB;
   p.V = (long long)p.nA * p.nB;
-  p.x = x; p.xmax = xmax; p.hidden = hidden; p.partial = partial; p.b1p = b1p;
+  p.x = x; p.xmax = xmax; p.xp = xp; p.hidden = hidden; p.partial = partial; p.b1p = b1p;
   p.wsum1 = W.wsum1; p.b1max = W.b1max; p.inv_sw1 = W.inv_sw1; p.inv_sw2 = W.inv_sw2;
-  const long long vt = (p.V + 127) / 128;
+  p.WP = nc_pitch(wB);
   const long long t1 = (long long)p.nA * ((p.nB + 127) / 128);
-  P2P_REQUIRE(vt < (1ll << 31) && t1 < (1ll << 31), "NeighConsensus: 4D volume too large");
+  P2P_REQUIRE(t1 < (1ll << 22) && p.nB < (1 << 22), "NeighConsensus: 4D volume too large");
+  nc_pad_split_kernel<<<(hA + 2) * (wA + 2), 256, 0, st>>>(p);
+  P2P_LAUNCH_OK();
   {
     p.wimg = W.img1;
     p.tiles = (int)t1;
-    const int seg = 9 * nc_l1_rows(wB) * (wB + 2) * 4;
+    const int seg = 9 * nc_l1_rows(wB) * p.WP * 4;
     const int fixed = kL1Stages * 2 * kNcAtom + 2 * 2 * 32 * 128 + 1024;
     p.l1_bufs = fixed + 2 * seg <= 220 * 1024 ? 2 : 1;
     const int smem = fixed + p.l1_bufs * seg;
@@ -672,11 +733,21 @@ int launch_neigh_consensus_umma(const float* x, int hA, int wA, int hB, int wB, 
   }
   {
     p.wimg = W.img2;
-    p.tiles = (int)vt;
-    const int smem = kL2Stages * kNcAtom + 9 * 16 * 128 + 1024;
+    nc_l2_geometry(hB, wB, l2_mode, p);
+    const long long t2 = (long long)p.nA * p.KB * p.LB;
+    P2P_REQUIRE(t2 < (1ll << 22), "NeighConsensus: 4D volume too large");
+    P2P_REQUIRE(p.ring >= 1, "NeighConsensus layer 2: block buffer does not fit in shared memory");
+    p.tiles = (int)t2;
+    CUtensorMap hmap;
+    const uint64_t dims[4] = {64, (uint64_t)wB, (uint64_t)hB, (uint64_t)p.nA};
+    const uint64_t strides[3] = {128, (uint64_t)wB * 128, (uint64_t)p.nB * 128};
+    const uint32_t box[4] = {64, (uint32_t)(p.TW + (p.copies == 1 ? 2 : 0)), (uint32_t)(p.R + 2), 1};
+    int rc = make_tmap_fp16(&hmap, hidden, 4, dims, strides, box);
+    if (rc) return rc;
+    const int smem = p.ring * p.unit_bytes + 9 * kL2WTap + 1024;
     auto k = nc_l2_umma_kernel;
     P2P_ENSURE_SMEM(k, smem);
-    k<<<p.tiles < num_sms ? p.tiles : num_sms, 512, smem, st>>>(p);
+    k<<<p.tiles < num_sms ? p.tiles : num_sms, 256, smem, st>>>(p, hmap);
     P2P_LAUNCH_OK();
   }
   if (colmax != nullptr) P2P_CUDA_OK(cudaMemsetAsync(colmax, 0, sizeof(unsigned int) * p.nB, st));
