@@ -100,6 +100,7 @@ struct p2p_handle_s {
   float *nc_w1p = nullptr, *nc_b1p = nullptr, *nc_w2p = nullptr;
   float nc_b2 = 0.f;
   NcUmmaWeights ncw;            // tensor-core NC operand images
+  void* dbg_nc[4] = {nullptr, nullptr, nullptr, nullptr};   // scratch of the last p2p_neigh_consensus call (tools/nc_debug.py)
   int opt_nc_l2_mode = 0;       // NC layer 2 block layout: 0 auto, 1 one haloed block per tile, 2 one block per column tap
   int opt_nc_impl = 1;          // 1: NeighConsensus on the tensor cores (nc_umma.cu); 0: fp32 CUDA-core kernels (shape-capped)
   Regressor reg[2];
@@ -750,6 +751,7 @@ int p2p_neigh_consensus(p2p_handle_t h, const float* in, int hA, int wA, int hB,
   uint32_t* xp = (uint32_t*)h->misc.take(nc_umma_xp_bytes(hA, wA, hB, wB));
   unsigned int* xmax = (unsigned int*)h->misc.take(16);
   P2P_REQUIRE(hidden && partial && xmax && xp, "scratch carve failed");
+  h->dbg_nc[0] = hidden; h->dbg_nc[1] = partial; h->dbg_nc[2] = xp; h->dbg_nc[3] = xmax;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (h->opt_nc_impl == 1) {
     if ((rc = launch_absmax(in, V, xmax, st))) return rc;
@@ -757,6 +759,17 @@ int p2p_neigh_consensus(p2p_handle_t h, const float* in, int hA, int wA, int hB,
                                        nullptr, nullptr, h->opt_nc_l2_mode, sms(h), st);
   }
   return launch_neigh_consensus(in, hA, wA, hB, wB, h->nc_w1p, h->nc_b1p, h->nc_w2p, h->nc_b2, hidden, out, st);
+}
+
+// Development hook (tools/nc_debug.py; not part of include/p2p_b200.h): copies `bytes` of an intermediate of the last
+// p2p_neigh_consensus call to the host -- which = 0 hidden [V][64] fp16, 1 partial [18][V] f32, 2 xp (padded hi|lo
+// words), 3 xmax word.
+P2P_API int p2p_debug_nc_scratch(p2p_handle_t h, int which, void* host_dst, size_t bytes) {
+  P2P_ENTER(h);
+  P2P_REQUIRE(which >= 0 && which < 4 && host_dst != nullptr && h->dbg_nc[which] != nullptr, "bad argument");
+  P2P_CUDA_OK(cudaDeviceSynchronize());
+  P2P_CUDA_OK(cudaMemcpy(host_dst, h->dbg_nc[which], bytes, cudaMemcpyDeviceToHost));
+  return 0;
 }
 
 int p2p_proposals(p2p_handle_t h, const float* corr4d, const uint8_t* delta_code, int hA, int wA, int hB, int wB,

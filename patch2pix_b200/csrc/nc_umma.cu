@@ -367,20 +367,19 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
 // k0-1 .. k0+R, zero-filled outside the grid -- into shared memory in the 128B-swizzled layout tcgen05 reads, and the
 // A operand of B-tap (tk, tl) is simply that block starting (tk * P + tl) lines further on:
 //   copies = 1   the block carries its column halo (box TW + 2 wide, P = TW + 2): one load per tile; the two MMA rows
-//                per tile row that fall on the halo are junk and skipped by the epilogue.  Tap starts are 128-byte
-//                granular, so the descriptors carry the swizzle phase ("base offset" = address bits 7..9).
-//   copies = 3   one block per column tap tl, loaded with the column origin shifted by tl - 1 (P = TW): no junk rows
-//                and, when TW % 8 == 0, every tap start is 1024-byte aligned; costs 3 loads per tile.
+//                per tile row that fall on the halo are junk and skipped by the epilogue.
+//   copies = 3   one block per column tap tl, loaded with the column origin shifted by tl - 1 (P = TW): no junk rows,
+//                3 loads per tile (wins when TW + 2 would waste too many of the 128 MMA rows, e.g. wB = 64).
+// Tap starts are 128-byte granular, not 1024-byte aligned.  The 128B swizzle -- of TMA writes and of tcgen05 operand
+// reads alike -- is a pure function of the shared-memory ADDRESS bits (chunk ^= address bits 7..9), so a descriptor
+// that starts mid-pattern reads consistently with its "base offset" field left 0 (measured: with the field set to the
+// start's phase the results are wrong, with 0 they are exact for every shift; tools/nc_debug.py).
 // Per tap and net: a_hi x [w_hi | w_lo] (one N = 32 MMA gives hi*hi and hi*lo) and a_lo x w_hi (N = 16): four
 // independent accumulator chains per tile, summed by the epilogue.
 // 256 threads (warp 1 MMA, 2 TMEM, 3 loader, 4..7 epilogue); ring of block buffers.
 // ------------------------------------------------------------------------------------------------
 constexpr int kL2MaxRing = 8;
 constexpr int kL2WTap = 32 * 128;     // weight image per B-tap: rows 0..15 w_hi (9 used), 16..31 w_lo; K16 slice = net
-
-__device__ __forceinline__ uint64_t sw128_desc_any(uint32_t saddr) {     // start need not be 1024-byte aligned
-  return make_sw128_desc(saddr) | ((uint64_t)((saddr >> 7) & 7u) << 49);
-}
 
 __global__ void __launch_bounds__(256, 1) nc_l2_umma_kernel(const __grid_constant__ NcParams p,
                                                             const __grid_constant__ CUtensorMap hmap) {
@@ -447,7 +446,7 @@ __global__ void __launch_bounds__(256, 1) nc_l2_umma_kernel(const __grid_constan
         const int slot = tl & 1;
         mbar_wait(&tempty_bar[slot], ((uint32_t)(tl >> 1) & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t d_slot = tmem_base + (uint32_t)(slot * 96);
+        const uint32_t d_slot = tmem_base + (uint32_t)(slot * 128);   // [0,64) hi products of net 0 | 1, [64,96) lo*hi
         for (int c = 0; c < copies; ++c, ++u) {
           const int s = u % ring;
           mbar_wait(&full_bar[s], (uint32_t)(u / ring) & 1u);
@@ -459,14 +458,13 @@ __global__ void __launch_bounds__(256, 1) nc_l2_umma_kernel(const __grid_constan
 #pragma unroll
             for (int tk = 0; tk < 3; ++tk) {
               const uint32_t astart = blk + (uint32_t)tk * tk_stride + (copies == 1 ? (uint32_t)(tlx * 128) : 0u);
-              const uint64_t adesc = sw128_desc_any(astart);
+              const uint64_t adesc = make_sw128_desc(astart);          // 128-byte granular start, base offset 0
               const uint64_t wdesc = make_sw128_desc(wbase + (uint32_t)((tk * 3 + tlx) * kL2WTap));
               const uint32_t acc = (tlx > 0 || tk > 0) ? 1u : 0u;
 #pragma unroll
               for (int net = 0; net < 2; ++net) {
-                const uint32_t d = d_slot + (uint32_t)(net * 48);
-                umma_f16(d, adesc + 2 * (net * 2), wdesc + 2 * net, IDESC32, acc);            // hi*hi | hi*lo
-                umma_f16(d + 32, adesc + 2 * (net * 2 + 1), wdesc + 2 * net, IDESC16, acc);   // lo*hi
+                umma_f16(d_slot + (uint32_t)(net * 32), adesc + 2 * (net * 2), wdesc + 2 * net, IDESC32, acc);           // hi*hi | hi*lo
+                umma_f16(d_slot + (uint32_t)(64 + net * 16), adesc + 2 * (net * 2 + 1), wdesc + 2 * net, IDESC16, acc);  // lo*hi
               }
             }
           }
@@ -488,13 +486,13 @@ __global__ void __launch_bounds__(256, 1) nc_l2_umma_kernel(const __grid_constan
       const int slot = tl & 1;
       mbar_wait(&tfull_bar[slot], (uint32_t)(tl >> 1) & 1u);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 96);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 128);
       float acc[2][9];
 #pragma unroll
       for (int net = 0; net < 2; ++net) {
         float da[32], db[16];
-        tmem_ld32(taddr + net * 48, da);                     // [0,16) hi*hi, [16,32) hi*lo
-        tmem_ld16(taddr + net * 48 + 32, db);                // lo*hi
+        tmem_ld32(taddr + net * 32, da);                     // [0,16) hi*hi, [16,32) hi*lo
+        tmem_ld16(taddr + 64 + net * 16, db);                // lo*hi
 #pragma unroll
         for (int d = 0; d < 9; ++d) acc[net][d] = (db[d] + da[16 + d]) + da[d];
       }
@@ -547,6 +545,9 @@ int launch_absmax(const float* x, size_t n, unsigned int* out, cudaStream_t st) 
 // ------------------------------------------------------------------------------------------------
 constexpr int kCombineRows = 2;      // A cells per block: nA / 2 blocks keep every SM busy with several blocks
 
+// VEC = 4: float4 columns (nB % 4 == 0).  Every neighbour plane is loaded unconditionally from a clamped (always valid)
+// cell and masked afterwards, so the 18 loads of an output element are independent and in flight together.
+template <int VEC>
 __global__ void __launch_bounds__(256) nc_combine_kernel(const float* __restrict__ P, int hA, int wA, int nB, float b2,
                                                         float* __restrict__ out, float* __restrict__ rowmax,
                                                         unsigned int* __restrict__ colmax) {
@@ -558,30 +559,55 @@ __global__ void __launch_bounds__(256) nc_combine_kernel(const float* __restrict
   float rm[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) rm[r] = -INFINITY;
-  for (int col = threadIdx.x; col < nB; col += 256) {
-    float cm = -INFINITY;
+  for (int col = threadIdx.x * VEC; col < nB; col += 256 * VEC) {
+    float cm[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) cm[e] = -INFINITY;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int a = r0 + r;
       if (a >= nA) continue;
       const int ia = a / wA, ja = a - ia * wA;
-      float tot = 0.f;
+      float v[2][9][VEC];
+      bool ok[9];
 #pragma unroll
-      for (int net = 0; net < 2; ++net) {
-        float acc = b2;
+      for (int d = 0; d < 9; ++d) {
+        const int i2 = ia + d / 3 - 1, j2 = ja + d % 3 - 1;
+        ok[d] = i2 >= 0 && i2 < hA && j2 >= 0 && j2 < wA;
+        const size_t cell = ok[d] ? (size_t)(i2 * wA + j2) : (size_t)a;
 #pragma unroll
-        for (int d = 0; d < 9; ++d) {
-          const int i2 = ia + d / 3 - 1, j2 = ja + d % 3 - 1;
-          if (i2 >= 0 && i2 < hA && j2 >= 0 && j2 < wA)
-            acc += __ldg(P + (size_t)(net * 9 + d) * V + (size_t)(i2 * wA + j2) * nB + col);
+        for (int net = 0; net < 2; ++net) {
+          const float* src = P + (size_t)(net * 9 + d) * V + cell * nB + col;
+          if (VEC == 4) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(src));
+            v[net][d][0] = q.x; v[net][d][VEC > 1 ? 1 : 0] = q.y; v[net][d][VEC > 2 ? 2 : 0] = q.z; v[net][d][VEC > 3 ? 3 : 0] = q.w;
+          } else {
+            v[net][d][0] = __ldg(src);
+          }
         }
-        tot += fmaxf(acc, 0.f);
       }
-      out[(size_t)a * nB + col] = tot;
-      rm[r] = fmaxf(rm[r], tot);
-      cm = fmaxf(cm, tot);
+      float tot[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        tot[e] = 0.f;
+#pragma unroll
+        for (int net = 0; net < 2; ++net) {
+          float acc = b2;
+#pragma unroll
+          for (int d = 0; d < 9; ++d) acc += ok[d] ? v[net][d][e] : 0.f;     // same order as before; adding +0 is exact
+          tot[e] += fmaxf(acc, 0.f);
+        }
+        rm[r] = fmaxf(rm[r], tot[e]);
+        cm[e] = fmaxf(cm[e], tot[e]);
+      }
+      float* o = out + (size_t)a * nB + col;
+      if (VEC == 4) *reinterpret_cast<float4*>(o) = make_float4(tot[0], tot[VEC > 1 ? 1 : 0], tot[VEC > 2 ? 2 : 0], tot[VEC > 3 ? 3 : 0]);
+      else o[0] = tot[0];
     }
-    if (colmax != nullptr) atomicMax(colmax + col, f2ord(cm));
+    if (colmax != nullptr) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) atomicMax(colmax + col + e, f2ord(cm[e]));
+    }
   }
   if (rowmax == nullptr) return;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -751,7 +777,10 @@ int launch_neigh_consensus_umma(const float* x, int hA, int wA, int hB, int wB, 
     P2P_LAUNCH_OK();
   }
   if (colmax != nullptr) P2P_CUDA_OK(cudaMemsetAsync(colmax, 0, sizeof(unsigned int) * p.nB, st));
-  nc_combine_kernel<<<cdiv(p.nA, kCombineRows), 256, 0, st>>>(partial, hA, wA, p.nB, b2, out, rowmax, colmax);
+  if (p.nB % 4 == 0)
+    nc_combine_kernel<4><<<cdiv(p.nA, kCombineRows), 256, 0, st>>>(partial, hA, wA, p.nB, b2, out, rowmax, colmax);
+  else
+    nc_combine_kernel<1><<<cdiv(p.nA, kCombineRows), 256, 0, st>>>(partial, hA, wA, p.nB, b2, out, rowmax, colmax);
   P2P_LAUNCH_OK();
   return 0;
 }

@@ -260,7 +260,7 @@ def test_neigh_consensus_tensor_core_vs_oracle(nets, cnets, seeded_sd, consensus
 @pytest.mark.parametrize('mode', [1, 2])
 def test_neigh_consensus_layer2_block_layouts(cnets, consensus_sd, mode):
     """NC layer 2 reads its A operand as SHIFTED windows of one block of hidden lines (nc_umma.cu): mode 1 = one
-    haloed block per tile (tap starts 128-byte granular: descriptor base offset), mode 2 = one block per column tap.
+    haloed block per tile, mode 2 = one block per column tap; tap starts are 128-byte granular in both.
     Both layouts against the oracle on shapes with wB % 8 == 0, wB % 8 != 0, multi-row / single-row / split-row tiles;
     the two layouts issue the same MMAs in the same order, so they must agree bit for bit."""
     from oracle import p2p_oracle as O
