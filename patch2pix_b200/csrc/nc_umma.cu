@@ -147,12 +147,12 @@ __host__ __device__ inline int nc_l1_rows(int wB) { return 127 / wB + 4; }      
 
 __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_constant__ NcParams p) {
   constexpr int STAGE_BYTES = 2 * kNcAtom;         // A_hi + A_lo of one atom
-  constexpr int WATOM = 32 * 128;
-  constexpr uint32_t IDESC = make_idesc_f16(128, 32);
+  constexpr int WATOM = 64 * 128;                  // weight image of one atom: rows 0..31 w_hi, 32..63 w_lo
+  constexpr uint32_t IDESC64 = make_idesc_f16(128, 64), IDESC32 = make_idesc_f16(128, 32);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* wsm = smem + kL1Stages * STAGE_BYTES;                          // [hi|lo][atom] weight images, 16 KB
-  uint8_t* xs = wsm + 4 * WATOM;                                          // [bufs][9][rows][pitch] words
+  uint8_t* wsm = smem + kL1Stages * STAGE_BYTES;                          // [atom][hi|lo] weight images, 16 KB
+  uint8_t* xs = wsm + 2 * WATOM;                                          // [bufs][9][rows][pitch] words
   __shared__ __align__(8) uint64_t full_bar[kL1Stages];
   __shared__ __align__(8) uint64_t empty_bar[kL1Stages];
   __shared__ __align__(8) uint64_t tfull_bar[2];
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
   const int nbuf = p.l1_bufs;
 
   for (int i = threadIdx.x; i < kL1Stages * STAGE_BYTES / 16; i += kL1Threads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = threadIdx.x; i < 4 * WATOM / 16; i += kL1Threads)
+  for (int i = threadIdx.x; i < 2 * WATOM / 16; i += kL1Threads)
     reinterpret_cast<uint4*>(wsm)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kL1Stages; ++i) {
@@ -193,32 +193,35 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 1) {
-    if (lane == 0) {
-      int it = 0, tl = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
-        const int slot = tl & 1;
-        mbar_wait(&tempty_bar[slot], ((uint32_t)(tl >> 1) & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t d0 = tmem_base + (uint32_t)(slot * 96);            // three 32-column blocks: lo*hi, hi*lo, hi*hi
+    // ===================== MMA issuer: the whole warp runs the loop (uniform), one elected lane issues =====================
+    int it = 0, tl = 0;
+    const uint32_t sbase = smem_u32(smem), wbase = smem_u32(wsm);
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
+      const int slot = tl & 1;
+      mbar_wait(&tempty_bar[slot], ((uint32_t)(tl >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + (uint32_t)(slot * 96);            // [0,32) hi*hi, [32,64) hi*lo, [64,96) lo*hi
 #pragma unroll
-        for (int atom = 0; atom < 2; ++atom, ++it) {
-          const int s = it % kL1Stages;
-          mbar_wait(&full_bar[s], (uint32_t)(it / kL1Stages) & 1u);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
-          const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + kNcAtom);
-          const uint32_t wb = smem_u32(wsm) + (uint32_t)(atom * WATOM);
-          const uint64_t w_hi = make_sw128_desc(wb), w_lo = make_sw128_desc(wb + 2 * WATOM);
-          const int nk = atom == 0 ? 4 : 2;           // taps 64..80 live in the first two K16 slices of atom 1
-          for (int kk = 0; kk < nk; ++kk) {
+      for (int atom = 0; atom < 2; ++atom, ++it) {
+        const int s = it % kL1Stages;
+        mbar_wait(&full_bar[s], (uint32_t)(it / kL1Stages) & 1u);
+        tc_fence_after();
+        const uint32_t sa = sbase + (uint32_t)(s * STAGE_BYTES);
+        const uint64_t a_hi = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + kNcAtom);
+        const uint64_t w = make_sw128_desc(wbase + (uint32_t)(atom * WATOM));     // rows 0..31 w_hi, 32..63 w_lo
+        constexpr int nk0 = 4, nk1 = 2;             // taps 64..80 live in the first two K16 slices of atom 1
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < nk0; ++kk) {
+            if (atom == 1 && kk >= nk1) break;
             const uint32_t acc = (atom > 0 || kk > 0) ? 1u : 0u;
-            umma_f16(d0, a_lo + 2 * kk, w_hi + 2 * kk, IDESC, acc);
-            umma_f16(d0 + 32, a_hi + 2 * kk, w_lo + 2 * kk, IDESC, acc);
-            umma_f16(d0 + 64, a_hi + 2 * kk, w_hi + 2 * kk, IDESC, acc);
+            umma_f16(d0, a_hi + 2 * kk, w + 2 * kk, IDESC64, acc);          // hi*hi | hi*lo
+            umma_f16(d0 + 64, a_lo + 2 * kk, w + 2 * kk, IDESC32, acc);     // lo*hi
           }
           umma_commit(&empty_bar[s]);
+          if (atom == 1) umma_commit(&tfull_bar[slot]);
         }
-        umma_commit(&tfull_bar[slot]);
+        __syncwarp();
       }
     }
   } else if (warp == 3) {
@@ -326,11 +329,11 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 96);
       float acc[32], t1[32];
-      tmem_ld32(taddr, acc);                       // lo*hi
+      tmem_ld32(taddr + 64, acc);                  // lo*hi
       tmem_ld32(taddr + 32, t1);                   // hi*lo
 #pragma unroll
       for (int c = 0; c < 32; ++c) acc[c] += t1[c];
-      tmem_ld32(taddr + 64, t1);                   // hi*hi
+      tmem_ld32(taddr, t1);                        // hi*hi
 #pragma unroll
       for (int c = 0; c < 32; ++c) acc[c] += t1[c];
       tc_fence_before();
@@ -381,6 +384,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
 constexpr int kL2MaxRing = 8;
 constexpr int kL2WTap = 32 * 128;     // weight image per B-tap: rows 0..15 w_hi (9 used), 16..31 w_lo; K16 slice = net
 
+template <int COPIES>
 __global__ void __launch_bounds__(256, 1) nc_l2_umma_kernel(const __grid_constant__ NcParams p,
                                                             const __grid_constant__ CUtensorMap hmap) {
   constexpr uint32_t IDESC32 = make_idesc_f16(128, 32), IDESC16 = make_idesc_f16(128, 16);
@@ -394,7 +398,8 @@ __global__ void __launch_bounds__(256, 1) nc_l2_umma_kernel(const __grid_constan
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles = p.tiles, ring = p.ring, copies = p.copies;
+  const int tiles = p.tiles, ring = p.ring;
+  constexpr int copies = COPIES;
   const int per_a = p.KB * p.LB;
   const float inv_pa = 1.f / (float)per_a, inv_lb = 1.f / (float)p.LB;
 
@@ -438,27 +443,29 @@ __global__ void __launch_bounds__(256, 1) nc_l2_umma_kernel(const __grid_constan
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int u = 0, tl = 0;
-      const uint32_t wbase = smem_u32(wsm);
-      const uint32_t tk_stride = (uint32_t)(p.P * 128);
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
-        const int slot = tl & 1;
-        mbar_wait(&tempty_bar[slot], ((uint32_t)(tl >> 1) & 1u) ^ 1u);
+    // ===================== MMA issuer: the whole warp runs the loop (uniform), one elected lane issues =====================
+    int u = 0, tl = 0;
+    const uint32_t wbase = smem_u32(wsm), sbase = smem_u32(smem);
+    const uint32_t tk_stride = (uint32_t)(p.P * 128);
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
+      const int slot = tl & 1;
+      mbar_wait(&tempty_bar[slot], ((uint32_t)(tl >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_slot = tmem_base + (uint32_t)(slot * 128);   // [0,64) hi products of net 0 | 1, [64,96) lo*hi
+#pragma unroll
+      for (int c = 0; c < COPIES; ++c, ++u) {
+        const int s = u % ring;
+        mbar_wait(&full_bar[s], (uint32_t)(u / ring) & 1u);
         tc_fence_after();
-        const uint32_t d_slot = tmem_base + (uint32_t)(slot * 128);   // [0,64) hi products of net 0 | 1, [64,96) lo*hi
-        for (int c = 0; c < copies; ++c, ++u) {
-          const int s = u % ring;
-          mbar_wait(&full_bar[s], (uint32_t)(u / ring) & 1u);
-          tc_fence_after();
-          const uint32_t blk = smem_u32(smem + (size_t)s * p.unit_bytes);
-          const int ntl = copies == 1 ? 3 : 1;
-          for (int j = 0; j < ntl; ++j) {                  // taps in (tl outer, tk inner) order for either mode
-            const int tlx = copies == 1 ? j : c;
+        const uint32_t blk = sbase + (uint32_t)(s * p.unit_bytes);
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < (COPIES == 1 ? 3 : 1); ++j) {        // taps in (tl outer, tk inner) order for either layout
+            const int tlx = COPIES == 1 ? j : c;
 #pragma unroll
             for (int tk = 0; tk < 3; ++tk) {
-              const uint32_t astart = blk + (uint32_t)tk * tk_stride + (copies == 1 ? (uint32_t)(tlx * 128) : 0u);
-              const uint64_t adesc = make_sw128_desc(astart);          // 128-byte granular start, base offset 0
+              // 128-byte granular start, base offset 0 (see above)
+              const uint64_t adesc = make_sw128_desc(blk + (uint32_t)tk * tk_stride + (COPIES == 1 ? (uint32_t)(tlx * 128) : 0u));
               const uint64_t wdesc = make_sw128_desc(wbase + (uint32_t)((tk * 3 + tlx) * kL2WTap));
               const uint32_t acc = (tlx > 0 || tk > 0) ? 1u : 0u;
 #pragma unroll
@@ -469,8 +476,9 @@ __global__ void __launch_bounds__(256, 1) nc_l2_umma_kernel(const __grid_constan
             }
           }
           umma_commit(&empty_bar[s]);
+          if (c == COPIES - 1) umma_commit(&tfull_bar[slot]);
         }
-        umma_commit(&tfull_bar[slot]);
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -656,15 +664,15 @@ int nc_umma_pack(const float* w1p, const float* b1p, const float* w2p, NcUmmaWei
   W.b1max = b1max;
   W.inv_sw1 = 1.f / s1;
   W.inv_sw2 = 1.f / s2;
-  // layer 1: [hi|lo][atom 0..1][32 rows][64]; k = tap (81 used)
-  std::vector<__half> img1((size_t)2 * 2 * 32 * 64, __float2half(0.f));
+  // layer 1: [atom 0..1][hi 32 rows | lo 32 rows][64]; k = tap (81 used)
+  std::vector<__half> img1((size_t)2 * 64 * 64, __float2half(0.f));
   for (int c = 0; c < 32; ++c)
     for (int t = 0; t < 81; ++t) {
       const float v = w1p[t * 32 + c] * s1;
       const __half h = __float2half_rn(v), l = __float2half_rn(v - __half2float(h));
       const int atom = t >> 6, k = t & 63;
-      img1[(size_t)(0 * 2 + atom) * 32 * 64 + sw128_index(c, k)] = h;
-      img1[(size_t)(1 * 2 + atom) * 32 * 64 + sw128_index(c, k)] = l;
+      img1[(size_t)atom * 64 * 64 + sw128_index(c, k)] = h;
+      img1[(size_t)atom * 64 * 64 + sw128_index(32 + c, k)] = l;
     }
   // layer 2: [B tap 0..8][32 rows][64]; rows 0..15 = hi, 16..31 = lo parts of partial map (ta,tb) (9 used each),
   // k = net * 16 + channel (K16 slice = net)
@@ -695,7 +703,9 @@ int nc_umma_pack(const float* w1p, const float* b1p, const float* w2p, NcUmmaWei
 
 size_t nc_umma_scratch_bytes(size_t V) { return V * 128 + 18 * V * 4 + 4096; }
 
-static int nc_pitch(int wB) { return (wB + 2 + 3) & ~3; }
+// padded row pitch of xp: a multiple of 4 words (16-byte bulk copies) and == wB + 32..35, so that the lanes of a warp --
+// consecutive B cells, which wrap to the next row mid-warp -- still hit 32 distinct shared-memory banks
+static int nc_pitch(int wB) { return (wB + 32 + 3) & ~3; }
 size_t nc_umma_xp_bytes(int hA, int wA, int hB, int wB) {
   return ((size_t)(hA + 2) * (wA + 2) * (hB + 2) + nc_l1_rows(wB)) * nc_pitch(wB) * 4 + 256;
 }
@@ -706,7 +716,6 @@ static void nc_l2_geometry(int hB, int wB, int mode, NcParams& p) {
   for (int copies = 1; copies <= 3; copies += 2) {
     if ((mode == 1 && copies != 1) || (mode == 2 && copies != 3)) continue;
     for (int tw = wB < 128 ? wB : 128; tw >= 1; --tw) {
-      if (copies == 3 && wB >= 8 && tw % 8 != 0 && tw != wB) continue;   // keep tap starts 1024-byte aligned when possible
       const int P = tw + (copies == 1 ? 2 : 0);
       if (P > 128 && copies == 1 && tw > 126) continue;
       const int R = (128 - tw) / P + 1;
@@ -747,10 +756,10 @@ int launch_neigh_consensus_umma(const float* x, int hA, int wA, int hB, int wB, 
     p.wimg = W.img1;
     p.tiles = (int)t1;
     const int seg = 9 * nc_l1_rows(wB) * p.WP * 4;
-    const int fixed = kL1Stages * 2 * kNcAtom + 2 * 2 * 32 * 128 + 1024;
+    const int fixed = kL1Stages * 2 * kNcAtom + 2 * 64 * 128 + 1024;
     p.l1_bufs = fixed + 2 * seg <= 220 * 1024 ? 2 : 1;
     const int smem = fixed + p.l1_bufs * seg;
-    P2P_REQUIRE(smem <= 220 * 1024, "NeighConsensus layer 1: B grid too wide for the shared-memory staging (wB <= ~500)");
+    P2P_REQUIRE(smem <= 220 * 1024, "NeighConsensus layer 1: B grid too wide for the shared-memory staging (wB <= ~480)");
     auto k = nc_l1_umma_kernel;
     P2P_ENSURE_SMEM(k, smem);
     const int grid = p.tiles < num_sms ? p.tiles : num_sms;
@@ -771,9 +780,16 @@ int launch_neigh_consensus_umma(const float* x, int hA, int wA, int hB, int wB, 
     int rc = make_tmap_fp16(&hmap, hidden, 4, dims, strides, box);
     if (rc) return rc;
     const int smem = p.ring * p.unit_bytes + 9 * kL2WTap + 1024;
-    auto k = nc_l2_umma_kernel;
-    P2P_ENSURE_SMEM(k, smem);
-    k<<<p.tiles < num_sms ? p.tiles : num_sms, 256, smem, st>>>(p, hmap);
+    const int grid = p.tiles < num_sms ? p.tiles : num_sms;
+    if (p.copies == 1) {
+      auto k = nc_l2_umma_kernel<1>;
+      P2P_ENSURE_SMEM(k, smem);
+      k<<<grid, 256, smem, st>>>(p, hmap);
+    } else {
+      auto k = nc_l2_umma_kernel<3>;
+      P2P_ENSURE_SMEM(k, smem);
+      k<<<grid, 256, smem, st>>>(p, hmap);
+    }
     P2P_LAUNCH_OK();
   }
   if (colmax != nullptr) P2P_CUDA_OK(cudaMemsetAsync(colmax, 0, sizeof(unsigned int) * p.nB, st));

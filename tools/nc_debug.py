@@ -32,7 +32,7 @@ def run(net, sd, dims, mode, verbose):
     torch.cuda.synchronize()
     nA, nB = hA * wA, hB * wB
     V = nA * nB
-    WP = (wB + 2 + 3) & ~3
+    WP = (wB + 32 + 3) & ~3
 
     def grab(which, dtype, n):
         a = np.empty(n, dtype=dtype)
