@@ -898,7 +898,10 @@ __global__ void __launch_bounds__(1024) unique_rows_kernel(const long long* __re
           idx[lo] = i1; idx[hi] = i0;
         }
       }
-      __syncthreads();
+      // pairs t in [32c, 32c + 32) touch only elements [64c, 64c + 64) while stride <= 32, and a warp always owns the
+      // same pair groups: those sub-steps need warp-level ordering only (33 block barriers instead of 78 at P = 4096)
+      if (stride > 32 || stride == 1) __syncthreads();
+      else __syncwarp();
     }
   }
   // compaction in sorted order: chunks of T elements, block-wide exclusive scan per chunk

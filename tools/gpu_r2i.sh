@@ -2,7 +2,7 @@
 # Round-2 run I: NC v6 (bulk-copy staged layer 1, shifted-window layer 2), bench with the profiler pass split off.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-KREG='regex:umma_|nc_|patch_gather|fc_parse|fc3_parse|pooled_split|corr_pool|l2norm|mutual_apply|rowcolmax|proposals|unique_rows|select_anchor|feature_prep|window_map|flai_risky|delta|absmax'
+KREG='regex:umma_|nc_|patch_gather|fc_parse|fc3_parse|pooled_split|corr_pool|l2norm|mutual_apply|rowcolmax|proposals|unique_rows|select_anchor|feature_prep|window_map|flag_risky|delta|absmax'
 echo "=== nc unit"; timeout 900 python -m pytest tests -q -m gpu -p no:cacheprovider --timeout 300 -k "neigh_consensus or large_shapes or coarse_stages" > gpurun_out/i_nc.log 2>&1; echo "rc=$?"; tail -12 gpurun_out/i_nc.log
 cat gpurun_out/parity_nc_layer2_mode1.json gpurun_out/parity_nc_layer2_mode2.json 2>/dev/null | tr -d '\n ' | head -c 3000; echo
 echo "=== bench 20"; timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/i_bench_20.json 2> gpurun_out/i_bench_20.err; echo "rc=$?"
