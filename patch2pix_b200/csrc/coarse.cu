@@ -887,7 +887,7 @@ __global__ void __launch_bounds__(1024) unique_rows_kernel(const long long* __re
   for (int size = 2; size <= P; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       for (int t = tid; t < (P >> 1); t += T) {
-        const int lo = (t / stride) * (stride << 1) + (t % stride);
+        const int lo = ((t & ~(stride - 1)) << 1) + (t & (stride - 1));   // stride is a power of two
         const int hi = lo + stride;
         const bool asc = ((lo & size) == 0);
         const unsigned long long k0 = keys[lo], k1 = keys[hi];

@@ -145,14 +145,16 @@ constexpr int kL1Threads = 768, kL1ProducerWarps = 16;
 
 __host__ __device__ inline int nc_l1_rows(int wB) { return 127 / wB + 4; }      // padded B rows a tile can touch
 
-__global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_constant__ NcParams p) {
+__global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_constant__ NcParams p,
+                                                                  const __grid_constant__ CUtensorMap hstore) {
   constexpr int STAGE_BYTES = 2 * kNcAtom;         // A_hi + A_lo of one atom
   constexpr int WATOM = 64 * 128;                  // weight image of one atom: rows 0..31 w_hi, 32..63 w_lo
   constexpr uint32_t IDESC64 = make_idesc_f16(128, 64), IDESC32 = make_idesc_f16(128, 32);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* wsm = smem + kL1Stages * STAGE_BYTES;                          // [atom][hi|lo] weight images, 16 KB
-  uint8_t* xs = wsm + 2 * WATOM;                                          // [bufs][9][rows][pitch] words
+  uint8_t* hst = wsm + 2 * WATOM;                                         // 2 x 16 KB staging of finished hidden tiles
+  uint8_t* xs = hst + 2 * kNcAtom;                                        // [bufs][9][rows][pitch] words
   __shared__ __align__(8) uint64_t full_bar[kL1Stages];
   __shared__ __align__(8) uint64_t empty_bar[kL1Stages];
   __shared__ __align__(8) uint64_t tfull_bar[2];
@@ -339,22 +341,37 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[slot]);     // accumulators are in registers: the slot can be refilled
-      const int a = fast_div(tile, inv_tb), b = ((tile - a * TB) << 7) + row;
-      if (b < p.nB) {
-        const long long v = (long long)a * p.nB + b;
-        uint4 o[8];
+      const int a = fast_div(tile, inv_tb), b0 = (tile - a * TB) << 7;
+      // The tile's 128 hidden lines are contiguous in global memory.  They go through a swizzled shared staging
+      // buffer (conflict-free 16-byte stores) and leave with ONE tensor-map store per tile: a per-thread
+      // st.global.v4 of its own 128-byte line costs 32 LSU wavefronts per warp instruction and made the epilogue the
+      // largest consumer of the LSU data pipe.  Rows past the end of the B grid are clipped by the tensor map.
+      uint8_t* sb = hst + (size_t)(tl & 1) * kNcAtom;
+      if (threadIdx.x == 128) bulk_wait_group_read<1>();        // the store of tile tl-2 has finished reading this buffer
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (b0 + row < p.nB) {
+        const uint32_t so = smem_u32(sb) + (uint32_t)(row * 128);
+        const uint32_t sw = (uint32_t)(row & 7);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {                    // 8 channels at a time: net 0 ch 0-7, 8-15, net 1 ch 0-7, 8-15
           float hval[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) hval[c] = fmaxf(fmaf(acc[g * 8 + c], inv, __ldg(p.b1p + g * 8 + c)), 0.f) * sh;
-          split8_bounded(hval, o[(g >> 1) * 4 + (g & 1)], o[(g >> 1) * 4 + 2 + (g & 1)]);   // [net][hi0 hi1 lo0 lo1]
+          uint4 hi, lo;
+          split8_bounded(hval, hi, lo);
+          const uint32_t chi = (uint32_t)((g >> 1) * 4 + (g & 1)), clo = chi + 2;        // [net][hi0 hi1 lo0 lo1]
+          sts_v4(so + ((chi ^ sw) << 4), hi.x, hi.y, hi.z, hi.w);
+          sts_v4(so + ((clo ^ sw) << 4), lo.x, lo.y, lo.z, lo.w);
         }
-        uint4* dst = reinterpret_cast<uint4*>(p.hidden + v * 64);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) dst[i] = o[i];
+      }
+      fence_proxy_async();
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (threadIdx.x == 128) {
+        tma_store_3d(&hstore, sb, 0, b0, a);
+        bulk_commit_group();
       }
     }
+    if (threadIdx.x == 128) bulk_wait_group_read<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -556,18 +573,18 @@ constexpr int kCombineRows = 2;      // A cells per block: nA / 2 blocks keep ev
 // VEC = 4: float4 columns (nB % 4 == 0).  Every neighbour plane is loaded unconditionally from a clamped (always valid)
 // cell and masked afterwards, so the 18 loads of an output element are independent and in flight together.
 template <int VEC>
-__global__ void __launch_bounds__(256) nc_combine_kernel(const float* __restrict__ P, int hA, int wA, int nB, float b2,
+__global__ void __launch_bounds__(1024) nc_combine_kernel(const float* __restrict__ P, int hA, int wA, int nB, float b2,
                                                         float* __restrict__ out, float* __restrict__ rowmax,
                                                         unsigned int* __restrict__ colmax) {
   constexpr int R = kCombineRows;
-  __shared__ float red[8][R];
+  __shared__ float red[32][R];
   const int nA = hA * wA;
   const size_t V = (size_t)nA * nB;
   const int r0 = blockIdx.x * R;
   float rm[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) rm[r] = -INFINITY;
-  for (int col = threadIdx.x * VEC; col < nB; col += 256 * VEC) {
+  for (int col = threadIdx.x * VEC; col < nB; col += (int)blockDim.x * VEC) {
     float cm[VEC];
 #pragma unroll
     for (int e = 0; e < VEC; ++e) cm[e] = -INFINITY;
@@ -627,8 +644,7 @@ __global__ void __launch_bounds__(256) nc_combine_kernel(const float* __restrict
   __syncthreads();
   if (threadIdx.x < R && r0 + threadIdx.x < nA) {
     float v = red[0][threadIdx.x];
-#pragma unroll
-    for (int wv = 1; wv < 8; ++wv) v = fmaxf(v, red[wv][threadIdx.x]);
+    for (int wv = 1; wv < (int)(blockDim.x >> 5); ++wv) v = fmaxf(v, red[wv][threadIdx.x]);
     rowmax[r0 + threadIdx.x] = v;
   }
 }
@@ -756,14 +772,20 @@ int launch_neigh_consensus_umma(const float* x, int hA, int wA, int hB, int wB, 
     p.wimg = W.img1;
     p.tiles = (int)t1;
     const int seg = 9 * nc_l1_rows(wB) * p.WP * 4;
-    const int fixed = kL1Stages * 2 * kNcAtom + 2 * 64 * 128 + 1024;
+    const int fixed = kL1Stages * 2 * kNcAtom + 2 * 64 * 128 + 2 * kNcAtom + 1024;
     p.l1_bufs = fixed + 2 * seg <= 220 * 1024 ? 2 : 1;
     const int smem = fixed + p.l1_bufs * seg;
     P2P_REQUIRE(smem <= 220 * 1024, "NeighConsensus layer 1: B grid too wide for the shared-memory staging (wB <= ~480)");
+    CUtensorMap hstore;
+    const uint64_t dims[3] = {64, (uint64_t)p.nB, (uint64_t)p.nA};
+    const uint64_t strides[2] = {128, (uint64_t)p.nB * 128};
+    const uint32_t box[3] = {64, 128, 1};
+    int rc = make_tmap_fp16(&hstore, hidden, 3, dims, strides, box);
+    if (rc) return rc;
     auto k = nc_l1_umma_kernel;
     P2P_ENSURE_SMEM(k, smem);
     const int grid = p.tiles < num_sms ? p.tiles : num_sms;
-    k<<<grid, kL1Threads, smem, st>>>(p);
+    k<<<grid, kL1Threads, smem, st>>>(p, hstore);
     P2P_LAUNCH_OK();
   }
   {
@@ -793,10 +815,14 @@ int launch_neigh_consensus_umma(const float* x, int hA, int wA, int hB, int wB, 
     P2P_LAUNCH_OK();
   }
   if (colmax != nullptr) P2P_CUDA_OK(cudaMemsetAsync(colmax, 0, sizeof(unsigned int) * p.nB, st));
-  if (p.nB % 4 == 0)
-    nc_combine_kernel<4><<<cdiv(p.nA, kCombineRows), 256, 0, st>>>(partial, hA, wA, p.nB, b2, out, rowmax, colmax);
+  // block = one pass over the columns of its rows when they fit (nB = 1200 -> 300 float4 columns -> 320 threads)
+  const int vec = p.nB % 4 == 0 ? 4 : 1;
+  int threads = (cdiv(p.nB, vec) + 31) & ~31;
+  threads = threads > 1024 ? 1024 : (threads < 64 ? 64 : threads);
+  if (vec == 4)
+    nc_combine_kernel<4><<<cdiv(p.nA, kCombineRows), threads, 0, st>>>(partial, hA, wA, p.nB, b2, out, rowmax, colmax);
   else
-    nc_combine_kernel<1><<<cdiv(p.nA, kCombineRows), 256, 0, st>>>(partial, hA, wA, p.nB, b2, out, rowmax, colmax);
+    nc_combine_kernel<1><<<cdiv(p.nA, kCombineRows), threads, 0, st>>>(partial, hA, wA, p.nB, b2, out, rowmax, colmax);
   P2P_LAUNCH_OK();
   return 0;
 }

@@ -97,6 +97,18 @@ __device__ __forceinline__ void tma_load_5d(const CUtensorMap* m, uint64_t* bar,
       : "memory");
 }
 
+// tensor-map store shared -> global (3-D), bulk-group completion
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {     // at most N groups still READING their shared source
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 // ---- CTA-pair (cta_group::2) variants: two CTAs of a cluster drive one M=256 MMA; the barrier that
 // collects TMA bytes / epilogue arrivals lives in the leader (cluster rank 0) CTA, addressed by clearing
 // the rank bit of the CTA-local shared address.
