@@ -45,6 +45,7 @@
 namespace p2p {
 
 constexpr int kNcAtom = 128 * 128;   // bytes of one [128 rows x 64 fp16] swizzled operand atom
+constexpr int kNcSlots = 4;          // TMEM accumulator slots per CTA: MMAs of up to 3 tiles run ahead of the epilogue
 
 struct NcParams {
   int hA, wA, hB, wB, nA, nB;
@@ -157,8 +158,8 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
   uint8_t* xs = hst + 2 * kNcAtom;                                        // [bufs][9][rows][pitch] words
   __shared__ __align__(8) uint64_t full_bar[kL1Stages];
   __shared__ __align__(8) uint64_t empty_bar[kL1Stages];
-  __shared__ __align__(8) uint64_t tfull_bar[2];
-  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ __align__(8) uint64_t tfull_bar[kNcSlots];
+  __shared__ __align__(8) uint64_t tempty_bar[kNcSlots];
   __shared__ __align__(8) uint64_t xfull_bar[2];
   __shared__ __align__(8) uint64_t xempty_bar[2];
   __shared__ uint32_t tmem_base_smem;
@@ -179,15 +180,17 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
       mbar_init(&full_bar[i], kL1ProducerWarps);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kNcSlots; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&xfull_bar[i], 1);
       mbar_init(&xempty_bar[i], kL1ProducerWarps);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(&tmem_base_smem, 256);
+  if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -199,8 +202,8 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
     int it = 0, tl = 0;
     const uint32_t sbase = smem_u32(smem), wbase = smem_u32(wsm);
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
-      const int slot = tl & 1;
-      mbar_wait(&tempty_bar[slot], ((uint32_t)(tl >> 1) & 1u) ^ 1u);
+      const int slot = tl % kNcSlots;
+      mbar_wait(&tempty_bar[slot], ((uint32_t)(tl / kNcSlots) & 1u) ^ 1u);
       tc_fence_after();
       const uint32_t d0 = tmem_base + (uint32_t)(slot * 96);            // [0,32) hi*hi, [32,64) hi*lo, [64,96) lo*hi
 #pragma unroll
@@ -231,8 +234,8 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
     if (lane == 0) {
       int tl = 0;
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
-        const int buf = tl % nbuf;
-        mbar_wait(&xempty_bar[buf], ((uint32_t)(tl / nbuf) & 1u) ^ 1u);
+        const int buf = nbuf == 2 ? (tl & 1) : 0;
+        mbar_wait(&xempty_bar[buf], ((uint32_t)(nbuf == 2 ? (tl >> 1) : tl) & 1u) ^ 1u);
         const int a = fast_div(tile, inv_tb), b0 = (tile - a * TB) << 7;
         const int ia = a / p.wA, ja = a - ia * p.wA;
         const int k0 = fast_div(b0, inv_wb);                          // padded row k0 = unpadded row k0 - 1
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
     const uint32_t otk = (uint32_t)(p.WP * 4);
     int it = 0, tl = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
-      const int buf = tl % nbuf;
+      const int buf = nbuf == 2 ? (tl & 1) : 0;
       const int a = fast_div(tile, inv_tb), b0 = (tile - a * TB) << 7;
       const int b = b0 + r;
       const bool rv = b < p.nB;                                // rows past the end of the B grid are not built: their
@@ -262,7 +265,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
       const int k0 = fast_div(b0, inv_wb);
       // shared address of the (tk, tl) = (0, 0) tap of A-neighbour 0: tap (d, tk, tl) is at + d*NRB + tk*otk + tl*4
       const uint32_t base = smem_u32(xs) + (uint32_t)buf * 9u * NRB + (uint32_t)(((k - k0) * p.WP + l) * 4);
-      mbar_wait(&xfull_bar[buf], (uint32_t)(tl / nbuf) & 1u);
+      mbar_wait(&xfull_bar[buf], (uint32_t)(nbuf == 2 ? (tl >> 1) : tl) & 1u);
       auto chunk = [&](auto ATOM, auto CH, uint32_t st) {
         constexpr int atom = decltype(ATOM)::value, c = decltype(CH)::value;
         uint32_t w[8];
@@ -326,8 +329,8 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
     const float inv = p.inv_sw1 / sx;
     int tl = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
-      const int slot = tl & 1;
-      mbar_wait(&tfull_bar[slot], (uint32_t)(tl >> 1) & 1u);
+      const int slot = tl % kNcSlots;
+      mbar_wait(&tfull_bar[slot], (uint32_t)(tl / kNcSlots) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 96);
       float acc[32], t1[32];
@@ -377,7 +380,7 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -410,8 +413,8 @@ __global__ void __launch_bounds__(256, 1) nc_l2_umma_kernel(const __grid_constan
   uint8_t* wsm = smem + (size_t)p.ring * p.unit_bytes;      // [9 taps][32 rows][64] weight images, 36 KB
   __shared__ __align__(8) uint64_t full_bar[kL2MaxRing];
   __shared__ __align__(8) uint64_t empty_bar[kL2MaxRing];
-  __shared__ __align__(8) uint64_t tfull_bar[2];
-  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ __align__(8) uint64_t tfull_bar[kNcSlots];
+  __shared__ __align__(8) uint64_t tempty_bar[kNcSlots];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -428,13 +431,13 @@ __global__ void __launch_bounds__(256, 1) nc_l2_umma_kernel(const __grid_constan
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kNcSlots; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(&tmem_base_smem, 256);
+  if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
   if (warp == 3 && lane == 0) tma_prefetch_desc(&hmap);
   fence_proxy_async();
   tc_fence_before();
@@ -465,8 +468,8 @@ __global__ void __launch_bounds__(256, 1) nc_l2_umma_kernel(const __grid_constan
     const uint32_t wbase = smem_u32(wsm), sbase = smem_u32(smem);
     const uint32_t tk_stride = (uint32_t)(p.P * 128);
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
-      const int slot = tl & 1;
-      mbar_wait(&tempty_bar[slot], ((uint32_t)(tl >> 1) & 1u) ^ 1u);
+      const int slot = tl % kNcSlots;
+      mbar_wait(&tempty_bar[slot], ((uint32_t)(tl / kNcSlots) & 1u) ^ 1u);
       tc_fence_after();
       const uint32_t d_slot = tmem_base + (uint32_t)(slot * 128);   // [0,64) hi products of net 0 | 1, [64,96) lo*hi
 #pragma unroll
@@ -508,8 +511,8 @@ __global__ void __launch_bounds__(256, 1) nc_l2_umma_kernel(const __grid_constan
     const float inv = p.inv_sw2 / sh;
     int tl = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
-      const int slot = tl & 1;
-      mbar_wait(&tfull_bar[slot], (uint32_t)(tl >> 1) & 1u);
+      const int slot = tl % kNcSlots;
+      mbar_wait(&tfull_bar[slot], (uint32_t)(tl / kNcSlots) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 128);
       float acc[2][9];
@@ -540,7 +543,7 @@ __global__ void __launch_bounds__(256, 1) nc_l2_umma_kernel(const __grid_constan
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -719,9 +722,27 @@ int nc_umma_pack(const float* w1p, const float* b1p, const float* w2p, NcUmmaWei
 
 size_t nc_umma_scratch_bytes(size_t V) { return V * 128 + 18 * V * 4 + 4096; }
 
-// padded row pitch of xp: a multiple of 4 words (16-byte bulk copies) and == wB + 32..35, so that the lanes of a warp --
-// consecutive B cells, which wrap to the next row mid-warp -- still hit 32 distinct shared-memory banks
-static int nc_pitch(int wB) { return (wB + 32 + 3) & ~3; }
+constexpr int kL1SmemBudget = 225 * 1024;
+constexpr int kL1SmemFixed = kL1Stages * 2 * kNcAtom + 2 * 64 * 128 + 2 * kNcAtom + 1024;   // operand ring, weights, store staging
+
+// Padded row pitch of xp (words) and the number of layer-1 staging buffers.  Preferred pitch: a multiple of 4 words
+// (16-byte bulk copies) that is == wB + 32..35, so that the lanes of a warp -- consecutive B cells, which wrap to the
+// next row mid-warp -- still hit 32 distinct shared-memory banks; very narrow or very wide grids fall back to the
+// compact pitch wB + 2..5 and / or a single buffer when the staging block would not fit.
+static void nc_l1_staging(int wB, int& pitch, int& bufs) {
+  const int wide = (wB + 32 + 3) & ~3, compact = (wB + 2 + 3) & ~3;
+  const int cand[4][2] = {{wide, 2}, {compact, 2}, {wide, 1}, {compact, 1}};
+  for (int i = 0; i < 4; ++i) {
+    pitch = cand[i][0];
+    bufs = cand[i][1];
+    if (kL1SmemFixed + bufs * 9 * nc_l1_rows(wB) * pitch * 4 <= kL1SmemBudget) return;
+  }
+}
+static int nc_pitch(int wB) {
+  int pitch, bufs;
+  nc_l1_staging(wB, pitch, bufs);
+  return pitch;
+}
 size_t nc_umma_xp_bytes(int hA, int wA, int hB, int wB) {
   return ((size_t)(hA + 2) * (wA + 2) * (hB + 2) + nc_l1_rows(wB)) * nc_pitch(wB) * 4 + 256;
 }
@@ -771,11 +792,11 @@ int launch_neigh_consensus_umma(const float* x, int hA, int wA, int hB, int wB, 
   {
     p.wimg = W.img1;
     p.tiles = (int)t1;
-    const int seg = 9 * nc_l1_rows(wB) * p.WP * 4;
-    const int fixed = kL1Stages * 2 * kNcAtom + 2 * 64 * 128 + 2 * kNcAtom + 1024;
-    p.l1_bufs = fixed + 2 * seg <= 220 * 1024 ? 2 : 1;
-    const int smem = fixed + p.l1_bufs * seg;
-    P2P_REQUIRE(smem <= 220 * 1024, "NeighConsensus layer 1: B grid too wide for the shared-memory staging (wB <= ~480)");
+    int pitch;
+    nc_l1_staging(wB, pitch, p.l1_bufs);
+    const int smem = kL1SmemFixed + p.l1_bufs * 9 * nc_l1_rows(wB) * p.WP * 4;
+    P2P_REQUIRE(pitch == p.WP && smem <= kL1SmemBudget,
+                "NeighConsensus layer 1: B grid too wide for the shared-memory staging (wB <= ~340)");
     CUtensorMap hstore;
     const uint64_t dims[3] = {64, (uint64_t)p.nB, (uint64_t)p.nA};
     const uint64_t strides[2] = {128, (uint64_t)p.nB * 128};

@@ -1,0 +1,26 @@
+#!/bin/bash
+# Round-2 run M: NC layer-1 tensor-map store epilogue, combine block sizing, unique_rows index math.
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+KREG='regex:umma_|nc_|patch_gather|fc_parse|fc3_parse|pooled_split|corr_pool|l2norm|mutual_apply|rowcolmax|proposals|unique_rows|select_anchor|feature_prep|window_map|flag_risky|delta|absmax'
+echo "=== tests"; timeout 2400 python -m pytest tests -q -m gpu -p no:cacheprovider --timeout 1200 > gpurun_out/m_tests.log 2>&1; echo "rc=$?"; tail -6 gpurun_out/m_tests.log
+echo "=== bench 20"; timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/m_bench_20.json 2> gpurun_out/m_bench_20.err; echo "rc=$?"
+echo "=== ncu launches"; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREG" -s 70 -c 140 --csv --log-file gpurun_out/m_launches.csv python bench.py --steps 8 --warmup 1 --no-cpu-baseline > gpurun_out/m_ncu_launch.log 2>&1; echo "rc=$?"
+echo "=== ncu full nc"; timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"nc_pad|nc_l1|nc_l2|nc_combine|unique_rows" -s 5 -c 5 -o gpurun_out/m_prof_nc -f python bench.py --steps 3 --warmup 1 --no-cpu-baseline > gpurun_out/m_ncu_nc.log 2>&1; echo "rc=$?"
+python - <<'PY'
+import json, csv, collections
+d=json.loads(open('gpurun_out/m_bench_20.json').read().strip().splitlines()[-1])
+print('value', round(d['value'],3), 'ms/step', round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value'],2), 'launches', d['gpu_launches'])
+print({k:round(v['ms_per_launch'],3) for k,v in d['kernels'].items()})
+r=d['roofline']; print({k:r[k] for k in ('gap_ms_per_step','kernel_event_sum_ms_per_step')}); print(d['config'].get('step_ms_quantiles'))
+rows=list(csv.reader(open('gpurun_out/m_launches.csv')))
+for i,r in enumerate(rows):
+    if 'Kernel Name' in r: hdr=r; start=i; break
+ki=hdr.index('Kernel Name'); vi=hdr.index('Metric Value')
+dd=collections.defaultdict(list)
+for r in rows[start+2:]:
+    if len(r)>vi:
+        try: dd[r[ki].split('(')[0][:50]].append(float(r[vi].replace(',','')))
+        except: pass
+for k,v in sorted(dd.items(), key=lambda kv:-sum(kv[1])): print(f'{k:52s} n={len(v):3d} avg={sum(v)/len(v)/1000:8.1f} us')
+PY
