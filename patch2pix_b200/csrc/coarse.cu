@@ -854,14 +854,16 @@ int launch_proposals(const float* corr, const uint8_t* code, int hA, int wA, int
 // ------------------------------------------------------------------------------------------------
 // `gscratch` != nullptr: keys / indices live in global scratch instead of shared memory (candidate lists beyond
 // 16384 rows, e.g. ksize 1 at 1024x768; slower, same result).
+// GLOBAL = false keeps the address space of keys / idx known at compile time (ld.shared / st.shared; with a pointer that
+// may be either space every access of the sort went through the generic path and the kernel was bound by it).
+template <bool GLOBAL>
 __global__ void __launch_bounds__(1024) unique_rows_kernel(const long long* __restrict__ rows, int n, int P, int mutual,
                                                           const float* __restrict__ scores, float thres,
                                                           int* __restrict__ ids_out, int* __restrict__ count_out,
                                                           unsigned char* gscratch) {
   extern __shared__ __align__(16) unsigned char smraw_[];
-  unsigned char* smraw = gscratch != nullptr ? gscratch : smraw_;
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smraw);
-  int* idx = reinterpret_cast<int*>(smraw + (size_t)P * 8);
+  unsigned long long* keys = GLOBAL ? reinterpret_cast<unsigned long long*>(gscratch) : reinterpret_cast<unsigned long long*>(smraw_);
+  int* idx = GLOBAL ? reinterpret_cast<int*>(gscratch + (size_t)P * 8) : reinterpret_cast<int*>(smraw_ + (size_t)P * 8);
   __shared__ int s_bad;
   __shared__ int s_warp[32];
   __shared__ int s_base;
@@ -965,11 +967,11 @@ int launch_unique_rows(const long long* rows, int n, int mutual, const float* sc
   while (P < n) P <<= 1;
   if (n > 16384) {
     P2P_REQUIRE(gscratch != nullptr, "unique_rows: scratch missing for a large candidate list");
-    unique_rows_kernel<<<1, 1024, 0, st>>>(rows, n, P, mutual, scores, thres, ids_out, count_out, gscratch);
+    unique_rows_kernel<true><<<1, 1024, 0, st>>>(rows, n, P, mutual, scores, thres, ids_out, count_out, gscratch);
   } else {
     const size_t smem = (size_t)P * 12;
-    P2P_ENSURE_SMEM(unique_rows_kernel, smem);
-    unique_rows_kernel<<<1, 1024, smem, st>>>(rows, n, P, mutual, scores, thres, ids_out, count_out, nullptr);
+    P2P_ENSURE_SMEM(unique_rows_kernel<false>, smem);
+    unique_rows_kernel<false><<<1, 1024, smem, st>>>(rows, n, P, mutual, scores, thres, ids_out, count_out, nullptr);
   }
   P2P_LAUNCH_OK();
   return 0;
