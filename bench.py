@@ -419,15 +419,19 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps, sampler=None):
+        import gc
         barrier()
         if sampler:
             sampler.start()
             time.sleep(0.01)
+        gc.collect()
+        gc.disable()          # a generational collection of this process's heap is a 10-40 ms host stall mid-region
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn(steps)
         e1.record()
         torch.cuda.synchronize()
+        gc.enable()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
