@@ -108,23 +108,27 @@ reasons = getattr(N, 'nvmlDeviceGetCurrentClocksEventReasons', None) or N.nvmlDe
 print('ready', N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM), flush=True)
 sys.stdin.readline()                      # 'go'
 import select
-i, pw = 0, 0.0
-while not select.select([sys.stdin], [], [], 0.005)[0]:
+i, pw, slow = 0, 0.0, 0.0
+while not select.select([sys.stdin], [], [], 0.01)[0]:
+    t0 = time.perf_counter()
     if i % 8 == 0:
         pw = N.nvmlDeviceGetPowerUsage(h) / 1e3
-    print(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), pw, int(reasons(h)), flush=False)
+    c, r = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM), int(reasons(h))
+    slow = max(slow, time.perf_counter() - t0)
+    print(c, pw, r, flush=False)
     i += 1
+print('slowest', slow * 1e3)
 sys.stdout.flush()
 """
 
 
 class ClockSampler:
-    """Samples SM clock / power / throttle reasons through NVML every ~5 ms while the timed region runs -- in a separate
+    """Samples SM clock / power / throttle reasons through NVML every ~10 ms while the timed region runs -- in a separate
     PROCESS (a sampler thread in this interpreter contends for the GIL with the launch loop and shows up as launch gaps;
     nvidia-smi's own start-up would miss a 0.5 s region)."""
 
     def __init__(self, index):
-        self.index, self.proc, self.sm_max, self.err = index, None, None, None
+        self.index, self.proc, self.sm_max, self.err, self.slowest_ms = index, None, None, None, None
         try:
             vis = os.environ.get('CUDA_VISIBLE_DEVICES')
             phys = int(vis.split(',')[index]) if vis and vis.split(',')[index].isdigit() else index
@@ -177,6 +181,8 @@ class ClockSampler:
                     p = ln.split()
                     if len(p) == 3:
                         rows.append((float(p[0]), float(p[1]), int(p[2])))
+                    elif len(p) == 2 and p[0] == 'slowest':
+                        self.slowest_ms = float(p[1])
             except Exception as e:
                 self.err = repr(e)
                 self.proc.kill()
@@ -189,7 +195,8 @@ class ClockSampler:
             allbits |= r[2]
         return {'sm_mhz': statistics.median(r[0] for r in rows), 'sm_min_mhz': min(r[0] for r in rows),
                 'sm_max_mhz': self.sm_max, 'power_w_max': max(r[1] for r in rows), 'samples': len(rows),
-                'interval_ms': 5 if self.proc else 20, 'source': 'nvml (separate process)' if self.proc else 'nvml (thread)', 'reasons': [n for n, b in bits.items() if allbits & b]}
+                'interval_ms': 10 if self.proc else 20, 'slowest_nvml_query_ms': self.slowest_ms,
+                'source': 'nvml (separate process)' if self.proc else 'nvml (thread)', 'reasons': [n for n, b in bits.items() if allbits & b]}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -360,6 +367,8 @@ def run_ours(args):
 
     step_events = [torch.cuda.Event(enable_timing=True) for _ in range(max(K, 1))]   # created before the timed region
 
+    host_stamps = [0.0] * max(K, 1)
+
     def hot_finish(tk, out_slot=None, keep=None, stamp=False):
         i, ticket = tk
         np.random.seed(mine[i] % (2 ** 31))               # the reference's global numpy RNG, seeded per pair
@@ -369,6 +378,7 @@ def run_ours(args):
             results[out_slot, :, 4] = fine_p[0]
             if stamp:
                 step_events[out_slot].record()
+                host_stamps[out_slot] = time.perf_counter()
         if keep is not None:
             keep.append(cm[0])
 
@@ -442,7 +452,8 @@ def run_ours(args):
     with torch.no_grad():
         # ---- hot path, features resident in HBM -------------------------------------------------
         hot_loop(0, Wm, False)
-        sharder.gather_results(results)                  # warm-up of the collective (NCCL sets up channels lazily)
+        hot_loop(0, min(Wm, K), True, [] if rank == 0 else None, stamp=True)   # the recorded path itself (result stores,
+        sharder.gather_results(results)                  # step events); warm-up of the collective (NCCL sets up channels lazily)
         l0 = net._handle.launch_count()
         sampler = ClockSampler(local) if rank == 0 else None
         anchors_seen = []
@@ -454,7 +465,11 @@ def run_ours(args):
         launches = net._handle.launch_count() - l0
         clocks = sampler.finish() if sampler else None
         nst = min(K, n_mine)
-        step_ms = sorted(step_events[j].elapsed_time(step_events[j + 1]) for j in range(nst - 1))
+        step_raw = [step_events[j].elapsed_time(step_events[j + 1]) for j in range(nst - 1)]
+        step_ms = sorted(step_raw)
+        worst = max(range(len(step_raw)), key=lambda j: step_raw[j]) if step_raw else None
+        worst_step = None if worst is None else {'step': worst + 1, 'gpu_ms': step_raw[worst],
+                                                 'host_ms': (host_stamps[worst + 1] - host_stamps[worst]) * 1e3}
         # ---- per-kernel breakdown: a SEPARATE, untimed-for-the-headline pass with an event pair around every launch
         # group (the event bookkeeping of the profiler stays out of the headline number) ----
         Kp = max(min(K, n_mine, 20), 1)
@@ -611,7 +626,8 @@ def run_ours(args):
                        'sequence': 'train_patch2pix.py:97-118 under eval/no_grad', 'pairs_per_step': world,
                        'total_pairs': pairs, 'distinct_proposals_first_pairs': distinct,
                        'step_ms_quantiles': ({'p10': step_ms[len(step_ms) // 10], 'p50': step_ms[len(step_ms) // 2],
-                                              'p90': step_ms[(len(step_ms) * 9) // 10], 'max': step_ms[-1]} if step_ms else None),
+                                              'p90': step_ms[(len(step_ms) * 9) // 10], 'max': step_ms[-1],
+                                              'slowest_step': worst_step} if step_ms else None),
                        'l2': f'{len(imgs)} distinct pairs cycled per rank; per-step working set (~3 GB of scratch written and '
                              f're-read) >> 126 MB L2',
                        'pipelining': f'{depth} pairs in flight per GPU (the coarse stages of the next pairs are enqueued before the host sync of the oldest)',
