@@ -49,25 +49,57 @@ def _feat_format(t, name):
 
 class _PinnedPool:
     """Recycled pinned int32 staging buffers.  A per-step `torch.empty(pin_memory=True)` can fall through PyTorch's
-    caching host allocator to cudaHostAlloc (hundreds of microseconds, serialising) whenever the cached block is still
-    marked in use; here a buffer returns to the pool with the event after which it may be rewritten."""
+    caching host allocator to cudaHostAlloc (page locking: anything from hundreds of microseconds to hundreds of
+    milliseconds on a loaded host, and serialising) whenever the cached block is still marked in use; here a buffer
+    returns to the pool with the event after which it may be rewritten, and the pool grows eight buffers at a time
+    from ONE pinned allocation, so a steady-state loop never page-locks memory."""
 
     def __init__(self):
         self._free = {}
+        self._slabs = []
 
     def get(self, n):
         lst = self._free.setdefault(n, [])
         for i, (t, ev) in enumerate(lst):
             if ev is None or ev.query():
                 lst.pop(i)
+                if ev is not None:
+                    _events.put(ev)
                 return t
-        return torch.empty(n, dtype=torch.int32).pin_memory()
+        slab = torch.empty(8 * n, dtype=torch.int32).pin_memory()
+        self._slabs.append(slab)
+        views = list(slab.view(8, n).unbind(0))
+        lst.extend((v, None) for v in views[1:])
+        return views[0]
 
     def put(self, t, ev=None):
         self._free.setdefault(t.numel(), []).append((t, ev))
 
 
+class _EventPool:
+    """Recycled CUDA events (one per ticket / staging copy), per device: no event creation in a steady-state loop."""
+
+    def __init__(self):
+        self._free = {}
+
+    def get(self, device):
+        ev = None
+        lst = self._free.get(torch.device(device).index)
+        if lst:
+            ev = lst.pop()
+        if ev is None:
+            ev = torch.cuda.Event()
+        ev._p2p_dev = torch.device(device).index
+        return ev
+
+    def put(self, ev):
+        lst = self._free.setdefault(getattr(ev, '_p2p_dev', None), [])
+        if len(lst) < 256:
+            lst.append(ev)
+
+
 _pinned = _PinnedPool()
+_events = _EventPool()
 
 
 class _UniqueTicket:
@@ -85,7 +117,8 @@ class _UniqueTicket:
             self.event.synchronize()
             self.n, bad, self.n_pass_selected, self.n_pass_all = self.cnt_host.tolist()
             _pinned.put(self.cnt_host)           # the copy has completed: the buffer may be reused at once
-            self.cnt_host = None
+            _events.put(self.event)
+            self.cnt_host = self.event = None
             if bad:
                 raise RuntimeError('filter_coarse: match coordinates must lie in [0, 65535]')
         return self.n
@@ -109,7 +142,7 @@ def unique_rows_submit(rows, mutual=True, handle=None, scores=None, thres=0.0):
         _lib.check(h.lib.p2p_unique_rows(h.h, _lib.ptr(rows), n, int(bool(mutual)), _lib.ptr(scores), float(thres),
                                          _lib.ptr(ids), _lib.ptr(cnt), h.stream()))
         cnt_host.copy_(cnt, non_blocking=True)
-        ev = torch.cuda.Event()
+        ev = _events.get(rows.device)
         ev.record(torch.cuda.current_stream(rows.device))
     return _UniqueTicket(ids, cnt_host, ev, float(thres) if scores is not None else None)
 
@@ -161,7 +194,7 @@ def _filter_coarse_core(coarse_matches, match_scores, ncn_thres, mutual, ptmax, 
                 stage = _pinned.get(int(ptmax))
                 stage.numpy()[:] = iids
                 sel, m = stage.to(imatches.device, non_blocking=True), int(ptmax)
-                ev = torch.cuda.Event()
+                ev = _events.get(imatches.device)
                 ev.record(torch.cuda.current_stream(imatches.device))
                 _pinned.put(stage, ev)           # reusable once the host-to-device copy has executed
             if ids is None and sel is None and panc == 1:
