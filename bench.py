@@ -438,7 +438,8 @@ def run_ours(args):
         gc.collect()
         gc.disable()          # a generational collection of this process's heap is a 10-40 ms host stall mid-region
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        barrier()             # ranks leave the preparations above (sampler start-up on rank 0, collection) together: a rank
+        e0.record()           # that starts early only waits for the late one in the gather that closes the region
         fn(steps)
         e1.record()
         torch.cuda.synchronize()
