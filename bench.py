@@ -61,6 +61,7 @@ def parse():
     ap.add_argument('--nc-impl', type=int, default=None, help='1: tensor-core NeighConsensus (default), 0: fp32 CUDA-core kernels')
     ap.add_argument('--backbone-fp32', action='store_true', help='keep cuDNN TF32 off in the e2e backbone')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--e2e-modes', default='tf32,fp16,fp32', help='backbone variants timed end to end (the first is the headline)')
     ap.add_argument('--pairs', type=int, default=0,
                     help='strong-scaling mode (BASELINE configs[4]): this many pairs in total, sharded over the ranks; '
                          'rank 0 re-computes a sample of the other ranks\' pairs and checks bit-equality')
@@ -533,7 +534,7 @@ def run_ours(args):
         # the fp32-backbone variant is measured beside it (parity: tests/test_gpu_parity.py::test_backbone_graph_tf32_path)
         e2e_ms = {}
         host_outs = [torch.empty(n_patches, 5).pin_memory() for _ in range(depth + 1)]
-        for mode in (['fp32'] if args.backbone_fp32 else ['tf32', 'fp16', 'fp32']):
+        for mode in (['fp32'] if args.backbone_fp32 else [m for m in args.e2e_modes.split(',') if m in ('tf32', 'fp16', 'fp32')]):
             if strong and mode != 'tf32' and not args.backbone_fp32:
                 continue
             torch.backends.cudnn.allow_tf32 = mode != 'fp32'
@@ -610,11 +611,11 @@ def run_ours(args):
                               f'({r["coarse_s"]:.2f} s) + mid/fine refine on {r["n_sample"]} of {r["n_full"]} patches scaled to '
                               f'the full pair ({r["refine_s_extrapolated"]:.2f} s); backbone excluded ({r["backbone_s"]:.2f} s)'),
                    'with_backbone_pairs_per_s': 1.0 / r['e2e_s']}
-        head = 'fp32' if args.backbone_fp32 else 'tf32'
+        head = 'fp32' if args.backbone_fp32 else next(m for m in args.e2e_modes.split(',') if m in e2e_ms)
         e2e = {'value': pairs / (e2e_ms[head] / 1e3), 'unit': 'pairs/s', 'ms_per_step': e2e_ms[head] / K,
                'h2d_bytes_per_step': 2 * 3 * H * W * 4, 'd2h_bytes_per_step': n_patches * 5 * 4,
                'path': 'pinned host images -> H2D -> cuDNN ResNet34 pyramid, both images as one batch, CUDA graph ('
-                       + ('fp32' if head == 'fp32' else 'TF32 convs, PyTorch default') + ') -> hot path -> D2H matches+scores'}
+                       + {'fp32': 'fp32', 'tf32': 'TF32 convs, PyTorch default', 'fp16': 'fp16 channels-last'}[head] + ') -> hot path -> D2H matches+scores'}
         if 'fp32' in e2e_ms and head != 'fp32':
             e2e['fp32_backbone_value'] = pairs / (e2e_ms['fp32'] / 1e3)
         if 'fp16' in e2e_ms:

@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 N=${1:-2}
 mkdir -p gpurun_out
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
-echo "=== weak N=$N"; timeout 900 $RUN bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/m_bench_${N}gpu.json 2> gpurun_out/m_bench_${N}gpu.err; echo "rc=$?"; tail -2 gpurun_out/m_bench_${N}gpu.err
+echo "=== weak N=$N"; timeout 900 $RUN bench.py --gpus $N --steps 20 --warmup 5 --e2e-modes tf32 > gpurun_out/m_bench_${N}gpu.json 2> gpurun_out/m_bench_${N}gpu.err; echo "rc=$?"; tail -2 gpurun_out/m_bench_${N}gpu.err
 echo "=== strong 512 pairs N=$N"; timeout 1200 $RUN bench.py --gpus $N --pairs 512 --warmup 3 > gpurun_out/m_bench_${N}gpu_512pairs.json 2> gpurun_out/m_bench_${N}gpu_512pairs.err; echo "rc=$?"; tail -2 gpurun_out/m_bench_${N}gpu_512pairs.err
 [ "$N" -le 2 ] && echo "=== 1 GPU, same box, same flags" && timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/m_bench_1gpu_samebox.json 2> gpurun_out/m_bench_1gpu_samebox.err; echo "rc=$?"
 python - <<PY
