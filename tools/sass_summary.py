@@ -8,7 +8,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'patch2pix_b200', 'libp2p_b200.so')
-PAT = {'tcgen05.mma (UTC*MMA)': r'\bUTC[A-Z]*MMA', 'tcgen05.mma cta_group::2 (.2CTA)': r'UTC[A-Z]*MMA\.2CTA', 'TMA load (UTMALDG)': r'\bUTMALDG',
+PAT = {'tcgen05.mma (UTC*MMA)': r'\bUTC[A-Z]*MMA', 'tcgen05.mma cta_group::2 (.2CTA)': r'UTC[A-Z]*MMA\.2CTA', 'TMA load (UTMALDG)': r'\bUTMALDG', 'TMA store (UTMASTG)': r'\bUTMASTG', 'bulk copy (UBLKCP)': r'\bUBLKCP',
        'tcgen05.ld (LDTM)': r'\bLDTM', 'tcgen05.commit (UTCBAR)': r'\bUTCBAR', 'TMEM alloc (UTCATOMSWS)': r'\bUTCATOMSWS',
        'mbarrier (SYNCS)': r'\bSYNCS', 'legacy HMMA (mma.sync)': r'\bHMMA', 'FFMA': r'\bFFMA'}
 
