@@ -61,6 +61,7 @@ def parse():
     ap.add_argument('--nc-impl', type=int, default=None, help='1: tensor-core NeighConsensus (default), 0: fp32 CUDA-core kernels')
     ap.add_argument('--backbone-fp32', action='store_true', help='keep cuDNN TF32 off in the e2e backbone')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--e2e-overlap', type=int, default=1, help='1: backbone graph of the next pair on a side stream (overlaps the hot path)')
     ap.add_argument('--e2e-modes', default='tf32,fp16,fp32', help='backbone variants timed end to end (the first is the headline)')
     ap.add_argument('--pairs', type=int, default=0,
                     help='strong-scaling mode (BASELINE configs[4]): this many pairs in total, sharded over the ranks; '
@@ -539,7 +540,7 @@ def run_ours(args):
                 continue
             torch.backends.cudnn.allow_tf32 = mode != 'fp32'
             torch.backends.cudnn.benchmark = True
-            net.enable_backbone_graphs(H, W, instances=depth + 1, fast=mode == 'fp16')
+            net.enable_backbone_graphs(H, W, instances=depth + 1, fast=mode == 'fp16', overlap=bool(args.e2e_overlap))
             e2e_loop(0, max(min(Wm, 3), 1), host_outs)
 
             def e2e_region(steps):
@@ -614,6 +615,7 @@ def run_ours(args):
         head = 'fp32' if args.backbone_fp32 else next(m for m in args.e2e_modes.split(',') if m in e2e_ms)
         e2e = {'value': pairs / (e2e_ms[head] / 1e3), 'unit': 'pairs/s', 'ms_per_step': e2e_ms[head] / K,
                'h2d_bytes_per_step': 2 * 3 * H * W * 4, 'd2h_bytes_per_step': n_patches * 5 * 4,
+               'backbone_overlap': bool(args.e2e_overlap),
                'path': 'pinned host images -> H2D -> cuDNN ResNet34 pyramid, both images as one batch, CUDA graph ('
                        + {'fp32': 'fp32', 'tf32': 'TF32 convs, PyTorch default', 'fp16': 'fp16 channels-last'}[head] + ') -> hot path -> D2H matches+scores'}
         if 'fp32' in e2e_ms and head != 'fp32':

@@ -597,6 +597,16 @@ class Patch2PixB200(nn.Module):
         if inst is not None:
             inst['pending'] -= 1
             ticket['inst'] = None
+            if inst['pending'] == 0:
+                # every kernel that reads this instance's pyramids is enqueued on the current stream: a replay on the
+                # side stream (overlap mode) may overwrite them once this point has executed
+                dev = inst['inp'].device
+                old = inst.get('free')
+                ev = _events.get(dev)
+                ev.record(torch.cuda.current_stream(dev))
+                inst['free'] = ev
+                if old is not None:
+                    _events.put(old)
 
     def finish_match(self, ticket, ncn_thres=0.0, ptmax=None, return_all=False):
         """Second half: wait for the count, run filter_coarse's host logic (numpy RNG sampling for
@@ -665,6 +675,22 @@ class Patch2PixB200(nn.Module):
                 # main stream; the instance's input buffer is free once its previous replay has finished
                 cs = g['copy_stream']
                 cs.wait_event(inst['consumed'])
+                if g.get('overlap'):
+                    # the whole backbone runs on the side stream and fills the SMs the main stream's small kernels and
+                    # kernel tails leave idle; its outputs are protected by the ticket protocol (inst['free'])
+                    if inst.get('free') is not None:
+                        cs.wait_event(inst['free'])
+                    with torch.cuda.stream(cs):
+                        inst['inp'][0:1].copy_(im1, non_blocking=True)
+                        inst['inp'][1:2].copy_(im2, non_blocking=True)
+                        inst['graph'].replay()
+                        done = cs.record_event()
+                    main.wait_event(done)
+                    inst['consumed'] = done
+                    feats = inst['out']
+                    f1, f2 = _FeatList(f[:1] for f in feats), _FeatList(f[1:] for f in feats)
+                    f1.graph_inst = f2.graph_inst = inst
+                    return f1, f2
                 with torch.cuda.stream(cs):
                     inst['inp'][0:1].copy_(im1, non_blocking=True)
                     inst['inp'][1:2].copy_(im2, non_blocking=True)
@@ -696,9 +722,12 @@ class Patch2PixB200(nn.Module):
         feats = self._extract16().forward_all(x32.to(dtype=torch.float16, memory_format=torch.channels_last), [], early_feat=True)
         return [x32] + feats[1:]
 
-    def enable_backbone_graphs(self, height, width, instances=2, fast=False):
+    def enable_backbone_graphs(self, height, width, instances=2, fast=False, overlap=False):
         """Capture the (launch-bound) backbone for a fixed image size into CUDA graphs.  fast=True: the fp16 /
-        channels_last backbone (levels 1..4 come out channels-last fp16, consumed directly by the C ABI's *_nhwc16 entries)."""
+        channels_last backbone (levels 1..4 come out channels-last fp16, consumed directly by the C ABI's *_nhwc16 entries).
+        overlap=True: for host images, extract_pair replays the graph on a side stream (after the H2D copy), so the
+        backbone of the next pair overlaps the hot path of the pairs in flight; the pyramids of an instance must then be
+        consumed through submit_coarse / finish_match tickets (which record when the instance may be overwritten)."""
         shape = (1, 3, height, width)
         insts = []
         fwd = self._forward_all_fast if fast else (lambda x: self.extract.forward_all(x, [], early_feat=True))
@@ -718,7 +747,7 @@ class Patch2PixB200(nn.Module):
             for inst in insts:
                 inst['consumed'] = torch.cuda.current_stream().record_event()
             copy_stream = torch.cuda.Stream()
-        self._bb_graphs = {'shape': shape, 'inst': insts, 'copy_stream': copy_stream, 'next': 0}
+        self._bb_graphs = {'shape': shape, 'inst': insts, 'copy_stream': copy_stream, 'next': 0, 'overlap': bool(overlap)}
 
     def predict_train_sequence(self, im1, im2, ksize=2, ptmax=400, return_all=False):
         """train_patch2pix.py:97-118 under eval()/no_grad: forward -> cal_coarse_matches ->

@@ -983,6 +983,30 @@ def test_backbone_graph_tf32_path(cnets, consensus_sd):
             torch.cuda.synchronize()
             rep = _e2e_report(o, g)
             rep['tf32_vs_fp32_backbone_rel_dev'] = dev
+            # overlap mode (the backbone graph of the next pair replays on a side stream while the hot path of the pairs
+            # in flight runs): a pipelined sequence over three different pairs equals the serial results bit for bit
+            pairs = [synthetic_pair_shifted(k, H, W) for k in (6, 7, 8)]
+            pinned = [(a.pin_memory(), b.pin_memory()) for a, b in pairs]
+            net.enable_backbone_graphs(H, W, instances=3, overlap=True)
+            serial = []
+            for k, (a, b) in enumerate(pinned):          # same graph instance per pair as in the pipelined rounds below
+                np.random.seed(10 + k)
+                serial.append(net.match_from_feats(*net.extract_pair(a, b), 2, ptmax=100))
+                torch.cuda.synchronize()
+            tks = []
+            for k, (a, b) in enumerate(pinned):
+                tks.append(net.submit_coarse(*net.extract_pair(a, b), 2, True))
+            for rnd in range(2):                     # second round re-uses the instances (inst['free'] protocol)
+                outs = []
+                for k, tk in enumerate(tks):
+                    np.random.seed(10 + k)
+                    outs.append(net.finish_match(tk, 0.0, 100))
+                    if rnd == 0:                     # refill the instance that was just released
+                        a, b = pinned[k]
+                        tks[k] = net.submit_coarse(*net.extract_pair(a, b), 2, True)
+                torch.cuda.synchronize()
+                for sref, out in zip(serial, outs):
+                    assert torch.equal(sref[0][0], out[0][0]) and torch.equal(sref[1][0], out[1][0]) and torch.equal(sref[2][0], out[2][0])
             _report('backbone_graph_tf32', rep)
             _assert_e2e(rep)
             assert dev < 2e-2, dev
