@@ -61,7 +61,7 @@ def parse():
     ap.add_argument('--nc-impl', type=int, default=None, help='1: tensor-core NeighConsensus (default), 0: fp32 CUDA-core kernels')
     ap.add_argument('--backbone-fp32', action='store_true', help='keep cuDNN TF32 off in the e2e backbone')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--e2e-overlap', type=int, default=1, help='1: backbone graph of the next pair on a side stream (overlaps the hot path)')
+    ap.add_argument('--e2e-overlap', type=int, default=0, help='1: backbone graph of the next pair on a side stream (overlaps the hot path)')
     ap.add_argument('--e2e-modes', default='tf32,fp16,fp32', help='backbone variants timed end to end (the first is the headline)')
     ap.add_argument('--pairs', type=int, default=0,
                     help='strong-scaling mode (BASELINE configs[4]): this many pairs in total, sharded over the ranks; '
