@@ -101,6 +101,8 @@ struct p2p_handle_s {
   float nc_b2 = 0.f;
   NcUmmaWeights ncw;            // tensor-core NC operand images
   void* dbg_nc[4] = {nullptr, nullptr, nullptr, nullptr};   // scratch of the last p2p_neigh_consensus call (tools/nc_debug.py)
+  int opt_unique_impl = 1;      // 1: rank sort over the whole GPU for lists <= 8192 rows; 0: single-block bitonic network
+  int* uniq_rank = nullptr;     // zeroed scratch of the rank-sort path
   int opt_nc_l2_mode = 0;       // NC layer 2 block layout: 0 auto, 1 one haloed block per tile, 2 one block per column tap
   int opt_nc_impl = 1;          // 1: NeighConsensus on the tensor cores (nc_umma.cu); 0: fp32 CUDA-core kernels (shape-capped)
   Regressor reg[2];
@@ -424,6 +426,7 @@ int p2p_destroy(p2p_handle_t h) {
   if (h->nc_w1p) cudaFree(h->nc_w1p);
   if (h->ncw.blob) cudaFree(h->ncw.blob);
   if (h->band_totals) cudaFree(h->band_totals);
+  if (h->uniq_rank) cudaFree(h->uniq_rank);
   for (int i = 0; i < 2; ++i)
     if (h->reg[i].blob) cudaFree(h->reg[i].blob);
   delete h;
@@ -486,6 +489,7 @@ static int* option_slot(p2p_handle_t h, const char* key) {
   if (!strcmp(key, "gemm_pair")) return &h->opt_gemm_pair;
   if (!strcmp(key, "nc_impl")) return &h->opt_nc_impl;
   if (!strcmp(key, "nc_l2_mode")) return &h->opt_nc_l2_mode;
+  if (!strcmp(key, "unique_impl")) return &h->opt_unique_impl;
   return nullptr;
 }
 
@@ -795,9 +799,13 @@ int p2p_unique_rows(p2p_handle_t h, const int64_t* rows, int n, int mutual, cons
     if (rc) return rc;
     scratch = (unsigned char*)h->uniq.take(sb);
   }
+  if (h->uniq_rank == nullptr && h->opt_unique_impl == 1) {     // zeroed once; the kernel leaves it zeroed
+    P2P_CUDA_OK(cudaMalloc(&h->uniq_rank, unique_rank_scratch_bytes()));
+    P2P_CUDA_OK(cudaMemset(h->uniq_rank, 0, unique_rank_scratch_bytes()));
+  }
   ProfScope ps(h, P2P_PROF_PROPOSALS, reinterpret_cast<cudaStream_t>(stream));
   return launch_unique_rows((const long long*)rows, n, mutual, scores, thres, ids_out, count_out, scratch,
-                            reinterpret_cast<cudaStream_t>(stream));
+                            h->opt_unique_impl == 1 ? h->uniq_rank : nullptr, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int p2p_select_anchor(p2p_handle_t h, const int64_t* rows, const float* scores, const int32_t* ids, const int32_t* sel,

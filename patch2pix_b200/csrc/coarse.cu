@@ -949,6 +949,125 @@ __global__ void __launch_bounds__(1024) unique_rows_kernel(const long long* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K8, lists of up to kRankMaxN rows (the proposal lists of every BASELINE size): rank sort over the whole GPU instead
+// of a bitonic network on one SM (62 us for 2400 rows, the other 147 SMs idle, on the critical path of the one host
+// sync).  Block (bi, bj) counts, for its 256 rows i, the rows j of chunk bj that sort before them -- by (key, index)
+// -- and the equal keys before / overall; the partial counts are added into zeroed scratch with atomics.  The last
+// block to finish (grid-wide ticket) turns ranks into the sorted order, detects first occurrences / duplicates,
+// compacts in sorted order exactly like the bitonic path, and re-zeroes the scratch for the next call.
+// scratch: int rank[kRankMaxN], eqb[kRankMaxN], eqt[kRankMaxN]; unsigned ticket, bad.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRankMaxN = 8192;
+
+size_t unique_rank_scratch_bytes() { return (size_t)(3 * kRankMaxN + 8) * sizeof(int); }
+
+__device__ __forceinline__ unsigned long long pack_row_key(const long long* __restrict__ rows, int i, int& bad) {
+  unsigned long long k = 0;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const long long v = rows[(size_t)i * 4 + c];
+    if (v < 0 || v > 65535) bad = 1;
+    k = (k << 16) | (unsigned long long)(v & 0xffff);
+  }
+  return k;
+}
+
+__global__ void __launch_bounds__(256) unique_rank_kernel(const long long* __restrict__ rows, int n, int jchunk, int mutual,
+                                                         const float* __restrict__ scores, float thres,
+                                                         int* __restrict__ ids_out, int* __restrict__ count_out,
+                                                         int* __restrict__ scratch) {
+  extern __shared__ __align__(16) unsigned char smraw_[];
+  unsigned long long* sk = reinterpret_cast<unsigned long long*>(smraw_);
+  int* rank = scratch;
+  int* eqb = scratch + kRankMaxN;
+  int* eqt = scratch + 2 * kRankMaxN;
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch + 3 * kRankMaxN);
+  int* badflag = scratch + 3 * kRankMaxN + 1;
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
+  const int i = blockIdx.x * 256 + tid;
+  const int j0 = blockIdx.y * jchunk, j1 = min(j0 + jchunk, n);
+  int bad = 0;
+  for (int j = j0 + tid; j < j1; j += 256) sk[j - j0] = pack_row_key(rows, j, bad);
+  unsigned long long ki = 0;
+  if (i < n) ki = pack_row_key(rows, i, bad);
+  if (bad && blockIdx.y == 0) atomicOr(badflag, 1);
+  __syncthreads();
+  if (i < n) {
+    int lt = 0, eb = 0, et = 0;
+    for (int j = j0; j < j1; ++j) {
+      const unsigned long long kj = sk[j - j0];        // broadcast read
+      const int e = kj == ki;
+      const int before = e & (j < i);
+      lt += (kj < ki) | before;
+      eb += before;
+      et += e;
+    }
+    if (lt) atomicAdd(rank + i, lt);
+    if (eb) atomicAdd(eqb + i, eb);
+    if (et) atomicAdd(eqt + i, et);
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // ---- last block: sorted order, selection, compaction ----
+  int* order = reinterpret_cast<int*>(smraw_);        // [n]
+  __shared__ int s_warp[8];
+  __shared__ int s_base, s_pass_sel, s_pass_all;
+  if (tid == 0) { s_base = 0; s_pass_sel = 0; s_pass_all = 0; }
+  for (int r = tid; r < n; r += 256) order[__ldcg(rank + r)] = r;
+  __syncthreads();
+  for (int c0 = 0; c0 < n; c0 += 256) {
+    const int p = c0 + tid;
+    int sel = 0, row = 0;
+    if (p < n) {
+      row = order[p];
+      const bool first = __ldcg(eqb + row) == 0;
+      const bool dup = __ldcg(eqt + row) > 1;
+      sel = first && (mutual ? dup : true);
+    }
+    const unsigned int ball = __ballot_sync(0xffffffffu, sel);
+    const int lane = tid & 31, wid = tid >> 5;
+    const int wpre = __popc(ball & ((1u << lane) - 1u));
+    if (lane == 0) s_warp[wid] = __popc(ball);
+    __syncthreads();
+    int woff = 0, tot = 0;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) {
+      const int cnt = s_warp[wv];
+      if (wv < wid) woff += cnt;
+      tot += cnt;
+    }
+    const int base = s_base;
+    if (sel) {
+      ids_out[base + woff + wpre] = row;
+      if (scores != nullptr && scores[row] > thres) atomicAdd(&s_pass_sel, 1);
+    }
+    __syncthreads();
+    if (tid == 0) s_base = base + tot;
+    __syncthreads();
+  }
+  if (scores != nullptr) {
+    int c = 0;
+    for (int r = tid; r < n; r += 256) c += scores[r] > thres;
+    if (c) atomicAdd(&s_pass_all, c);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    count_out[0] = s_base;
+    count_out[1] = __ldcg(badflag);
+    count_out[2] = s_pass_sel;
+    count_out[3] = s_pass_all;
+    *ticket = 0;
+    *badflag = 0;
+  }
+  for (int r = tid; r < n; r += 256) { rank[r] = 0; eqb[r] = 0; eqt[r] = 0; }   // zero again for the next call
+}
+
 size_t unique_rows_scratch_bytes(int n) {
   if (n <= 16384) return 0;
   size_t P = 2;
@@ -957,10 +1076,22 @@ size_t unique_rows_scratch_bytes(int n) {
 }
 
 int launch_unique_rows(const long long* rows, int n, int mutual, const float* scores, float thres, int* ids_out,
-                       int* count_out, unsigned char* gscratch, cudaStream_t st) {
+                       int* count_out, unsigned char* gscratch, int* rank_scratch, cudaStream_t st) {
   P2P_REQUIRE(n >= 0 && n <= (1 << 22), "unique_rows: at most 4 Mi candidate rows");
   if (n == 0) {
     P2P_CUDA_OK(cudaMemsetAsync(count_out, 0, 4 * sizeof(int), st));
+    return 0;
+  }
+  if (n <= kRankMaxN && rank_scratch != nullptr) {
+    const int bx = cdiv(n, 256);
+    int by = cdiv(160, bx);                                   // >= 160 blocks in all
+    if (by > cdiv(n, 32)) by = cdiv(n, 32);
+    const int jchunk = cdiv(n, by);
+    by = cdiv(n, jchunk);
+    const size_t smem = (size_t)jchunk * 8 > (size_t)n * 4 ? (size_t)jchunk * 8 : (size_t)n * 4;
+    P2P_ENSURE_SMEM(unique_rank_kernel, smem);
+    unique_rank_kernel<<<dim3(bx, by), 256, smem, st>>>(rows, n, jchunk, mutual, scores, thres, ids_out, count_out, rank_scratch);
+    P2P_LAUNCH_OK();
     return 0;
   }
   int P = 2;

@@ -29,8 +29,9 @@ int launch_neigh_consensus(const float* x, int hA, int wA, int hB, int wB, const
 int launch_proposals(const float* corr, const uint8_t* code, int hA, int wA, int hB, int wB, int ksize, int upsample,
                      int center, int do_softmax, long long* matches, float* scores, cudaStream_t st);
 size_t unique_rows_scratch_bytes(int n);
+size_t unique_rank_scratch_bytes();     // zero-initialised, handle-owned scratch of the rank-sort path (n <= 8192)
 int launch_unique_rows(const long long* rows, int n, int mutual, const float* scores, float thres, int* ids_out,
-                       int* count_out, unsigned char* gscratch, cudaStream_t st);
+                       int* count_out, unsigned char* gscratch, int* rank_scratch, cudaStream_t st);
 int launch_select_anchor(const long long* rows, const float* scores, const int* ids, const int* sel, int m, int panc,
                          int pshift, long long* matches_out, float* scores_out, long long* anchors_out, cudaStream_t st);
 

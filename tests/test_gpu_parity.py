@@ -926,6 +926,31 @@ def test_unique_rows_large_lists_and_many_outstanding_tickets():
     for r, tk in zip(lists, tickets):
         _, ref_ids, counts = np.unique(r.numpy(), axis=0, return_index=True, return_counts=True)
         assert np.array_equal(tk.wait().cpu().numpy(), ref_ids[counts > 1])
+    # both implementations (rank sort over the whole GPU for lists <= 8192 rows, single-block bitonic network) at the
+    # sizes around their block / chunk boundaries, with triple and double occurrences, and the out-of-range error
+    from patch2pix_b200 import _lib
+    h = _lib.default_handle(torch.device('cuda', 0))
+    try:
+        for n in (1, 2, 3, 255, 256, 257, 1000, 2400, 4097, 8192, 8193, 12000):
+            r = torch.randint(0, 12, (n, 4), generator=g) * 16 + 4
+            if n >= 9:
+                r[n // 3:n // 3 + n // 9] = r[:n // 9]
+                r[2 * (n // 3):2 * (n // 3) + n // 18] = r[:n // 18]
+            _, ref_ids, counts = np.unique(r.numpy(), axis=0, return_index=True, return_counts=True)
+            for impl in (1, 0):
+                h.set_option('unique_impl', impl)
+                for mutual in (True, False):
+                    ids = unique_rows(r.cuda(), mutual, h).cpu().numpy()
+                    assert np.array_equal(ids, ref_ids[counts > 1] if mutual else ref_ids), (n, impl, mutual)
+        h.set_option('unique_impl', 1)
+        bad = torch.full((300, 4), 70000, dtype=torch.int64)
+        with pytest.raises(RuntimeError, match='65535'):
+            unique_rows(bad.cuda(), True, h)
+        ok = torch.randint(0, 12, (300, 4), generator=g) * 16 + 4            # the scratch is clean again after the error
+        _, ref_ids, counts = np.unique(ok.numpy(), axis=0, return_index=True, return_counts=True)
+        assert np.array_equal(unique_rows(ok.cuda(), False, h).cpu().numpy(), ref_ids)
+    finally:
+        h.set_option('unique_impl', 1)
 
 
 def test_select_anchor_kernel_matches_reference_indexing(cnets):
