@@ -82,7 +82,8 @@ P2P_API int p2p_set_regressor_weights(p2p_handle_t h, int which, const p2p_regre
  * of a materialised patch tensor; all four give bit-identical results except 0, which skips one fp16 rounding),
  * "nc_impl" (default 1: NeighConsensus on the tensor cores, nc_umma.cu; 0: fp32 CUDA-core kernels, B grid <= 3072 cells),
  * "nc_l2_mode" (layout of NC layer 2's block of hidden lines: 0 = chosen per shape, 1 = one haloed block per tile,
- * 2 = one block per column tap; bit-identical results), "fc_impl" (default 1: the 512-512 and 512-256 Linear layers run on
+ * 2 = one block per column tap; bit-identical results), "unique_impl" (default 1: rank sort over the whole GPU for lists of
+ * up to 8192 rows; 0: single-block bitonic network; identical results), "fc_impl" (default 1: the 512-512 and 512-256 Linear layers run on
  * the tensor cores, 3-pass; 0: fp32 CUDA-core FC kernel), "gemm_pair" (bitmask of GEMM launches that run
  * on the CTA-pair kernel -- tcgen05.mma.cta_group::2, one M=256 tile over the two SMs of a TPC, bit-identical
  * results: 1 = 1-pass convs, 2 = 3-pass convs, 4 = FC, 8 = correlation, 16 = p2p_test_gemm, 32 = fused-gather conv1;
