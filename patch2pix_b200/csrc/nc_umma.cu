@@ -66,6 +66,7 @@ struct NcParams {
   int TW, R, P, KB, LB;        // KB x LB tiles per A cell
   int copies;                  // 1: one haloed block per tile (pitch TW + 2); 3: one block per column tap (pitch TW)
   int ring, unit_bytes;        // ring of block buffers in shared memory
+  int l2_ctas;                 // CTAs of layer 2 per SM (1 or 2)
 };
 
 // Power-of-two activation scales: max|x| * sx and (hidden bound) * sh land in [2048, 4096).
@@ -399,22 +400,25 @@ __global__ void __launch_bounds__(kL1Threads, 1) nc_l1_umma_kernel(const __grid_
 // start's phase the results are wrong, with 0 they are exact for every shift; tools/nc_debug.py).
 // Per tap and net: a_hi x [w_hi | w_lo] (one N = 32 MMA gives hi*hi and hi*lo) and a_lo x w_hi (N = 16): four
 // independent accumulator chains per tile, summed by the epilogue.
-// 256 threads (warp 1 MMA, 2 TMEM, 3 loader, 4..7 epilogue); ring of block buffers.
+// 256 threads (warp 1 MMA, 2 TMEM, 3 loader, 4..7 epilogue); ring of block buffers; two CTAs per SM when the ring fits
+// twice (each with two of the TMEM accumulator slots): the kernel is bound by the tensor cores' shared-memory operand
+// fetch of its many tiny MMAs, which two interleaved streams keep busier than one (105 -> 92 us).
 // ------------------------------------------------------------------------------------------------
 constexpr int kL2MaxRing = 8;
 constexpr int kL2WTap = 32 * 128;     // weight image per B-tap: rows 0..15 w_hi (9 used), 16..31 w_lo; K16 slice = net
 
-template <int COPIES>
-__global__ void __launch_bounds__(256, 1) nc_l2_umma_kernel(const __grid_constant__ NcParams p,
+template <int COPIES, int CTAS>
+__global__ void __launch_bounds__(256, CTAS) nc_l2_umma_kernel(const __grid_constant__ NcParams p,
                                                             const __grid_constant__ CUtensorMap hmap) {
   constexpr uint32_t IDESC32 = make_idesc_f16(128, 32), IDESC16 = make_idesc_f16(128, 16);
+  constexpr int SLOTS = CTAS == 1 ? kNcSlots : 2;      // two CTAs per SM share the 512 TMEM columns
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* wsm = smem + (size_t)p.ring * p.unit_bytes;      // [9 taps][32 rows][64] weight images, 36 KB
   __shared__ __align__(8) uint64_t full_bar[kL2MaxRing];
   __shared__ __align__(8) uint64_t empty_bar[kL2MaxRing];
-  __shared__ __align__(8) uint64_t tfull_bar[kNcSlots];
-  __shared__ __align__(8) uint64_t tempty_bar[kNcSlots];
+  __shared__ __align__(8) uint64_t tfull_bar[SLOTS];
+  __shared__ __align__(8) uint64_t tempty_bar[SLOTS];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -431,13 +435,13 @@ __global__ void __launch_bounds__(256, 1) nc_l2_umma_kernel(const __grid_constan
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < kNcSlots; ++i) {
+    for (int i = 0; i < SLOTS; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
+  if (warp == 2) tmem_alloc(&tmem_base_smem, SLOTS * 128);
   if (warp == 3 && lane == 0) tma_prefetch_desc(&hmap);
   fence_proxy_async();
   tc_fence_before();
@@ -468,8 +472,8 @@ __global__ void __launch_bounds__(256, 1) nc_l2_umma_kernel(const __grid_constan
     const uint32_t wbase = smem_u32(wsm), sbase = smem_u32(smem);
     const uint32_t tk_stride = (uint32_t)(p.P * 128);
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
-      const int slot = tl % kNcSlots;
-      mbar_wait(&tempty_bar[slot], ((uint32_t)(tl / kNcSlots) & 1u) ^ 1u);
+      const int slot = tl % SLOTS;
+      mbar_wait(&tempty_bar[slot], ((uint32_t)(tl / SLOTS) & 1u) ^ 1u);
       tc_fence_after();
       const uint32_t d_slot = tmem_base + (uint32_t)(slot * 128);   // [0,64) hi products of net 0 | 1, [64,96) lo*hi
 #pragma unroll
@@ -511,8 +515,8 @@ __global__ void __launch_bounds__(256, 1) nc_l2_umma_kernel(const __grid_constan
     const float inv = p.inv_sw2 / sh;
     int tl = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tl) {
-      const int slot = tl % kNcSlots;
-      mbar_wait(&tfull_bar[slot], (uint32_t)(tl / kNcSlots) & 1u);
+      const int slot = tl % SLOTS;
+      mbar_wait(&tfull_bar[slot], (uint32_t)(tl / SLOTS) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(slot * 128);
       float acc[2][9];
@@ -543,7 +547,7 @@ __global__ void __launch_bounds__(256, 1) nc_l2_umma_kernel(const __grid_constan
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, SLOTS * 128);
   }
 }
 
@@ -748,7 +752,7 @@ size_t nc_umma_xp_bytes(int hA, int wA, int hB, int wB) {
 }
 
 // Layer-2 tiling: the (TW, R) with the fewest tiles; mode 0 compares both block layouts (ties: one haloed block).
-static void nc_l2_geometry(int hB, int wB, int mode, NcParams& p) {
+static void nc_l2_geometry(int hB, int wB, int mode, int ctas, NcParams& p) {
   long long best = -1;
   for (int copies = 1; copies <= 3; copies += 2) {
     if ((mode == 1 && copies != 1) || (mode == 2 && copies != 3)) continue;
@@ -767,13 +771,19 @@ static void nc_l2_geometry(int hB, int wB, int mode, NcParams& p) {
   p.LB = cdiv(wB, p.TW);
   const int lines_box = (p.R + 2) * p.P, lines_read = 128 + 2 * p.P + 2;
   p.unit_bytes = (int)align_up((size_t)(lines_box > lines_read ? lines_box : lines_read) * 128, 1024);
-  p.ring = (int)((200 * 1024 - 9 * kL2WTap) / p.unit_bytes);
+  p.l2_ctas = ctas;
+  p.ring = (int)(((ctas == 2 ? 110 : 200) * 1024 - 9 * kL2WTap) / p.unit_bytes);
+  if (p.ring < 1 && ctas == 2) {
+    p.l2_ctas = 1;
+    p.ring = (int)((200 * 1024 - 9 * kL2WTap) / p.unit_bytes);
+  }
   if (p.ring > kL2MaxRing) p.ring = kL2MaxRing;
 }
 
 // x [hA*wA][hB*wB] -> out (NeighConsensus output); rowmax / colmax (optional) receive the maxima MutualMatching needs.
 // xmax: device word holding the float bits of max |x| (launch_absmax or the fused mutual_apply pass).
-// xp: scratch of nc_umma_xp_bytes().  l2_mode: 0 auto, 1 one haloed block per tile, 2 one block per column tap.
+// xp: scratch of nc_umma_xp_bytes().  l2_mode: 0 auto, 1 one haloed block per tile, 2 one block per column tap; + 8: one
+// layer-2 CTA per SM with four TMEM slots instead of two CTAs with two slots each (105 vs 92 us at 640x480).
 int launch_neigh_consensus_umma(const float* x, int hA, int wA, int hB, int wB, const NcUmmaWeights& W, const float* b1p,
                                 float b2, const unsigned int* xmax, uint32_t* xp, __half* hidden, float* partial,
                                 float* out, float* rowmax, unsigned int* colmax, int l2_mode, int num_sms, cudaStream_t st) {
@@ -811,7 +821,7 @@ int launch_neigh_consensus_umma(const float* x, int hA, int wA, int hB, int wB, 
   }
   {
     p.wimg = W.img2;
-    nc_l2_geometry(hB, wB, l2_mode, p);
+    nc_l2_geometry(hB, wB, l2_mode & 3, (l2_mode & 8) ? 1 : 2, p);      // +8 (development): one CTA per SM
     const long long t2 = (long long)p.nA * p.KB * p.LB;
     P2P_REQUIRE(t2 < (1ll << 22), "NeighConsensus: 4D volume too large");
     P2P_REQUIRE(p.ring >= 1, "NeighConsensus layer 2: block buffer does not fit in shared memory");
@@ -823,16 +833,19 @@ int launch_neigh_consensus_umma(const float* x, int hA, int wA, int hB, int wB, 
     int rc = make_tmap_fp16(&hmap, hidden, 4, dims, strides, box);
     if (rc) return rc;
     const int smem = p.ring * p.unit_bytes + 9 * kL2WTap + 1024;
-    const int grid = p.tiles < num_sms ? p.tiles : num_sms;
-    if (p.copies == 1) {
-      auto k = nc_l2_umma_kernel<1>;
-      P2P_ENSURE_SMEM(k, smem);
-      k<<<grid, 256, smem, st>>>(p, hmap);
-    } else {
-      auto k = nc_l2_umma_kernel<3>;
-      P2P_ENSURE_SMEM(k, smem);
-      k<<<grid, 256, smem, st>>>(p, hmap);
-    }
+    const int slots = num_sms * p.l2_ctas;
+    const int grid = p.tiles < slots ? p.tiles : slots;
+#define P2P_NC_L2_LAUNCH(C, T)                    \
+  {                                               \
+    auto k = nc_l2_umma_kernel<C, T>;             \
+    P2P_ENSURE_SMEM(k, smem);                     \
+    k<<<grid, 256, smem, st>>>(p, hmap);          \
+  }
+    if (p.copies == 1 && p.l2_ctas == 1) P2P_NC_L2_LAUNCH(1, 1)
+    else if (p.copies == 1) P2P_NC_L2_LAUNCH(1, 2)
+    else if (p.l2_ctas == 1) P2P_NC_L2_LAUNCH(3, 1)
+    else P2P_NC_L2_LAUNCH(3, 2)
+#undef P2P_NC_L2_LAUNCH
     P2P_LAUNCH_OK();
   }
   if (colmax != nullptr) P2P_CUDA_OK(cudaMemsetAsync(colmax, 0, sizeof(unsigned int) * p.nB, st));
