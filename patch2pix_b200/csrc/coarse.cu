@@ -768,16 +768,19 @@ __device__ __forceinline__ void emit_match(long long* m, float* sc, int row, int
   sc[row] = score;
 }
 
-// best A for every B cell: block = 32 columns x 32 row phases (each thread scans nA/32 rows)
+// best A for every B cell: block = 8 columns x 128 row phases (each thread scans nA/128 rows; nB/8 blocks cover every
+// SM -- with 32 columns per block only 38 blocks existed at 640x480 and the kernel took 20 us)
 __global__ void __launch_bounds__(1024) proposals_dir1_kernel(const float* __restrict__ x, int nA, int nB, int wA, int wB,
                                                              const uint8_t* __restrict__ code, int ks, int upsample,
                                                              int shift, int do_softmax, long long* __restrict__ m,
                                                              float* __restrict__ sc) {
-  constexpr int R = 32;
-  __shared__ float sv[R][33];
-  __shared__ int si[R][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int b = blockIdx.x * 32 + tx;
+  constexpr int C = 8, R = 128;
+  __shared__ float sv[R][C + 1];
+  __shared__ int si[R][C + 1];
+  __shared__ float sbest[C];
+  __shared__ int sbi[C];
+  const int tx = threadIdx.x & (C - 1), ty = threadIdx.x / C;
+  const int b = blockIdx.x * C + tx;
   float best = -INFINITY;
   int bi = 0x7fffffff;
   if (b < nB)
@@ -785,19 +788,35 @@ __global__ void __launch_bounds__(1024) proposals_dir1_kernel(const float* __res
   sv[ty][tx] = best;
   si[ty][tx] = bi;
   __syncthreads();
-  best = sv[0][tx];
-  bi = si[0][tx];
-#pragma unroll
-  for (int r = 1; r < R; ++r) better(best, bi, sv[r][tx], si[r][tx]);
+  if (ty < 4) {                      // 4 x 8 threads: each reduces 32 phases, then thread row 0 the 4 partials
+    best = sv[ty * 32][tx];
+    bi = si[ty * 32][tx];
+#pragma unroll 8
+    for (int r = 1; r < 32; ++r) better(best, bi, sv[ty * 32 + r][tx], si[ty * 32 + r][tx]);
+  }
   __syncthreads();
+  if (ty < 4) {
+    sv[ty][tx] = best;
+    si[ty][tx] = bi;
+  }
+  __syncthreads();
+  if (ty == 0) {
+#pragma unroll
+    for (int r = 1; r < 4; ++r) better(best, bi, sv[r][tx], si[r][tx]);
+    sbest[tx] = best;
+    sbi[tx] = bi;
+  }
+  __syncthreads();
+  best = sbest[tx];
+  bi = sbi[tx];
   float s = 0.f;
   if (b < nB && do_softmax)
     for (int a = ty; a < nA; a += R) s += expf(x[(size_t)a * nB + b] - best);
+  __syncthreads();
   sv[ty][tx] = s;
   __syncthreads();
   if (ty == 0 && b < nB) {
     float tot = 0.f;
-#pragma unroll
     for (int r = 0; r < R; ++r) tot += sv[r][tx];
     const float score = do_softmax ? __fdiv_rn(1.f, tot) : best;
     emit_match(m, sc, b, bi, b, score, wA, wB, nB, code, ks, upsample, shift);
@@ -836,7 +855,7 @@ int launch_proposals(const float* corr, const uint8_t* code, int hA, int wA, int
                      int center, int do_softmax, long long* matches, float* scores, cudaStream_t st) {
   const int nA = hA * wA, nB = hB * wB;
   const int shift = center ? upsample / 2 : 0;
-  proposals_dir1_kernel<<<cdiv(nB, 32), 1024, 0, st>>>(corr, nA, nB, wA, wB, code, ksize, upsample, shift, do_softmax,
+  proposals_dir1_kernel<<<cdiv(nB, 8), 1024, 0, st>>>(corr, nA, nB, wA, wB, code, ksize, upsample, shift, do_softmax,
                                                       matches, scores);
   P2P_LAUNCH_OK();
   proposals_dir2_kernel<<<cdiv(nA, 8), 256, 0, st>>>(corr, nA, nB, wA, wB, code, ksize, upsample, shift, do_softmax,
