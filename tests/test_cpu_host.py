@@ -178,3 +178,37 @@ def test_preprocess_oracle_is_pinned_against_pillow():
     from patch2pix_b200.preprocess import cal_rescale_size
     for w, h, s in ((500, 375, 320), (1024, 768, 1024), (640, 480, 1000), (123, 457, 300)):
         assert cal_rescale_size(s, w, h, 2, 1 / 16) == PO.cal_rescale_size(s, w, h, 2, 1 / 16)
+
+
+def test_shipped_library_is_blackwell_native_sass():
+    """The hot kernels of the built library contain the sm_100a tensor-core / TMA mnemonics (tcgen05.mma = UTC*MMA incl.
+    the cta_group::2 form, cp.async.bulk.tensor = UTMALDG / UTMASTG, cp.async.bulk = UBLKCP, tcgen05.ld = LDTM) and no
+    legacy mma.sync (HMMA); profiles/r02_sass_summary.md is generated by the same scan (tools/sass_summary.py)."""
+    import shutil
+    if shutil.which('cuobjdump') is None:
+        pytest.skip('cuobjdump not on PATH')
+    import __graft_entry__ as ge
+    ge.build()
+    from patch2pix_b200 import _lib
+    sass = subprocess.run(['cuobjdump', '-sass', _lib.LIB_PATH], capture_output=True, text=True, timeout=600).stdout
+    per, cur = {}, None
+    for ln in sass.splitlines():
+        m = re.search(r'Function : (\S+)', ln)
+        if m:
+            cur = m.group(1)
+            per[cur] = ''
+        elif cur is not None:
+            per[cur] += ln + '\n'
+
+    def body(tag):
+        hits = [v for k, v in per.items() if tag in k]
+        assert hits, tag
+        return '\n'.join(hits)
+    assert re.search(r'(?<![A-Z])HMMA', sass) is None          # UTCHMMA is tcgen05; a bare HMMA would be mma.sync
+    l1, l2 = body('nc_l1_umma_kernel'), body('nc_l2_umma_kernel')
+    assert l1.count('UTCHMMA') == 12 and 'UBLKCP' in l1 and 'UTMASTG' in l1 and 'LDTM' in l1
+    assert l2.count('UTCHMMA') >= 36 and 'UTMALDG' in l2 and 'LDTM' in l2
+    c1 = body('umma_conv1_tma_kernel')
+    assert 'UTCHMMA.2CTA' in c1 and 'UTMALDG' in c1
+    gemm = body('umma_gemm_kernel')
+    assert 'UTCHMMA.2CTA' in gemm and 'UTMALDG' in gemm and 'UTCBAR' in gemm
